@@ -1,0 +1,213 @@
+"""ctypes binding of the C-ABI library (include/b200cvt.h, graphitethree_b200/libb200cvt.so).
+
+There is no CPU fallback: importing works anywhere (so that CPU-only checks can verify the
+exported symbols), but every compute call needs a CUDA device and raises B200CVTError
+otherwise. The library must have been built in-tree by __graft_entry__.build().
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200cvt.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200cvt.h")
+
+FLAG_EXHAUSTED, FLAG_TIE, FLAG_POLY_OVERFLOW, FLAG_KMAX = 1, 2, 4, 8
+KMAX = 124
+
+_dp = C.POINTER(C.c_double)
+_up = C.POINTER(C.c_uint32)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+_fp = C.POINTER(C.c_float)
+_qp = C.POINTER(C.c_uint64)
+
+PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_double, C.c_double)
+
+_SIGNATURES = {
+    "b200cvt_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200cvt_destroy": (None, [C.c_void_p]),
+    "b200cvt_last_error": (C.c_char_p, []),
+    "b200cvt_set_mesh": (C.c_int, [C.c_void_p, _dp, C.c_uint32, C.c_uint32, _up, _ip, C.c_uint32, _dp]),
+    "b200cvt_set_seeds": (C.c_int, [C.c_void_p, _dp, C.c_uint32]),
+    "b200cvt_knn": (C.c_int, [C.c_void_p, C.c_uint32, _up, _up, _dp, _bp]),
+    "b200cvt_nearest": (C.c_int, [C.c_void_p, _dp, C.c_uint32, _up]),
+    "b200cvt_centroids": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "b200cvt_funcgrad": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "b200cvt_get_flags": (C.c_int, [C.c_void_p, _bp]),
+    "b200cvt_get_seed_energy": (C.c_int, [C.c_void_p, _dp]),
+    "b200cvt_get_stats": (C.c_int, [C.c_void_p, _qp]),
+    "b200cvt_lloyd": (C.c_int, [C.c_void_p, C.c_uint32, _bp, _dp, C.c_uint32, PROGRESS_CB, C.c_void_p]),
+    "b200cvt_newton": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _bp, _dp, C.c_uint32, PROGRESS_CB, C.c_void_p, _up]),
+    "b200cvt_set_partition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "b200cvt_set_seeds_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "b200cvt_lloyd_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200cvt_commit_sorted_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200cvt_get_seeds_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200cvt_get_seeds": (C.c_int, [C.c_void_p, _dp]),
+    "b200cvt_get_timings": (C.c_int, [C.c_void_p, _fp]),
+    "b200cvt_launch_count": (C.c_uint64, [C.c_void_p]),
+}
+
+_LIB = None
+
+
+class B200CVTError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200cvt error %d: %s" % (code, msg))
+        self.code = code
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads the in-tree CUDA library; fails loudly if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(no CPU fallback exists for this path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200CVTError(rc, lib().b200cvt_last_error().decode("utf-8", "replace"))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Handle:
+    """Thin object wrapper over a b200cvt_handle."""
+
+    def __init__(self, dim=3, volumetric=False, device=-1):
+        self._h = C.c_void_p()
+        self.dim = dim
+        self.S = 0
+        _check(lib().b200cvt_create(device, dim, int(volumetric), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200cvt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mesh(self, vertices, elems, adjacency=None, weights=None):
+        V = _f64(vertices)
+        E = np.ascontiguousarray(elems, dtype=np.uint32)
+        adj = None if adjacency is None else np.ascontiguousarray(adjacency, dtype=np.int32)
+        w = None if weights is None else _f64(weights)
+        _check(lib().b200cvt_set_mesh(self._h, V.ctypes.data_as(_dp), V.shape[0], V.shape[1], E.ctypes.data_as(_up),
+                                      None if adj is None else adj.ctypes.data_as(_ip), E.shape[0],
+                                      None if w is None else w.ctypes.data_as(_dp)))
+
+    def set_seeds(self, x):
+        x = _f64(x)
+        self.S = x.shape[0]
+        _check(lib().b200cvt_set_seeds(self._h, x.ctypes.data_as(_dp), self.S))
+
+    def set_seeds_device(self, ptr, S):
+        self.S = S
+        _check(lib().b200cvt_set_seeds_device(self._h, C.c_void_p(ptr), S))
+
+    def knn(self, k=20):
+        idx = np.empty((self.S, k), dtype=np.uint32)
+        cnt = np.empty(self.S, dtype=np.uint32)
+        sqd = np.empty((self.S, k))
+        fl = np.empty(self.S, dtype=np.uint8)
+        _check(lib().b200cvt_knn(self._h, k, idx.ctypes.data_as(_up), cnt.ctypes.data_as(_up), sqd.ctypes.data_as(_dp),
+                                 fl.ctypes.data_as(_bp)))
+        return idx, cnt, sqd, fl
+
+    def nearest(self, q):
+        q = _f64(q)
+        out = np.empty(q.shape[0], dtype=np.uint32)
+        _check(lib().b200cvt_nearest(self._h, q.ctypes.data_as(_dp), q.shape[0], out.ctypes.data_as(_up)))
+        return out
+
+    def centroids(self, check_SR=False, mg=None, m=None):
+        mg = np.zeros((self.S, self.dim)) if mg is None else mg
+        m = np.zeros(self.S) if m is None else m
+        _check(lib().b200cvt_centroids(self._h, int(check_SR), mg.ctypes.data_as(_dp), m.ctypes.data_as(_dp)))
+        return mg, m
+
+    def funcgrad(self, check_SR=True, g=None, f0=0.0):
+        g = np.zeros((self.S, self.dim)) if g is None else g
+        f = C.c_double(f0)
+        _check(lib().b200cvt_funcgrad(self._h, int(check_SR), C.byref(f), g.ctypes.data_as(_dp)))
+        return f.value, g
+
+    def flags(self):
+        fl = np.empty(self.S, dtype=np.uint8)
+        _check(lib().b200cvt_get_flags(self._h, fl.ctypes.data_as(_bp)))
+        return fl
+
+    def seed_energy(self):
+        fs = np.empty(self.S)
+        _check(lib().b200cvt_get_seed_energy(self._h, fs.ctypes.data_as(_dp)))
+        return fs
+
+    def stats(self):
+        st = np.zeros(8, dtype=np.uint64)
+        _check(lib().b200cvt_get_stats(self._h, st.ctypes.data_as(_qp)))
+        return dict(planes=int(st[0]), cuts=int(st[1]), triangles=int(st[2]), nonempty_pairs=int(st[3]),
+                    redo_seeds=int(st[4]), candidate_pairs=int(st[5]), pair_cap=int(st[6]), grid_cells=int(st[7]))
+
+    def lloyd(self, x, nb_iter, locked=None, callback=None):
+        x = np.array(x, dtype=np.float64, order="C", copy=True)
+        self.S = x.shape[0]
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        _check(lib().b200cvt_lloyd(self._h, nb_iter, None if lk is None else lk.ctypes.data_as(_bp),
+                                   x.ctypes.data_as(_dp), self.S, cb, None))
+        return x
+
+    def newton(self, x, nb_iter, m=7, locked=None, callback=None):
+        x = np.array(x, dtype=np.float64, order="C", copy=True)
+        self.S = x.shape[0]
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        info = np.zeros(4, dtype=np.uint32)
+        _check(lib().b200cvt_newton(self._h, nb_iter, m, None if lk is None else lk.ctypes.data_as(_bp),
+                                    x.ctypes.data_as(_dp), self.S, cb, None, info.ctypes.data_as(_up)))
+        return x, dict(iters=int(info[0]), nfev=int(info[1]), ls_info=int(info[2]))
+
+    def set_partition(self, rank, nranks):
+        _check(lib().b200cvt_set_partition(self._h, rank, nranks))
+
+    def lloyd_step_device(self, slice_ptr=None):
+        _check(lib().b200cvt_lloyd_step_device(self._h, C.c_void_p(slice_ptr) if slice_ptr else None, None))
+
+    def commit_sorted_device(self, ptr):
+        _check(lib().b200cvt_commit_sorted_device(self._h, C.c_void_p(ptr), None))
+
+    def get_seeds_device(self, ptr):
+        _check(lib().b200cvt_get_seeds_device(self._h, C.c_void_p(ptr)))
+
+    def get_seeds(self):
+        x = np.empty((self.S, self.dim))
+        _check(lib().b200cvt_get_seeds(self._h, x.ctypes.data_as(_dp)))
+        return x
+
+    def timings(self):
+        ms = np.zeros(6, dtype=np.float32)
+        _check(lib().b200cvt_get_timings(self._h, ms.ctypes.data_as(_fp)))
+        return dict(sort=float(ms[0]), knn=float(ms[1]), pairs=float(ms[2]), clip=float(ms[3]), update=float(ms[4]), total=float(ms[5]))
+
+    def launch_count(self):
+        return int(lib().b200cvt_launch_count(self._h))

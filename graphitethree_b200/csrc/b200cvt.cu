@@ -1,0 +1,852 @@
+// b200cvt.cu — handle, orchestration and C-ABI of the B200 CVT / restricted Voronoi diagram path.
+// See include/b200cvt.h for the reference interfaces each entry point replaces.
+//
+// Per evaluation (one Lloyd iteration or one Newton function evaluation), on one GPU:
+//   1. seed_keys + radix sort + gather      : Morton-sort the seeds into the uniform grid
+//   2. knn_kernel                           : k nearest seeds of every owned seed (FP64 exact)
+//   3. pairs_kernel                         : candidate (facet, seed) pairs, rows per seed
+//   4. clip_kernel                          : one warp per seed clips + integrates, FP64
+//   5. update / scatter / reductions        : x <- mg/m (Lloyd) or f, g (Newton)
+// Everything stays in device memory between iterations.
+#include "common.cuh"
+#include "knn.cuh"
+#include "clip.cuh"
+#include "lbfgs.cuh"
+#include "../../include/b200cvt.h"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void seed_keys_kernel(const double* x, u32 S, GridParams g, u32* keys, u32* vals) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const double* p = x + (size_t)i * D;
+    keys[i] = morton_encode(g, grid_coord(g, p[0], 0), grid_coord(g, p[1], 1), grid_coord(g, p[2], 2));
+    vals[i] = i;
+}
+
+template <int D>
+__global__ void gather_kernel(const double* x, const u32* keys, const u32* vals, u32 S,
+                              SeedRec<D>* xs, u32* rank_of, uint2* cell_range) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    u32 o = vals[i];
+    SeedRec<D> r;
+#pragma unroll
+    for (int c = 0; c < D; ++c) r.p[c] = x[(size_t)o * D + c];
+    r.orig = (long long)o;
+    xs[i] = r;
+    rank_of[o] = i;
+    u32 k = keys[i];
+    if (i == 0 || keys[i - 1] != k) cell_range[k].x = i;
+    if (i == S - 1 || keys[i + 1] != k) cell_range[k].y = i + 1;
+}
+
+// CentroidalVoronoiTesselation::Lloyd_iterations update rule (geogram/voronoi/CVT.cpp:153-162)
+template <int D>
+__global__ void lloyd_update_kernel(const SeedRec<D>* xs, const double* m, const double* mg, const uint8_t* locked,
+                                    u32 qbegin, u32 qend, double* x_orig, double* slice_out, u32 slice_len) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slice_len) return;
+    u32 s = qbegin + i;
+    if (s >= qend) {
+        if (slice_out) for (int c = 0; c < D; ++c) slice_out[(size_t)i * D + c] = 0.0;
+        return;
+    }
+    u32 o = (u32)xs[s].orig;
+    double p[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) p[c] = xs[s].p[c];
+    double mm = m[s];
+    if (mm > 1e-30 && !(locked && locked[o])) {
+        double sc = 1.0 / mm;
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = sc * mg[(size_t)s * D + c];
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        if (x_orig) x_orig[(size_t)o * D + c] = p[c];
+        if (slice_out) slice_out[(size_t)i * D + c] = p[c];
+    }
+}
+
+template <int D>
+__global__ void commit_sorted_kernel(const SeedRec<D>* xs, const double* all_sorted, u32 S, double* x_orig) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    u32 o = (u32)xs[i].orig;
+#pragma unroll
+    for (int c = 0; c < D; ++c) x_orig[(size_t)o * D + c] = all_sorted[(size_t)i * D + c];
+}
+
+// sorted -> original order
+template <int D>
+__global__ void scatter_results_kernel(const SeedRec<D>* xs, u32 qbegin, u32 qend, const double* out_s, const double* out_v,
+                                       const uint8_t* flags, const u32* pair_cnt, const uint8_t* locked, int zero_locked,
+                                       double* s_orig, double* v_orig, uint8_t* flags_orig, u32* cnt_orig) {
+    u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= qend) return;
+    u32 o = (u32)xs[s].orig;
+    if (s_orig) s_orig[o] = out_s[s];
+    if (v_orig) {
+        bool z = zero_locked && locked && locked[o];   // constrain_points, CVT.cpp:309-321
+#pragma unroll
+        for (int c = 0; c < D; ++c) v_orig[(size_t)o * D + c] = z ? 0.0 : out_v[(size_t)s * D + c];
+    }
+    if (flags_orig) flags_orig[o] = flags[s];
+    if (cnt_orig) cnt_orig[o] = pair_cnt[s];
+}
+
+template <int D>
+__global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u32* nbr_n, const double* sqd, const uint8_t* flags,
+                                  u32 S, u32 k, u32* idx_out, u32* cnt_out, double* sqd_out, uint8_t* flags_out) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    u32 o = (u32)xs[s].orig;
+    u32 n = nbr_n[s];
+    cnt_out[o] = n;
+    for (u32 j = 0; j < k; ++j) {
+        u32 t = nbr[(size_t)s * k + j];
+        idx_out[(size_t)o * k + j] = (j < n && t != B200_NONE) ? (u32)xs[t].orig : B200_NONE;
+        if (sqd_out) sqd_out[(size_t)o * k + j] = sqd[(size_t)s * k + j];
+    }
+    if (flags_out) flags_out[o] = flags[s];
+}
+
+__global__ void fill_u32_kernel(u32* p, size_t n, u32 v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 16;
+        CUDA_CHECK(cudaMalloc((void**)&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct b200cvt_ctx {
+    int device = 0, dim = 3, volumetric = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    u64 launches = 0;
+    // mesh
+    u32 nv = 0, T = 0;
+    bool has_mesh = false, weighted = false;
+    DevBuf<double> tri, triw;
+    DevBuf<u32> facet_guess;
+    double bb_lo[3], bb_hi[3], mesh_measure = 0.0;
+    // seeds
+    u32 S = 0;
+    bool has_seeds = false, grid_valid = false;
+    DevBuf<double> x;                 // [S][D] original order
+    DevBuf<u32> keys, vals, keys2, vals2;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned char> xs;         // SeedRec<D>[S]
+    DevBuf<u32> rank_of;
+    DevBuf<uint2> cell_range;
+    GridParams g;
+    // kNN
+    u32 k = 20, kstride = 20;
+    bool knn_valid = false;
+    DevBuf<u32> nbr, nbr_n;
+    DevBuf<double> sqd;
+    DevBuf<uint8_t> flags;            // sorted order
+    // redo (check_SR) tables
+    DevBuf<u32> redo_a, redo_b, redo_n, nbr_big, nbr_big_n;
+    // pairs
+    u32 pair_cap = 0;
+    DevBuf<u32> pair_cnt, pair_facet, max_cnt;
+    // outputs (sorted order) and original-order staging
+    DevBuf<double> out_s, out_v, s_orig, v_orig;
+    DevBuf<uint8_t> flags_orig, locked;
+    DevBuf<u32> cnt_orig;
+    DevBuf<unsigned long long> stats;
+    bool want_stats = false;
+    bool has_results = false, has_energy = false;
+    // partition
+    u32 rank = 0, nranks = 1;
+    // L-BFGS
+    DevBuf<double> lb_g, lb_q, lb_px, lb_pg, lb_wa, lb_s, lb_y, lb_part;
+    DevBuf<LbfgsScalars> lb_sc;
+    // timing
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    u64 host_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    u32 slice_len() const { return (S + nranks - 1) / nranks; }
+    u32 qbegin() const { return std::min<u64>((u64)rank * slice_len(), S); }
+    u32 qend() const { return std::min<u64>((u64)qbegin() + slice_len(), S); }
+};
+
+#define LAUNCH(h, kernel, grid, block, smem, ...)                                  \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);             \
+        (h)->launches++;                                                            \
+        CUDA_CHECK(cudaGetLastError());                                             \
+    } while (0)
+
+static inline u32 div_up(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+struct ArgError : public std::runtime_error { explicit ArgError(const std::string& s) : std::runtime_error(s) {} };
+struct StateError : public std::runtime_error { explicit StateError(const std::string& s) : std::runtime_error(s) {} };
+struct CapacityError : public std::runtime_error { explicit CapacityError(const std::string& s) : std::runtime_error(s) {} };
+struct CanceledError : public std::runtime_error { explicit CanceledError(const std::string& s) : std::runtime_error(s) {} };
+
+template <class F> static int guarded(F&& f) {
+    try { f(); return B200CVT_OK; }
+    catch (const ArgError& e) { g_last_error = e.what(); return B200CVT_ERR_ARG; }
+    catch (const StateError& e) { g_last_error = e.what(); return B200CVT_ERR_STATE; }
+    catch (const CapacityError& e) { g_last_error = e.what(); return B200CVT_ERR_CAPACITY; }
+    catch (const CanceledError& e) { g_last_error = e.what(); return B200CVT_ERR_CANCELED; }
+    catch (const CudaError& e) { g_last_error = e.what(); return B200CVT_ERR_CUDA; }
+    catch (const std::exception& e) { g_last_error = e.what(); return B200CVT_ERR_CUDA; }
+}
+
+// ---------------------------------------------------------------------------------------
+// grid construction
+// ---------------------------------------------------------------------------------------
+static void choose_grid(b200cvt_ctx* h, const double lo[3], const double hi[3]) {
+    GridParams& g = h->g;
+    double ext[3], maxext = 0.0;
+    for (int a = 0; a < 3; ++a) { ext[a] = hi[a] - lo[a]; maxext = std::max(maxext, ext[a]); }
+    if (!(maxext > 0.0)) maxext = 1.0;
+    double S = (double)std::max<u32>(h->S, 1);
+    double cell;
+    if (h->has_mesh && h->mesh_measure > 0.0) {
+        if (h->volumetric) cell = 2.0 * cbrt(h->mesh_measure / S);   // ~8 seeds per cell
+        else cell = 3.0 * sqrt(h->mesh_measure / S);                 // ~9 seeds per occupied cell, 21-NN radius ~2.6 spacings
+    } else {
+        double vol = 1.0;
+        for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], maxext * 1e-3);
+        cell = cbrt(vol * 8.0 / S);
+    }
+    cell = std::max(cell, maxext * 1e-6);
+    for (;;) {
+        int tb = 0;
+        for (int a = 0; a < 3; ++a) {
+            int res = (int)std::floor(ext[a] / cell) + 1;
+            res = std::max(res, 1);
+            int bits = 0;
+            while ((1 << bits) < res) ++bits;
+            g.res[a] = res; g.bits[a] = bits; tb += bits;
+        }
+        g.total_bits = tb;
+        if (tb <= 26 && g.bits[0] <= 10 && g.bits[1] <= 10 && g.bits[2] <= 10) break;
+        cell *= 1.2599210498948732;
+    }
+    // slight outward margin so that boundary points stay inside without clamping surprises
+    for (int a = 0; a < 3; ++a) g.lo[a] = lo[a] - 1e-9 * maxext;
+    g.h = cell; g.inv_h = 1.0 / cell;
+    g.ncells = 1u << g.total_bits;
+}
+
+template <int D>
+static void build_grid_t(b200cvt_ctx* h) {
+    const u32 S = h->S;
+    if (h->has_mesh) {
+        choose_grid(h, h->bb_lo, h->bb_hi);
+    } else {
+        // bounding box of the seeds (host side: only taken without a mesh)
+        std::vector<double> hx((size_t)S * D);
+        CUDA_CHECK(cudaMemcpyAsync(hx.data(), h->x.p, sizeof(double) * (size_t)S * D, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (u32 i = 0; i < S; ++i)
+            for (int a = 0; a < 3; ++a) { double v = hx[(size_t)i * D + a]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+        choose_grid(h, lo, hi);
+    }
+    h->keys.ensure(S); h->vals.ensure(S); h->keys2.ensure(S); h->vals2.ensure(S);
+    h->xs.ensure((size_t)S * sizeof(SeedRec<D>));
+    h->rank_of.ensure(S);
+    h->cell_range.ensure(h->g.ncells);
+    CUDA_CHECK(cudaMemsetAsync(h->cell_range.p, 0, sizeof(uint2) * (size_t)h->g.ncells, h->stream));
+    LAUNCH(h, seed_keys_kernel<D>, div_up(S, 256), 256, 0, h->x.p, S, h->g, h->keys.p, h->vals.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, (int)S, 0,
+                                    std::max(h->g.total_bits, 1), h->stream);
+    h->cub_tmp.ensure(tmp_bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, (int)S, 0,
+                                               std::max(h->g.total_bits, 1), h->stream));
+    h->launches += 4;
+    LAUNCH(h, gather_kernel<D>, div_up(S, 256), 256, 0, h->x.p, h->keys2.p, h->vals2.p, S,
+           (SeedRec<D>*)h->xs.p, h->rank_of.p, h->cell_range.p);
+    h->flags.ensure(S);
+    CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, S, h->stream));
+    h->grid_valid = true;
+    h->knn_valid = false;
+    h->has_results = false;
+}
+
+static void build_grid(b200cvt_ctx* h) {
+    if (h->dim == 3) build_grid_t<3>(h); else build_grid_t<6>(h);
+}
+
+// ---------------------------------------------------------------------------------------
+// kNN
+// ---------------------------------------------------------------------------------------
+template <int D>
+static void launch_knn(b200cvt_ctx* h, const KnnArgs& a, u32 nq) {
+    if (nq == 0) return;
+    u32 kneed = std::min<u64>((u64)a.kstride + 2, a.S);
+    u32 blocks = std::min<u32>(div_up(nq, KNN_WARPS), 148u * 16u);
+    if (kneed <= 32) LAUNCH(h, (knn_kernel<D, 1>), blocks, KNN_WARPS * 32, 0, a);
+    else if (kneed <= 64) LAUNCH(h, (knn_kernel<D, 2>), blocks, KNN_WARPS * 32, 0, a);
+    else LAUNCH(h, (knn_kernel<D, 4>), blocks, KNN_WARPS * 32, 0, a);
+}
+
+static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds) {
+    const u32 S = h->S;
+    h->k = k; h->kstride = std::max<u32>(k, 1);
+    h->nbr.ensure((size_t)S * h->kstride);
+    h->nbr_n.ensure(S);
+    if (want_sqd) h->sqd.ensure((size_t)S * h->kstride);
+    KnnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+    a.query_list = nullptr; a.ksize = nullptr; a.out_by_slot = 0;
+    a.k = k; a.kstride = h->kstride; a.S = S;
+    a.qbegin = all_seeds ? 0 : h->qbegin(); a.qend = all_seeds ? S : h->qend();
+    a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.sqd = want_sqd ? h->sqd.p : nullptr; a.flags = h->flags.p; a.g = h->g;
+    if (h->dim == 3) launch_knn<3>(h, a, a.qend - a.qbegin); else launch_knn<6>(h, a, a.qend - a.qbegin);
+    h->knn_valid = true;
+}
+
+// ---------------------------------------------------------------------------------------
+// evaluation = pairs + clip (+ neighbourhood enlargement when check_SR)
+// ---------------------------------------------------------------------------------------
+template <int D>
+static void run_pairs_t(b200cvt_ctx* h) {
+    const u32 S = h->S;
+    if (h->pair_cap == 0) {
+        double ratio = (double)h->T / (double)std::max<u32>(S, 1);
+        u32 want = (u32)(ratio * 4.0 + 24.0);
+        u32 cap = 32; while (cap < want) cap <<= 1;
+        h->pair_cap = cap;
+    }
+    h->pair_cnt.ensure(S);
+    h->max_cnt.ensure(1);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        h->pair_facet.ensure((size_t)S * h->pair_cap);
+        CUDA_CHECK(cudaMemsetAsync(h->pair_cnt.p, 0, sizeof(u32) * S, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->max_cnt.p, 0, sizeof(u32), h->stream));
+        PairArgs a;
+        a.tri = h->tri.p; a.fbegin = 0; a.fend = h->T; a.xs = h->xs.p; a.cell_range = h->cell_range.p;
+        a.rank_of = h->rank_of.p; a.facet_guess = h->facet_guess.p; a.qbegin = h->qbegin(); a.qend = h->qend();
+        a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.cap = h->pair_cap; a.max_cnt = h->max_cnt.p; a.g = h->g;
+        LAUNCH(h, pairs_kernel<D>, div_up(h->T, 128), 128, 0, a);
+        u32 mx = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&mx, h->max_cnt.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (mx <= h->pair_cap) return;
+        u32 cap = h->pair_cap; while (cap < mx + mx / 4) cap <<= 1;
+        h->pair_cap = cap;
+    }
+    throw CapacityError("candidate pair rows keep overflowing");
+}
+
+template <int D>
+static void launch_clip(b200cvt_ctx* h, ClipArgs& a) {
+    if (a.nseeds == 0) return;
+    size_t smem = (size_t)CLIP_WARPS * a.kstride * (D + 2) * sizeof(double);
+    u32 blocks = div_up(a.nseeds, CLIP_WARPS);
+    if (h->weighted) {
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(h, (clip_kernel<D, true>), blocks, CLIP_WARPS * 32, smem, a);
+    } else {
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(h, (clip_kernel<D, false>), blocks, CLIP_WARPS * 32, smem, a);
+    }
+}
+
+template <int D>
+static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
+    if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
+    if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
+    if (h->volumetric) throw ArgError("volumetric evaluation is not available in this build");
+    const u32 S = h->S;
+    if (!h->ev[0]) for (int i = 0; i < 6; ++i) { CUDA_CHECK(cudaEventCreate(&h->ev[i])); CUDA_CHECK(cudaEventRecord(h->ev[i], h->stream)); }
+    CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+    if (!h->grid_valid) build_grid(h);
+    CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+    if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, false);
+    CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
+    run_pairs_t<D>(h);
+    CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+
+    h->out_s.ensure(S); h->out_v.ensure((size_t)S * D);
+    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(2);
+    h->stats.ensure(8);
+    CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 2 * sizeof(u32), h->stream));
+    if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    ClipArgs c;
+    memset(&c, 0, sizeof(c));
+    c.xs = h->xs.p; c.nbr = h->nbr.p; c.nbr_n = h->nbr_n.p; c.kstride = h->kstride; c.nbr_by_slot = 0;
+    c.tri = h->tri.p; c.triw = h->weighted ? h->triw.p : nullptr;
+    c.pair_cnt = h->pair_cnt.p; c.pair_facet = h->pair_facet.p; c.cap = h->pair_cap;
+    c.seed_list = nullptr; c.nseeds = h->qend() - h->qbegin(); c.qbegin = h->qbegin();
+    c.mode = mode; c.check_SR = check_SR; c.S = S;
+    c.out_s = h->out_s.p; c.out_v = h->out_v.p; c.flags = h->flags.p;
+    c.redo_list = check_SR ? h->redo_a.p : nullptr; c.redo_n = h->redo_n.p;
+    c.stats = h->want_stats ? h->stats.p : nullptr;
+    launch_clip<D>(h, c);
+
+    if (check_SR) {
+        // enlarge_neighborhood loop (generic_RVD.h:2179-2197), batched over the seeds that need it
+        u32 kbig = 40;
+        u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
+        int cur_slot = 0;
+        for (;;) {
+            u32 nredo = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            if (nredo == 0) break;
+            h->host_stats[4] += nredo;
+            kbig = std::min<u32>(kbig, B200CVT_KMAX);
+            kbig = std::min<u32>(kbig, S - 1);
+            h->nbr_big.ensure((size_t)nredo * kbig);
+            h->nbr_big_n.ensure(nredo);
+            KnnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
+            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
+            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+            launch_knn<D>(h, a, nredo);
+            int nslot = cur_slot ^ 1;
+            CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
+            ClipArgs r = c;
+            r.nbr = h->nbr_big.p; r.nbr_n = h->nbr_big_n.p; r.kstride = kbig; r.nbr_by_slot = 1;
+            r.seed_list = cur_list; r.nseeds = nredo;
+            r.redo_list = nxt_list; r.redo_n = h->redo_n.p + nslot;
+            launch_clip<D>(h, r);
+            std::swap(cur_list, nxt_list);
+            cur_slot = nslot;
+            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) {
+                // the kernel flags KMAX itself when the list cannot grow any more
+                break;
+            }
+            kbig *= 2;
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
+    h->has_results = true;
+    h->has_energy = (mode == 1);
+    h->ev_valid = true;
+}
+
+static void evaluate(b200cvt_ctx* h, int mode, int check_SR) {
+    if (h->dim == 3) evaluate_t<3>(h, mode, check_SR); else evaluate_t<6>(h, mode, check_SR);
+}
+
+static void scatter_results(b200cvt_ctx* h, bool want_s, bool want_v, bool zero_locked) {
+    const u32 S = h->S;
+    h->s_orig.ensure(S); h->v_orig.ensure((size_t)S * h->dim); h->flags_orig.ensure(S); h->cnt_orig.ensure(S);
+    u32 n = h->qend() - h->qbegin();
+    if (n == 0) return;
+    if (h->dim == 3)
+        LAUNCH(h, scatter_results_kernel<3>, div_up(n, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->qbegin(), h->qend(),
+               h->out_s.p, h->out_v.p, h->flags.p, h->pair_cnt.p, h->locked.p, zero_locked ? 1 : 0,
+               want_s ? h->s_orig.p : nullptr, want_v ? h->v_orig.p : nullptr, h->flags_orig.p, h->cnt_orig.p);
+    else
+        LAUNCH(h, scatter_results_kernel<6>, div_up(n, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->qbegin(), h->qend(),
+               h->out_s.p, h->out_v.p, h->flags.p, h->pair_cnt.p, h->locked.p, zero_locked ? 1 : 0,
+               want_s ? h->s_orig.p : nullptr, want_v ? h->v_orig.p : nullptr, h->flags_orig.p, h->cnt_orig.p);
+}
+
+static void upload_locked(b200cvt_ctx* h, const uint8_t* locked, u32 S) {
+    if (locked) {
+        h->locked.ensure(S);
+        CUDA_CHECK(cudaMemcpyAsync(h->locked.p, locked, S, cudaMemcpyHostToDevice, h->stream));
+    } else if (h->locked.p) {
+        CUDA_CHECK(cudaMemsetAsync(h->locked.p, 0, std::min<size_t>(h->locked.cap, S), h->stream));
+    }
+}
+
+static void set_seeds_common(b200cvt_ctx* h, u32 S) {
+    if (S != h->S) { h->pair_cap = 0; }
+    h->S = S;
+    h->has_seeds = true;
+    h->grid_valid = false; h->knn_valid = false; h->has_results = false;
+}
+
+static void lloyd_update(b200cvt_ctx* h, double* d_slice_out) {
+    u32 n = h->slice_len();
+    if (n == 0) return;
+    const uint8_t* lk = h->locked.p;
+    // single rank: write straight into the original-order seed array
+    double* xo = (h->nranks == 1) ? h->x.p : nullptr;
+    if (h->dim == 3)
+        LAUNCH(h, lloyd_update_kernel<3>, div_up(n, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+               h->qbegin(), h->qend(), xo, d_slice_out, n);
+    else
+        LAUNCH(h, lloyd_update_kernel<6>, div_up(n, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+               h->qbegin(), h->qend(), xo, d_slice_out, n);
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200cvt_last_error(void) { return g_last_error.c_str(); }
+
+int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is NULL");
+        if (dim != 3 && dim != 6) throw ArgError("dim must be 3 or 6 (other dimensions stay on the reference implementation)");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+        if (device >= ndev) throw ArgError("device ordinal out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        b200cvt_ctx* h = new b200cvt_ctx;
+        h->device = device; h->dim = dim; h->volumetric = volumetric;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+        *out = h;
+    });
+}
+
+void b200cvt_destroy(b200cvt_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->tri.release(); h->triw.release(); h->facet_guess.release(); h->x.release();
+    h->keys.release(); h->vals.release(); h->keys2.release(); h->vals2.release(); h->cub_tmp.release();
+    h->xs.release(); h->rank_of.release(); h->cell_range.release(); h->nbr.release(); h->nbr_n.release();
+    h->sqd.release(); h->flags.release(); h->redo_a.release(); h->redo_b.release(); h->redo_n.release();
+    h->nbr_big.release(); h->nbr_big_n.release(); h->pair_cnt.release(); h->pair_facet.release(); h->max_cnt.release();
+    h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
+    h->locked.release(); h->cnt_orig.release(); h->stats.release();
+    h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
+    h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint32_t stride, const uint32_t* elems,
+                     const int32_t* adjacency, uint32_t ne, const double* weights) {
+    (void)adjacency;
+    return guarded([&] {
+        if (!h || !vertices || !elems) throw ArgError("null argument");
+        if (stride < (u32)h->dim) throw ArgError("vertex stride smaller than the dimension (geo_assert(dimension_ <= mesh->vertices.dimension()), CVT.cpp:64)");
+        if (h->volumetric) throw ArgError("volumetric meshes are not available in this build");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        const int D = h->dim;
+        const int per = 3;
+        std::vector<double> soup((size_t)ne * 3 * D);
+        std::vector<double> sw;
+        if (weights) sw.resize((size_t)ne * 3);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        double area = 0.0;
+        for (u32 f = 0; f < ne; ++f) {
+            const double* p[3];
+            for (int lv = 0; lv < per; ++lv) {
+                u32 v = elems[(size_t)f * per + lv];
+                if (v >= nv) throw ArgError("element references a vertex out of range");
+                p[lv] = vertices + (size_t)v * stride;
+                for (int c = 0; c < D; ++c) soup[((size_t)f * 3 + lv) * D + c] = p[lv][c];
+                if (weights) sw[(size_t)f * 3 + lv] = weights[v];
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[lv][a]); hi[a] = std::max(hi[a], p[lv][a]); }
+            }
+            double e1[3], e2[3];
+            for (int a = 0; a < 3; ++a) { e1[a] = p[1][a] - p[0][a]; e2[a] = p[2][a] - p[0][a]; }
+            double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            area += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+        }
+        h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = area;
+        for (int a = 0; a < 3; ++a) { h->bb_lo[a] = lo[a]; h->bb_hi[a] = hi[a]; }
+        h->tri.ensure(soup.size());
+        CUDA_CHECK(cudaMemcpyAsync(h->tri.p, soup.data(), sizeof(double) * soup.size(), cudaMemcpyHostToDevice, h->stream));
+        if (weights) {
+            h->triw.ensure(sw.size());
+            CUDA_CHECK(cudaMemcpyAsync(h->triw.p, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice, h->stream));
+        }
+        h->facet_guess.ensure(ne);
+        LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)ne, B200_NONE);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->has_mesh = true; h->grid_valid = false; h->knn_valid = false; h->has_results = false; h->pair_cap = 0;
+    });
+}
+
+int b200cvt_set_seeds(b200cvt_handle h, const double* x, uint32_t S) {
+    return guarded([&] {
+        if (!h || !x) throw ArgError("null argument");
+        if (S == 0) throw ArgError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        h->x.ensure((size_t)S * h->dim);
+        CUDA_CHECK(cudaMemcpyAsync(h->x.p, x, sizeof(double) * (size_t)S * h->dim, cudaMemcpyHostToDevice, h->stream));
+        if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
+        set_seeds_common(h, S);
+        build_grid(h);
+        run_knn_main(h, 20, false, false);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int b200cvt_set_seeds_device(b200cvt_handle h, const double* d_x, uint32_t S) {
+    return guarded([&] {
+        if (!h || !d_x) throw ArgError("null argument");
+        if (S == 0) throw ArgError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        h->x.ensure((size_t)S * h->dim);
+        if (d_x != h->x.p)
+            CUDA_CHECK(cudaMemcpyAsync(h->x.p, d_x, sizeof(double) * (size_t)S * h->dim, cudaMemcpyDeviceToDevice, h->stream));
+        if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
+        set_seeds_common(h, S);
+    });
+}
+
+int b200cvt_knn(b200cvt_handle h, uint32_t k, uint32_t* idx_out, uint32_t* count_out, double* sqdist_out, uint8_t* flags_out) {
+    return guarded([&] {
+        if (!h || !idx_out || !count_out) throw ArgError("null argument");
+        if (!h->has_seeds) throw StateError("no seeds");
+        if (k == 0 || k > B200CVT_KMAX) throw ArgError("k out of range");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        const u32 S = h->S;
+        if (!h->grid_valid) build_grid(h);
+        CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, S, h->stream));
+        run_knn_main(h, k, true, true);
+        DevBuf<u32> d_idx, d_cnt; DevBuf<double> d_sq; DevBuf<uint8_t> d_fl;
+        d_idx.ensure((size_t)S * k); d_cnt.ensure(S); d_sq.ensure((size_t)S * k); d_fl.ensure(S);
+        if (h->dim == 3)
+            LAUNCH(h, knn_export_kernel<3>, div_up(S, 128), 128, 0, (const SeedRec<3>*)h->xs.p, h->nbr.p, h->nbr_n.p, h->sqd.p,
+                   h->flags.p, S, k, d_idx.p, d_cnt.p, d_sq.p, d_fl.p);
+        else
+            LAUNCH(h, knn_export_kernel<6>, div_up(S, 128), 128, 0, (const SeedRec<6>*)h->xs.p, h->nbr.p, h->nbr_n.p, h->sqd.p,
+                   h->flags.p, S, k, d_idx.p, d_cnt.p, d_sq.p, d_fl.p);
+        CUDA_CHECK(cudaMemcpyAsync(idx_out, d_idx.p, sizeof(u32) * (size_t)S * k, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(count_out, d_cnt.p, sizeof(u32) * S, cudaMemcpyDeviceToHost, h->stream));
+        if (sqdist_out) CUDA_CHECK(cudaMemcpyAsync(sqdist_out, d_sq.p, sizeof(double) * (size_t)S * k, cudaMemcpyDeviceToHost, h->stream));
+        if (flags_out) CUDA_CHECK(cudaMemcpyAsync(flags_out, d_fl.p, S, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        d_idx.release(); d_cnt.release(); d_sq.release(); d_fl.release();
+        if (k != 20) h->knn_valid = false;   // the evaluation path uses the default list size (delaunay_nn.cpp:49)
+    });
+}
+
+int b200cvt_nearest(b200cvt_handle h, const double* q, uint32_t nq, uint32_t* out) {
+    return guarded([&] {
+        if (!h || !q || !out) throw ArgError("null argument");
+        if (!h->has_seeds) throw StateError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (!h->grid_valid) build_grid(h);
+        DevBuf<double> dq; DevBuf<u32> dout;
+        dq.ensure((size_t)nq * h->dim); dout.ensure(nq);
+        CUDA_CHECK(cudaMemcpyAsync(dq.p, q, sizeof(double) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, h->stream));
+        if (h->dim == 3) LAUNCH(h, nearest_kernel<3>, div_up(nq, 128), 128, 0, (const SeedRec<3>*)h->xs.p, h->cell_range.p, h->g, dq.p, nq, dout.p);
+        else LAUNCH(h, nearest_kernel<6>, div_up(nq, 128), 128, 0, (const SeedRec<6>*)h->xs.p, h->cell_range.p, h->g, dq.p, nq, dout.p);
+        CUDA_CHECK(cudaMemcpyAsync(out, dout.p, sizeof(u32) * nq, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        dq.release(); dout.release();
+    });
+}
+
+static void accumulate_host(b200cvt_ctx* h, double* s_accum, double* v_accum) {
+    const u32 S = h->S; const int D = h->dim;
+    std::vector<double> hs(S), hv((size_t)S * D);
+    CUDA_CHECK(cudaMemcpyAsync(hs.data(), h->s_orig.p, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(hv.data(), h->v_orig.p, sizeof(double) * (size_t)S * D, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (s_accum) for (u32 i = 0; i < S; ++i) s_accum[i] += hs[i];
+    if (v_accum) for (size_t i = 0; i < (size_t)S * D; ++i) v_accum[i] += hv[i];
+}
+
+int b200cvt_centroids(b200cvt_handle h, int check_SR, double* mg_accum, double* m_accum) {
+    return guarded([&] {
+        if (!h || !mg_accum || !m_accum) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->nranks != 1) throw StateError("host-pointer API needs the whole seed range (nranks == 1)");
+        evaluate(h, 0, check_SR);
+        scatter_results(h, true, true, false);
+        accumulate_host(h, m_accum, mg_accum);
+    });
+}
+
+int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_accum) {
+    return guarded([&] {
+        if (!h || !f_accum || !g_accum) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->nranks != 1) throw StateError("host-pointer API needs the whole seed range (nranks == 1)");
+        evaluate(h, 1, check_SR);
+        scatter_results(h, true, true, false);
+        const u32 S = h->S;
+        std::vector<double> fs(S);
+        accumulate_host(h, nullptr, g_accum);
+        CUDA_CHECK(cudaMemcpy(fs.data(), h->s_orig.p, sizeof(double) * S, cudaMemcpyDeviceToHost));
+        double f = 0.0;
+        for (u32 i = 0; i < S; ++i) f += fs[i];
+        *f_accum += f;
+    });
+}
+
+int b200cvt_get_flags(b200cvt_handle h, uint8_t* flags_out) {
+    return guarded([&] {
+        if (!h || !flags_out) throw ArgError("null argument");
+        if (!h->has_results) throw StateError("no evaluation yet");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaMemcpy(flags_out, h->flags_orig.p, h->S, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out) {
+    return guarded([&] {
+        if (!h || !f_seed_out) throw ArgError("null argument");
+        if (!h->has_results || !h->has_energy) throw StateError("no func/grad evaluation yet");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaMemcpy(f_seed_out, h->s_orig.p, sizeof(double) * h->S, cudaMemcpyDeviceToHost));
+    });
+}
+
+// stats: [0] planes tested [1] planes that cut [2] integration triangles [3] non-empty pairs
+//        [4] seeds re-clipped with an enlarged neighbourhood [5] candidate pairs [6] pair row capacity [7] grid cells
+int b200cvt_get_stats(b200cvt_handle h, uint64_t* out) {
+    return guarded([&] {
+        if (!h || !out) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (h->stats.p && h->want_stats) CUDA_CHECK(cudaMemcpy(st, h->stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4; ++i) out[i] = st[i];
+        out[4] = h->host_stats[4];
+        u64 total = 0;
+        if (h->has_results && h->cnt_orig.p) {
+            std::vector<u32> c(h->S);
+            CUDA_CHECK(cudaMemcpy(c.data(), h->cnt_orig.p, sizeof(u32) * h->S, cudaMemcpyDeviceToHost));
+            for (u32 v : c) total += v;
+        }
+        out[5] = total; out[6] = h->pair_cap; out[7] = h->g.ncells;
+        h->want_stats = true;   // counters are collected from the next evaluation on
+    });
+}
+
+int b200cvt_set_partition(b200cvt_handle h, uint32_t rank, uint32_t nranks) {
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        if (nranks == 0 || rank >= nranks) throw ArgError("bad partition");
+        h->rank = rank; h->nranks = nranks;
+        h->knn_valid = false; h->has_results = false;
+    });
+}
+
+int b200cvt_get_seeds_device(b200cvt_handle h, double* d_x_out) {
+    return guarded([&] {
+        if (!h || !d_x_out) throw ArgError("null argument");
+        if (!h->has_seeds) throw StateError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaMemcpyAsync(d_x_out, h->x.p, sizeof(double) * (size_t)h->S * h->dim, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int b200cvt_get_seeds(b200cvt_handle h, double* x_out) {
+    return guarded([&] {
+        if (!h || !x_out) throw ArgError("null argument");
+        if (!h->has_seeds) throw StateError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaMemcpyAsync(x_out, h->x.p, sizeof(double) * (size_t)h->S * h->dim, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int b200cvt_lloyd_step_device(b200cvt_handle h, double* d_slice_out, void* stream) {
+    (void)stream;
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->nranks > 1 && !d_slice_out) throw ArgError("d_slice_out is required when the seeds are partitioned");
+        evaluate(h, 0, 0);
+        lloyd_update(h, d_slice_out);
+        CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->nranks == 1) { h->grid_valid = false; h->knn_valid = false; }
+    });
+}
+
+int b200cvt_commit_sorted_device(b200cvt_handle h, const double* d_all_sorted, void* stream) {
+    (void)stream;
+    return guarded([&] {
+        if (!h || !d_all_sorted) throw ArgError("null argument");
+        if (!h->grid_valid) throw StateError("no sorted order: run b200cvt_lloyd_step_device first");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->dim == 3) LAUNCH(h, commit_sorted_kernel<3>, div_up(h->S, 256), 256, 0, (const SeedRec<3>*)h->xs.p, d_all_sorted, h->S, h->x.p);
+        else LAUNCH(h, commit_sorted_kernel<6>, div_up(h->S, 256), 256, 0, (const SeedRec<6>*)h->xs.p, d_all_sorted, h->S, h->x.p);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->grid_valid = false; h->knn_valid = false; h->has_results = false;
+    });
+}
+
+int b200cvt_lloyd(b200cvt_handle h, uint32_t nb_iter, const uint8_t* locked, double* x_inout, uint32_t S,
+                  b200cvt_progress_cb cb, void* user) {
+    return guarded([&] {
+        if (!h || !x_inout) throw ArgError("null argument");
+        if (S == 0) throw ArgError("no seeds");
+        if (h->nranks != 1) throw StateError("b200cvt_lloyd drives one GPU; use b200cvt_lloyd_step_device for sharded runs");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        h->x.ensure((size_t)S * h->dim);
+        CUDA_CHECK(cudaMemcpyAsync(h->x.p, x_inout, sizeof(double) * (size_t)S * h->dim, cudaMemcpyHostToDevice, h->stream));
+        if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
+        set_seeds_common(h, S);
+        upload_locked(h, locked, S);
+        h->flags_orig.ensure(S);
+        bool canceled = false;
+        for (u32 it = 0; it < nb_iter; ++it) {
+            evaluate(h, 0, 0);
+            lloyd_update(h, nullptr);
+            CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
+            h->grid_valid = false; h->knn_valid = false;
+            if (it + 1 == nb_iter) scatter_results(h, false, false, false);
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            if (cb && cb(user, it + 1, 0.0, 0.0)) { canceled = true; break; }
+        }
+        CUDA_CHECK(cudaMemcpyAsync(x_inout, h->x.p, sizeof(double) * (size_t)S * h->dim, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->has_results = false;
+        if (canceled) throw CanceledError("canceled by the progress callback");
+    });
+}
+
+int b200cvt_get_timings(b200cvt_handle h, float* ms) {
+    return guarded([&] {
+        if (!h || !ms) throw ArgError("null argument");
+        if (!h->ev_valid) throw StateError("no evaluation yet");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 4; ++i) CUDA_CHECK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+        ms[4] = 0.f; ms[5] = 0.f;
+        if (cudaEventQuery(h->ev[5]) == cudaSuccess) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, h->ev[4], h->ev[5]) == cudaSuccess && t >= 0.f) ms[4] = t;
+            if (cudaEventElapsedTime(&t, h->ev[0], h->ev[5]) == cudaSuccess && t >= 0.f) ms[5] = t;
+        }
+        cudaGetLastError();
+    });
+}
+
+uint64_t b200cvt_launch_count(b200cvt_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+#include "newton.inl"

@@ -1,0 +1,151 @@
+/*
+ * b200cvt.h — C-ABI of the B200-native CVT / restricted-Voronoi-diagram hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. Each entry
+ * point names the reference interface it replaces (paths relative to the GraphiteThree
+ * tree; G/ = geogram/src/lib/geogram/). INTEGRATION.md shows the C++ adapter a geogram
+ * maintainer adds on top (Delaunay factory backend, RVD subclass, CVT subclass).
+ *
+ * Conventions:
+ *  - every function returns 0 on success, non-zero on error; b200cvt_last_error() then
+ *    describes the failure. No exception crosses this boundary.
+ *  - host pointers are borrowed for the duration of the call only.
+ *  - one handle per host thread; a handle is bound to one CUDA device.
+ *  - seeds are S x dim doubles (AoS, like CentroidalVoronoiTesselation::points_,
+ *    G/voronoi/CVT.h:434-456); mesh vertices are nv x stride doubles of which the first
+ *    `dim` are used (Mesh::vertices.point_ptr, G/mesh/mesh.h); elements are uint32
+ *    vertex ids (index_t without GARGANTUA).
+ *  - there is NO CPU fallback: every call fails with B200CVT_ERR_CUDA if no device.
+ */
+#ifndef B200CVT_H
+#define B200CVT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200cvt_ctx* b200cvt_handle;
+
+enum {
+    B200CVT_OK = 0,
+    B200CVT_ERR_ARG = 1,        /* precondition failure (geo_assert in the reference) */
+    B200CVT_ERR_CUDA = 2,       /* CUDA runtime error or no device */
+    B200CVT_ERR_STATE = 3,      /* call order (no mesh / no seeds) */
+    B200CVT_ERR_CAPACITY = 4,   /* internal capacity exceeded after retries */
+    B200CVT_ERR_CANCELED = 5    /* progress callback asked to stop (TaskCanceled) */
+};
+
+/* per-seed status bits (b200cvt_get_flags) */
+enum {
+    B200CVT_FLAG_EXHAUSTED = 1, /* neighbour list used up before the security-radius test passed
+                                   (Lloyd mode, check_SR=0): cell truncated to k neighbours, G/voronoi/generic_RVD.h:2179-2181 */
+    B200CVT_FLAG_TIE = 2,       /* exact distance tie in the kNN list: order among ties is traversal-defined
+                                   in the reference (G/points/kd_tree.h:173-195) */
+    B200CVT_FLAG_POLY_OVERFLOW = 4, /* clipped polygon exceeded the per-lane vertex budget */
+    B200CVT_FLAG_KMAX = 8       /* check_SR=1 but the neighbourhood hit the implementation cap (B200CVT_KMAX) */
+};
+
+#define B200CVT_KMAX 124u       /* largest neighbour list (reference: unbounded, S-1) */
+
+/* progress callback: called after each Lloyd iteration / each L-BFGS iteration
+ * (CentroidalVoronoiTesselation::newiteration, G/voronoi/CVT.cpp:340-345).
+ * Return non-zero to cancel (ProgressTask::next throwing TaskCanceled). */
+typedef int (*b200cvt_progress_cb)(void* user, uint32_t iter, double f, double gnorm);
+
+/* Replaces: CentroidalVoronoiTesselation ctor = Delaunay::create(dim,"NN") +
+ * RestrictedVoronoiDiagram::create (G/voronoi/CVT.cpp:56-75, G/voronoi/RVD.cpp:2540-2600).
+ * device: CUDA ordinal, or -1 for the current device. dim: 3 or 6 (other dimensions stay on
+ * the reference implementation). volumetric: RestrictedVoronoiDiagram::set_volumetric. */
+int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out);
+void b200cvt_destroy(b200cvt_handle h);
+const char* b200cvt_last_error(void);
+
+/* Replaces: the borrowed GEO::Mesh* of RestrictedVoronoiDiagram (G/voronoi/RVD.h:103-147):
+ * vertices (point_ptr / dimension stride), facets.vertex(f,lv) or cells.tet_vertex(t,lv),
+ * facet_corners.adjacent_facet / cells.tet_adjacent (adjacency may be NULL: not needed by
+ * compute_centroids / compute_CVT_func_grad), and the optional "weight" vertex attribute
+ * (G/voronoi/RVD.cpp:143-146). The mesh is copied to the device (replicated on every GPU). */
+int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint32_t stride_doubles,
+                     const uint32_t* elems, const int32_t* adjacency_or_null, uint32_t n_elems,
+                     const double* weights_or_null);
+
+/* Replaces: Delaunay_NearestNeighbors::set_vertices (G/delaunay/delaunay_nn.cpp:97-103):
+ * uploads S seeds, Morton-sorts them into the uniform grid and rebuilds every neighbour list
+ * at its current (sticky) size, default 20 (delaunay_nn.cpp:49, G/delaunay/delaunay.cpp:259-274). */
+int b200cvt_set_seeds(b200cvt_handle h, const double* x, uint32_t S);
+
+/* Replaces: Delaunay::get_neighbors over all seeds (G/delaunay/delaunay.h:477-484) after a
+ * set_vertices with k stored neighbours: idx_out is S x k (original seed indices, ascending
+ * distance, padded with 0xffffffff), count_out is S, sqdist_out (optional) S x k squared
+ * distances bit-equal to Geom::distance2 (G/basic/geometry_nd.h:65-74), flags_out (optional) S. */
+int b200cvt_knn(b200cvt_handle h, uint32_t k, uint32_t* idx_out, uint32_t* count_out,
+                double* sqdist_out, uint8_t* flags_out);
+
+/* Replaces: Delaunay_NearestNeighbors::nearest_vertex (G/delaunay/delaunay_nn.cpp:147-149)
+ * for nq query points (nq x dim doubles). */
+int b200cvt_nearest(b200cvt_handle h, const double* q, uint32_t nq, uint32_t* out);
+
+/* Replaces: RestrictedVoronoiDiagram::compute_centroids(double* mg, double* m)
+ * (G/voronoi/RVD.h:284, impl G/voronoi/RVD.cpp:371-412 / 500-527). mg (S x dim) and m (S)
+ * are ACCUMULATED INTO, as in the reference (caller zeroes, G/voronoi/CVT.cpp:149-150).
+ * check_SR: RestrictedVoronoiDiagram::set_check_SR. Uses the seeds of the last set_seeds. */
+int b200cvt_centroids(b200cvt_handle h, int check_SR, double* mg_accum, double* m_accum);
+
+/* Replaces: RestrictedVoronoiDiagram::compute_CVT_func_grad(double& f, double* g)
+ * (G/voronoi/RVD.h:335, impl G/voronoi/RVD.cpp:726-774 / 878-910). *f and g are accumulated into. */
+int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_accum);
+
+/* Per-seed results of the last centroids/funcgrad call, original seed order:
+ * flags (S), per-seed energy (S; funcgrad only), candidate (facet,seed) pair counts (S). */
+int b200cvt_get_flags(b200cvt_handle h, uint8_t* flags_out);
+int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out);
+int b200cvt_get_stats(b200cvt_handle h, uint64_t* stats_out /* 8 entries, see b200cvt.cu */);
+
+/* Replaces: CentroidalVoronoiTesselation::Lloyd_iterations (G/voronoi/CVT.cpp:133-167).
+ * x_inout: S x dim seeds, updated in place. locked_or_null: S bytes (point_is_locked_).
+ * Seeds stay on the device between iterations. */
+int b200cvt_lloyd(b200cvt_handle h, uint32_t nb_iter, const uint8_t* locked_or_null,
+                  double* x_inout, uint32_t S, b200cvt_progress_cb cb, void* user);
+
+/* Replaces: CentroidalVoronoiTesselation::Newton_iterations (G/voronoi/CVT.cpp:272-338) =
+ * HLBFGS (G/third_party/HLBFGS/HLBFGS.cpp:281-587) with M=m, eps=0, max_iter=nb_iter, each
+ * evaluation = set_vertices + compute_CVT_func_grad(check_SR=true) + constrain_points.
+ * Vectors, dot products and the More-Thuente line search stay on the device.
+ * info_out (optional, 4 entries): iterations, evaluations, line-search info, reserved. */
+int b200cvt_newton(b200cvt_handle h, uint32_t nb_iter, uint32_t m, const uint8_t* locked_or_null,
+                   double* x_inout, uint32_t S, b200cvt_progress_cb cb, void* user, uint32_t* info_out);
+
+/* ---- device-resident / multi-GPU entry points (bench.py, torch.distributed harness) ---- */
+
+/* Shards the seeds by contiguous Morton range: this handle evaluates sorted positions
+ * [rank*ceil(S/nranks), (rank+1)*ceil(S/nranks)) only. Default 0/1. */
+int b200cvt_set_partition(b200cvt_handle h, uint32_t rank, uint32_t nranks);
+
+/* Seeds already in device memory (S x dim doubles); same effect as b200cvt_set_seeds. */
+int b200cvt_set_seeds_device(b200cvt_handle h, const double* d_x, uint32_t S);
+
+/* One Lloyd evaluation on the owned Morton slice, device-resident:
+ * kNN + candidate pairs + clip + x <- mg/m. The updated slice is written, in SORTED order,
+ * to d_slice_out (ceil(S/nranks) x dim doubles, zero padded). stream: cudaStream_t or NULL. */
+int b200cvt_lloyd_step_device(b200cvt_handle h, double* d_slice_out, void* stream);
+
+/* After the allgather of the slices (sorted order, nranks*ceil(S/nranks) x dim doubles):
+ * scatters them back to the original seed order and makes them the current seeds. */
+int b200cvt_commit_sorted_device(b200cvt_handle h, const double* d_all_sorted, void* stream);
+
+/* Copies the current seeds (original order) to device or host memory. */
+int b200cvt_get_seeds_device(b200cvt_handle h, double* d_x_out);
+int b200cvt_get_seeds(b200cvt_handle h, double* x_out);
+
+/* Device timing of the phases of the last evaluation, milliseconds (CUDA events):
+ * [0] sort+grid, [1] kNN, [2] candidate pairs, [3] clip+integrate, [4] update/reduce, [5] total. */
+int b200cvt_get_timings(b200cvt_handle h, float* ms_out /* 6 entries */);
+/* Kernel launches issued by this handle since creation (bench.py gpu_launches). */
+uint64_t b200cvt_launch_count(b200cvt_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
