@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — CVT seed-iterations/s of the B200 path next to the reference CPU RVD.
+
+Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]; rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[1], weak-scaled with N): noise-displaced sphere with ~2 M triangles
+per GPU (frequency round(316*sqrt(N)) geodesic icosphere, 3-octave value noise, amplitude 0.1) and
+200 000 seeds per GPU drawn uniformly by area (fixed RNG seed). One STEP = one CVT job on that input:
+10 Lloyd iterations + Newton_iterations(30, m=7), restarted from the same initial seeds every step.
+metric = seed-iterations/s = S * (Lloyd iterations + Newton function evaluations) / seconds.
+
+  value : seeds resident in HBM when the timed region starts (device-resident loops)
+  e2e   : the same job through the host-pointer C-ABI calls a geogram adapter makes
+          (b200cvt_lloyd / b200cvt_newton with pinned host seeds: H2D + D2H inside the timed region)
+  N > 1 : one process per GPU (torchrun), seeds sharded by Morton range, mesh replicated, one NCCL
+          all-gather per evaluation through torch.distributed (scaling "weak")
+  --impl reference : the unmodified reference (oracle/_ref, built from /root/reference by
+          oracle/Makefile.ref) on the host cores, a bounded sample of the same job per step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLOYD_ITERS, NEWTON_ITERS, NEWTON_M = 10, 30, 7
+SEEDS_PER_GPU = 200000
+BASE_FREQ = 316
+
+
+def workload(n_gpus, small=False):
+    from graphitethree_b200 import shapes
+    if small:
+        V, F = shapes.noise_sphere(60)
+        S = 8000 * n_gpus
+    else:
+        V, F = shapes.noise_sphere(int(round(BASE_FREQ * n_gpus ** 0.5)))
+        S = SEEDS_PER_GPU * n_gpus
+    X = shapes.sample_surface(V, F, S, 1)
+    return V, F, X
+
+
+def workload_name(n_gpus, T, S):
+    return ("noise-displaced sphere %d triangles, %d seeds, %d Lloyd + %d Newton (HLBFGS m=%d) iterations per step"
+            % (T, S, LLOYD_ITERS, NEWTON_ITERS, NEWTON_M))
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 8:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_flops_per_seed_iteration(V, F, states, func_grad):
+    """F = 17 N_planes + 16 N_plane*vertex + 18 N_intersections + C N_triangles, counted on
+    the oracle for the same inputs (C = 52 for Lloyd, 100 for energy+gradient), per seed."""
+    from oracle import port
+    tot = 0.0
+    for x in states:
+        e = port.surface_eval(V, F, x, 1 if func_grad else 0, bool(func_grad))
+        c = e.counters
+        Fl = 17.0 * c["planes"] + 16.0 * c["plane_vertex"] + 18.0 * c["intersections"] + (100.0 if func_grad else 52.0) * c["triangles"]
+        tot += Fl / x.shape[0]
+    return tot / len(states)
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation on the host cores (all threads), bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import ref
+    V, F, X = workload(args.gpus, args.small)
+    S = X.shape[0]
+    line = {"impl": "reference", "metric": "CVT seed-iterations/sec", "unit": "seed-iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.gpus, F.shape[0], S), "l2": "inputs larger than L2"}}
+    sample_lloyd, sample_newton = 2, 2
+    if ref.available():
+        kind = "reference"
+        r = ref.RefCVT(V, F, multithread=True)
+        cores = ref.RefCVT.nb_threads()
+
+        def step():
+            r.set_points(X)
+            c0 = r.counters()["funcgrad"]
+            t = r.lloyd(sample_lloyd) + r.newton(sample_newton, NEWTON_M)
+            return t, sample_lloyd + (r.counters()["funcgrad"] - c0)
+    else:
+        from oracle import port
+        kind, cores = "port", 1
+
+        def step():
+            t0 = time.time()
+            x, _ = port.lloyd(V, F, X, sample_lloyd)
+            x, info = port.newton(V, F, x, sample_newton, NEWTON_M)
+            return time.time() - t0, sample_lloyd + info["nfev"]
+    for _ in range(args.warmup):
+        step()
+    tt, ev = 0.0, 0
+    for _ in range(args.steps):
+        t, e = step()
+        tt += t; ev += e
+    value = S * ev / tt
+    sample = "%d Lloyd + Newton_iterations(%d) per step (%d evaluations/step) on the full %d-seed / %d-triangle input" % (
+        sample_lloyd, sample_newton, ev // max(args.steps, 1), S, F.shape[0])
+    line.update({"value": value, "ms_per_step": 1e3 * tt / max(args.steps, 1),
+                 "cpu_baseline": {"value": value, "unit": "seed-iterations/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "seed-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "graphitethree_b200", "libb200cvt.so")):
+        __graft_entry__.build()
+    from graphitethree_b200 import capi, sharding
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    V, F, X = workload(args.gpus, args.small)
+    S, dim = X.shape
+    stream = torch.cuda.Stream()
+    h = capi.Handle(3, device=local_rank)
+    h.set_stream(stream.cuda_stream)
+    h.set_mesh(V, F)
+    h.set_partition(rank, world)
+    x0_dev = torch.from_numpy(X).cuda()
+    ex = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            ex = sharding.TorchExchange(dim, S, rank, world, torch.device("cuda", local_rank))
+
+            def exchange():
+                with torch.cuda.stream(stream):
+                    return ex()
+        h.set_exchange(ex.slice.data_ptr(), ex.all.data_ptr(), ex.chunk, exchange)
+    x_pin = torch.empty((S, dim), dtype=torch.float64).pin_memory()
+    x_pin_np = x_pin.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    evals = {}
+
+    def step_resident():
+        h.set_seeds_device(x0_dev.data_ptr(), S)
+        h.lloyd_device(LLOYD_ITERS)
+        info = h.newton_device(NEWTON_ITERS, NEWTON_M)
+        evals["n"] = LLOYD_ITERS + info["nfev"]
+        evals["newton"] = info
+
+    def step_e2e():
+        x_pin_np[...] = X
+        h.lloyd(x_pin_np, 0)          # no-op placeholder keeps the call sequence explicit
+        xl = lib_lloyd(x_pin_np)
+        lib_newton(xl)
+
+    # host-pointer calls on the pinned buffer, in place (what a geogram adapter does with points_.data())
+    import ctypes as C
+
+    def lib_lloyd(buf):
+        capi._check(capi.lib().b200cvt_lloyd(h._h, LLOYD_ITERS, None, buf.ctypes.data_as(C.POINTER(C.c_double)), S,
+                                             capi.PROGRESS_CB(), None))
+        return buf
+
+    def lib_newton(buf):
+        info = np.zeros(4, dtype=np.uint32)
+        capi._check(capi.lib().b200cvt_newton(h._h, NEWTON_ITERS, NEWTON_M, None, buf.ctypes.data_as(C.POINTER(C.c_double)), S,
+                                              capi.PROGRESS_CB(), None, info.ctypes.data_as(C.POINTER(C.c_uint32))))
+        evals["n_e2e"] = LLOYD_ITERS + int(info[1])
+
+    def step_e2e_host():
+        x_pin_np[...] = X
+        lib_lloyd(x_pin_np)
+        lib_newton(x_pin_np)
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        step_resident()
+    h.cumulative(reset=True)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+    barrier()
+    wall = time.time() - t0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = h.launch_count() - launches0
+    cum = h.cumulative(reset=True)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    n_eval = evals["n"]
+    value = S * n_eval * args.steps / (ms_total * 1e-3)
+    x_final = h.get_seeds()
+
+    # ---- end-to-end through the host-pointer API (single process per GPU; N = 1 only has host seeds) ----
+    e2e = None
+    if world == 1:
+        for _ in range(2):
+            step_e2e_host()
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            step_e2e_host()
+        barrier()
+        te = time.time() - t0
+        e2e = {"value": S * evals["n_e2e"] * args.steps / te, "unit": "seed-iterations/s",
+               "h2d_bytes_per_step": 2 * S * dim * 8, "d2h_bytes_per_step": 2 * S * dim * 8}
+    else:
+        # sharded runs: seeds enter from pinned host memory on every rank and the result is read back
+        def step_e2e_sharded():
+            x0_dev.copy_(x_pin, non_blocking=True)
+            torch.cuda.synchronize()
+            step_resident()
+            h.get_seeds()
+        x_pin_np[...] = X
+        step_e2e_sharded()
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            step_e2e_sharded()
+        barrier()
+        te = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": S * evals["n"] * args.steps / float(te.item()), "unit": "seed-iterations/s",
+               "h2d_bytes_per_step": S * dim * 8, "d2h_bytes_per_step": S * dim * 8}
+
+    if rank == 0:
+        own = (S + world - 1) // world
+        line = {"metric": "CVT seed-iterations/sec", "value": value, "unit": "seed-iterations/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args.gpus, F.shape[0], S), "seeds": S, "triangles": int(F.shape[0]),
+                           "evaluations_per_step": n_eval, "newton": evals["newton"], "parallelism": "morton-range x%d" % world,
+                           "l2": "inputs larger than L2 (facet table %d MB, re-sorted seeds every evaluation)" % (F.shape[0] * 72 // 2 ** 20),
+                           "wall_s": wall},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        # roofline of the dominant kernel (clip + integrate), SURVEY.md §8(d)
+        try:
+            fp32, fp64, copy = capi.measure_peaks(local_rank)
+            states = [X, x_final]
+            if args.small or not args.no_cpu_baseline:
+                f_lloyd = algorithmic_flops_per_seed_iteration(V, F, states, False)
+                f_newton = algorithmic_flops_per_seed_iteration(V, F, [x_final], True)
+            else:
+                f_lloyd, f_newton = 8500.0, 9500.0
+            n_newton = n_eval - LLOYD_ITERS
+            flops_step = own * (LLOYD_ITERS * f_lloyd + n_newton * f_newton)
+            clip_s = cum["clip"] * 1e-3 / args.steps
+            achieved = flops_step / clip_s / 1e12
+            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32, "unit": "TFLOP/s", "frac": achieved / fp32,
+                                "traffic": None, "kernel": "clip_kernel", "peak_source": "FMA microbenchmark on this GPU (b200cvt_measure_peaks)",
+                                "fp64_peak": fp64, "frac_fp64": achieved / fp64, "kernel_ms_per_launch": 1e3 * clip_s / n_eval,
+                                "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton},
+                                "share_of_step": cum["clip"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"])}
+            knn_bytes = own * (dim * 8 + 20 * 4 + 4) * n_eval          # read seed, write k indices + count
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            knn_gbs = knn_bytes / (cum["knn"] * 1e-3 / args.steps) / 1e9
+            line["roofline_knn"] = {"bound": "hbm", "achieved": knn_gbs, "peak": hbm, "unit": "GB/s", "frac": knn_gbs / hbm,
+                                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "copy_gbs_here": copy, "traffic": None}
+            line["phase_ms_per_evaluation"] = {k: cum[k] / max(cum["evals"], 1) for k in ("sort", "knn", "pairs", "clip")}
+        except Exception as ex_:   # the bench value stands even if the roofline leg fails
+            line["roofline"] = {"error": str(ex_)}
+        # CPU baseline on the host cores, bounded sample of the same workload
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    r = ref.RefCVT(V, F, multithread=True)
+                    r.set_points(X)
+                    t = r.lloyd(1)                       # warm-up (thread partition of the mesh)
+                    r.set_points(X)
+                    c0 = r.counters()["funcgrad"]
+                    t = r.lloyd(3) + r.newton(2, NEWTON_M)
+                    ev = 3 + r.counters()["funcgrad"] - c0
+                    line["cpu_baseline"] = {"value": S * ev / t, "unit": "seed-iterations/s", "cores": ref.RefCVT.nb_threads(),
+                                            "kind": "reference", "sample": "3 Lloyd + Newton_iterations(2) = %d evaluations on the full input, %.1f s" % (ev, t)}
+                    r.close()
+                else:
+                    from oracle import port
+                    t0 = time.time()
+                    port.lloyd(V, F, X, 2)
+                    t = time.time() - t0
+                    line["cpu_baseline"] = {"value": S * 2 / t, "unit": "seed-iterations/s", "cores": 1, "kind": "port",
+                                            "sample": "2 Lloyd iterations on the full input, %.1f s" % t}
+            except Exception as ex_:
+                line["cpu_baseline"] = {"error": str(ex_)}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ _fp = C.POINTER(C.c_float)
 _qp = C.POINTER(C.c_uint64)
 
 PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_double, C.c_double)
+EXCHANGE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 _SIGNATURES = {
     "b200cvt_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -41,11 +42,17 @@ _SIGNATURES = {
     "b200cvt_newton": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _bp, _dp, C.c_uint32, PROGRESS_CB, C.c_void_p, _up]),
     "b200cvt_set_partition": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "b200cvt_set_seeds_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
-    "b200cvt_lloyd_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b200cvt_commit_sorted_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200cvt_exchange_chunk_doubles": (C.c_uint64, [C.c_int, C.c_uint32, C.c_uint32]),
+    "b200cvt_set_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, EXCHANGE_CB, C.c_void_p]),
+    "b200cvt_set_locked": (C.c_int, [C.c_void_p, _bp, C.c_uint32]),
+    "b200cvt_lloyd_device": (C.c_int, [C.c_void_p, C.c_uint32, PROGRESS_CB, C.c_void_p]),
+    "b200cvt_newton_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, PROGRESS_CB, C.c_void_p, _up]),
     "b200cvt_get_seeds_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200cvt_get_seeds": (C.c_int, [C.c_void_p, _dp]),
     "b200cvt_get_timings": (C.c_int, [C.c_void_p, _fp]),
+    "b200cvt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200cvt_get_cumulative": (C.c_int, [C.c_void_p, _dp, _qp, C.c_int]),
+    "b200cvt_measure_peaks": (C.c_int, [C.c_int, _dp, _dp, _dp]),
     "b200cvt_launch_count": (C.c_uint64, [C.c_void_p]),
 }
 
@@ -190,11 +197,24 @@ class Handle:
     def set_partition(self, rank, nranks):
         _check(lib().b200cvt_set_partition(self._h, rank, nranks))
 
-    def lloyd_step_device(self, slice_ptr=None):
-        _check(lib().b200cvt_lloyd_step_device(self._h, C.c_void_p(slice_ptr) if slice_ptr else None, None))
+    def set_exchange(self, slice_ptr, all_ptr, chunk_doubles, callback):
+        """callback() -> 0 must all-gather the slice buffer of every rank into the all buffer."""
+        self._xcb = EXCHANGE_CB(lambda user: int(callback()))   # keep alive
+        _check(lib().b200cvt_set_exchange(self._h, C.c_void_p(slice_ptr), C.c_void_p(all_ptr), chunk_doubles, self._xcb, None))
 
-    def commit_sorted_device(self, ptr):
-        _check(lib().b200cvt_commit_sorted_device(self._h, C.c_void_p(ptr), None))
+    def set_locked(self, locked):
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        _check(lib().b200cvt_set_locked(self._h, None if lk is None else lk.ctypes.data_as(_bp), self.S))
+
+    def lloyd_device(self, nb_iter, callback=None):
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        _check(lib().b200cvt_lloyd_device(self._h, nb_iter, cb, None))
+
+    def newton_device(self, nb_iter, m=7, callback=None):
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        info = np.zeros(4, dtype=np.uint32)
+        _check(lib().b200cvt_newton_device(self._h, nb_iter, m, cb, None, info.ctypes.data_as(_up)))
+        return dict(iters=int(info[0]), nfev=int(info[1]), ls_info=int(info[2]))
 
     def get_seeds_device(self, ptr):
         _check(lib().b200cvt_get_seeds_device(self._h, C.c_void_p(ptr)))
@@ -209,5 +229,21 @@ class Handle:
         _check(lib().b200cvt_get_timings(self._h, ms.ctypes.data_as(_fp)))
         return dict(sort=float(ms[0]), knn=float(ms[1]), pairs=float(ms[2]), clip=float(ms[3]), update=float(ms[4]), total=float(ms[5]))
 
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().b200cvt_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def cumulative(self, reset=False):
+        ms = np.zeros(4)
+        n = C.c_uint64(0)
+        _check(lib().b200cvt_get_cumulative(self._h, ms.ctypes.data_as(_dp), C.byref(n), int(reset)))
+        return dict(sort=ms[0], knn=ms[1], pairs=ms[2], clip=ms[3], evals=int(n.value))
+
     def launch_count(self):
         return int(lib().b200cvt_launch_count(self._h))
+
+
+def measure_peaks(device=-1):
+    """(fp32 TFLOP/s, fp64 TFLOP/s, copy GB/s) measured with FMA / copy microbenchmarks."""
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _check(lib().b200cvt_measure_peaks(device, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value

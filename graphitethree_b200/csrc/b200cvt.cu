@@ -88,6 +88,34 @@ __global__ void commit_sorted_kernel(const SeedRec<D>* xs, const double* all_sor
     for (int c = 0; c < D; ++c) x_orig[(size_t)o * D + c] = all_sorted[(size_t)i * D + c];
 }
 
+// exchange chunk of one rank: [slice_len][D] vector part, then [slice_len] scalar part (zero padded)
+template <int D>
+__global__ void pack_slice_kernel(const double* out_s, const double* out_v, u32 qbegin, u32 qend, u32 slice_len, double* chunk) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slice_len) return;
+    u32 s = qbegin + i;
+    bool in = s < qend;
+#pragma unroll
+    for (int c = 0; c < D; ++c) chunk[(size_t)i * D + c] = in ? out_v[(size_t)s * D + c] : 0.0;
+    chunk[(size_t)slice_len * D + i] = in ? out_s[s] : 0.0;
+}
+
+// gathered chunks (rank-major, sorted order) -> x (original order)           [Lloyd]
+//                                            -> g (original order), f_seed  [Newton]
+template <int D>
+__global__ void unpack_all_kernel(const SeedRec<D>* xs, const double* all, u32 S, u32 slice_len, const uint8_t* locked,
+                                  int zero_locked, double* v_orig, double* s_sorted) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    u32 r = s / slice_len, i = s - r * slice_len;
+    const double* chunk = all + (size_t)r * slice_len * (D + 1);
+    u32 o = (u32)xs[s].orig;
+    bool z = zero_locked && locked && locked[o];
+#pragma unroll
+    for (int c = 0; c < D; ++c) v_orig[(size_t)o * D + c] = z ? 0.0 : chunk[(size_t)i * D + c];
+    if (s_sorted) s_sorted[s] = chunk[(size_t)slice_len * D + i];
+}
+
 // sorted -> original order
 template <int D>
 __global__ void scatter_results_kernel(const SeedRec<D>* xs, u32 qbegin, u32 qend, const double* out_s, const double* out_v,
@@ -181,8 +209,11 @@ struct b200cvt_ctx {
     DevBuf<unsigned long long> stats;
     bool want_stats = false;
     bool has_results = false, has_energy = false;
-    // partition
+    // partition + exchange (all-gather done by the host harness, e.g. torch.distributed over NCCL)
     u32 rank = 0, nranks = 1;
+    double* x_slice = nullptr; double* x_all = nullptr; u64 x_chunk = 0;
+    b200cvt_exchange_cb xcb = nullptr; void* xuser = nullptr;
+    u64 exchanges = 0;
     // L-BFGS
     DevBuf<double> lb_g, lb_q, lb_px, lb_pg, lb_wa, lb_s, lb_y, lb_part;
     DevBuf<LbfgsScalars> lb_sc;
@@ -190,6 +221,9 @@ struct b200cvt_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     u64 host_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool ev_pending = false;          // phase events recorded but not yet accumulated
+    double cum_ms[5] = {0, 0, 0, 0, 0};  // sort+grid, kNN, pairs, clip(+redo), evaluations
+    u64 cum_evals = 0;
 
     u32 slice_len() const { return (S + nranks - 1) / nranks; }
     u32 qbegin() const { return std::min<u64>((u64)rank * slice_len(), S); }
@@ -218,6 +252,19 @@ template <class F> static int guarded(F&& f) {
     catch (const CanceledError& e) { g_last_error = e.what(); return B200CVT_ERR_CANCELED; }
     catch (const CudaError& e) { g_last_error = e.what(); return B200CVT_ERR_CUDA; }
     catch (const std::exception& e) { g_last_error = e.what(); return B200CVT_ERR_CUDA; }
+}
+
+// stream sync that also folds the phase events of the last evaluation into the cumulative timers
+static void sync_stream(b200cvt_ctx* h) {
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (h->ev_pending) {
+        for (int i = 0; i < 4; ++i) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->cum_ms[i] += t;
+        }
+        h->cum_evals++;
+        h->ev_pending = false;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -450,6 +497,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     h->has_results = true;
     h->has_energy = (mode == 1);
     h->ev_valid = true;
+    h->ev_pending = true;
 }
 
 static void evaluate(b200cvt_ctx* h, int mode, int check_SR) {
@@ -487,18 +535,118 @@ static void set_seeds_common(b200cvt_ctx* h, u32 S) {
     h->grid_valid = false; h->knn_valid = false; h->has_results = false;
 }
 
-static void lloyd_update(b200cvt_ctx* h, double* d_slice_out) {
+static void run_exchange(b200cvt_ctx* h) {
+    if (!h->xcb || !h->x_slice || !h->x_all) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
+    if (h->x_chunk < (u64)h->slice_len() * (h->dim + 1)) throw ArgError("exchange buffers too small");
+    sync_stream(h);
+    if (h->xcb(h->xuser) != 0) throw std::runtime_error("exchange callback failed");
+    h->exchanges++;
+}
+
+template <int D>
+static void pack_slice(b200cvt_ctx* h, const double* out_s, const double* out_v) {
     u32 n = h->slice_len();
-    if (n == 0) return;
-    const uint8_t* lk = h->locked.p;
-    // single rank: write straight into the original-order seed array
-    double* xo = (h->nranks == 1) ? h->x.p : nullptr;
-    if (h->dim == 3)
-        LAUNCH(h, lloyd_update_kernel<3>, div_up(n, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
-               h->qbegin(), h->qend(), xo, d_slice_out, n);
-    else
-        LAUNCH(h, lloyd_update_kernel<6>, div_up(n, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
-               h->qbegin(), h->qend(), xo, d_slice_out, n);
+    LAUNCH(h, pack_slice_kernel<D>, div_up(n, 256), 256, 0, out_s, out_v, h->qbegin(), h->qend(), n, h->x_slice);
+}
+
+// Lloyd_iterations (geogram/voronoi/CVT.cpp:133-167) on the device-resident seeds
+static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void* user) {
+    const u32 S = h->S;
+    for (u32 it = 0; it < nb_iter; ++it) {
+        evaluate(h, 0, 0);
+        u32 n = h->slice_len();
+        const uint8_t* lk = h->locked.p;
+        if (h->nranks == 1) {
+            if (h->dim == 3)
+                LAUNCH(h, lloyd_update_kernel<3>, div_up(n, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+                       h->qbegin(), h->qend(), h->x.p, (double*)nullptr, n);
+            else
+                LAUNCH(h, lloyd_update_kernel<6>, div_up(n, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+                       h->qbegin(), h->qend(), h->x.p, (double*)nullptr, n);
+        } else {
+            // updated owned slice, sorted order -> all-gather -> every rank rebuilds the full seed array
+            if (!h->x_slice) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
+            if (h->dim == 3) {
+                LAUNCH(h, lloyd_update_kernel<3>, div_up(n, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+                       h->qbegin(), h->qend(), (double*)nullptr, h->x_slice, n);
+                run_exchange(h);
+                LAUNCH(h, unpack_all_kernel<3>, div_up(S, 256), 256, 0, (const SeedRec<3>*)h->xs.p, h->x_all, S, n,
+                       (const uint8_t*)nullptr, 0, h->x.p, (double*)nullptr);
+            } else {
+                LAUNCH(h, lloyd_update_kernel<6>, div_up(n, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->out_s.p, h->out_v.p, lk,
+                       h->qbegin(), h->qend(), (double*)nullptr, h->x_slice, n);
+                run_exchange(h);
+                LAUNCH(h, unpack_all_kernel<6>, div_up(S, 256), 256, 0, (const SeedRec<6>*)h->xs.p, h->x_all, S, n,
+                       (const uint8_t*)nullptr, 0, h->x.p, (double*)nullptr);
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
+        if (it + 1 == nb_iter) scatter_results(h, false, false, false);
+        h->grid_valid = false; h->knn_valid = false;
+        sync_stream(h);
+        if (cb && cb(user, it + 1, 0.0, 0.0)) throw CanceledError("canceled by the progress callback");
+    }
+    h->has_results = nb_iter > 0;
+    h->has_energy = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// roofline denominators measured on the box: non-tensor FP32 / FP64 FMA rate
+// and a STREAM-style copy
+// ---------------------------------------------------------------------------------------
+template <class T>
+__global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
+    T v0 = (T)threadIdx.x, v1 = v0 + (T)1, v2 = v0 + (T)2, v3 = v0 + (T)3, v4 = v0 + (T)4, v5 = v0 + (T)5, v6 = v0 + (T)6, v7 = v0 + (T)7;
+    for (int i = 0; i < iters; ++i) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    T r = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (r == (T)123456789) out[0] = r;
+}
+__global__ void copy_peak_kernel(const double4* __restrict__ in, double4* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+static void measure_peaks(double* fp32_tflops, double* fp64_tflops, double* copy_gbs) {
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    void* scratch = nullptr;
+    CUDA_CHECK(cudaMalloc(&scratch, 64));
+    const int blocks = 148 * 8, threads = 256, iters = 20000;
+    auto run = [&](auto launch) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            launch();
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        return best;
+    };
+    double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (fp32_tflops) {
+        float ms = run([&] { fma_peak_kernel<float><<<blocks, threads>>>((float*)scratch, iters, 1.0000001f, 1e-7f); });
+        *fp32_tflops = flops / (ms * 1e-3) / 1e12;
+    }
+    if (fp64_tflops) {
+        float ms = run([&] { fma_peak_kernel<double><<<blocks, threads>>>((double*)scratch, iters, 1.0000001, 1e-7); });
+        *fp64_tflops = flops / (ms * 1e-3) / 1e12;
+    }
+    if (copy_gbs) {
+        size_t n = (size_t)1 << 25;   // 2 x 1 GiB
+        double4 *a = nullptr, *b = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&a, n * sizeof(double4)));
+        CUDA_CHECK(cudaMalloc((void**)&b, n * sizeof(double4)));
+        CUDA_CHECK(cudaMemset(a, 0, n * sizeof(double4)));
+        float ms = run([&] { copy_peak_kernel<<<148 * 16, 512>>>(a, b, n); });
+        *copy_gbs = 2.0 * n * sizeof(double4) / (ms * 1e-3) / 1e9;
+        cudaFree(a); cudaFree(b);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    cudaFree(scratch);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -771,30 +919,35 @@ int b200cvt_get_seeds(b200cvt_handle h, double* x_out) {
     });
 }
 
-int b200cvt_lloyd_step_device(b200cvt_handle h, double* d_slice_out, void* stream) {
-    (void)stream;
+uint64_t b200cvt_exchange_chunk_doubles(int dim, uint32_t S, uint32_t nranks) {
+    if (nranks == 0) return 0;
+    u64 sl = ((u64)S + nranks - 1) / nranks;
+    return sl * (u64)(dim + 1);
+}
+
+int b200cvt_set_exchange(b200cvt_handle h, double* d_slice, double* d_all, uint64_t chunk_doubles,
+                         b200cvt_exchange_cb cb, void* user) {
     return guarded([&] {
         if (!h) throw ArgError("null handle");
-        CUDA_CHECK(cudaSetDevice(h->device));
-        if (h->nranks > 1 && !d_slice_out) throw ArgError("d_slice_out is required when the seeds are partitioned");
-        evaluate(h, 0, 0);
-        lloyd_update(h, d_slice_out);
-        CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        if (h->nranks == 1) { h->grid_valid = false; h->knn_valid = false; }
+        h->x_slice = d_slice; h->x_all = d_all; h->x_chunk = chunk_doubles; h->xcb = cb; h->xuser = user;
     });
 }
 
-int b200cvt_commit_sorted_device(b200cvt_handle h, const double* d_all_sorted, void* stream) {
-    (void)stream;
+int b200cvt_set_locked(b200cvt_handle h, const uint8_t* locked, uint32_t S) {
     return guarded([&] {
-        if (!h || !d_all_sorted) throw ArgError("null argument");
-        if (!h->grid_valid) throw StateError("no sorted order: run b200cvt_lloyd_step_device first");
+        if (!h) throw ArgError("null handle");
         CUDA_CHECK(cudaSetDevice(h->device));
-        if (h->dim == 3) LAUNCH(h, commit_sorted_kernel<3>, div_up(h->S, 256), 256, 0, (const SeedRec<3>*)h->xs.p, d_all_sorted, h->S, h->x.p);
-        else LAUNCH(h, commit_sorted_kernel<6>, div_up(h->S, 256), 256, 0, (const SeedRec<6>*)h->xs.p, d_all_sorted, h->S, h->x.p);
+        upload_locked(h, locked, S);
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        h->grid_valid = false; h->knn_valid = false; h->has_results = false;
+    });
+}
+
+int b200cvt_lloyd_device(b200cvt_handle h, uint32_t nb_iter, b200cvt_progress_cb cb, void* user) {
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        if (!h->has_seeds) throw StateError("no seeds");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        lloyd_loop(h, nb_iter, cb, user);
     });
 }
 
@@ -803,28 +956,45 @@ int b200cvt_lloyd(b200cvt_handle h, uint32_t nb_iter, const uint8_t* locked, dou
     return guarded([&] {
         if (!h || !x_inout) throw ArgError("null argument");
         if (S == 0) throw ArgError("no seeds");
-        if (h->nranks != 1) throw StateError("b200cvt_lloyd drives one GPU; use b200cvt_lloyd_step_device for sharded runs");
         CUDA_CHECK(cudaSetDevice(h->device));
         h->x.ensure((size_t)S * h->dim);
         CUDA_CHECK(cudaMemcpyAsync(h->x.p, x_inout, sizeof(double) * (size_t)S * h->dim, cudaMemcpyHostToDevice, h->stream));
         if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
         set_seeds_common(h, S);
         upload_locked(h, locked, S);
-        h->flags_orig.ensure(S);
         bool canceled = false;
-        for (u32 it = 0; it < nb_iter; ++it) {
-            evaluate(h, 0, 0);
-            lloyd_update(h, nullptr);
-            CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
-            h->grid_valid = false; h->knn_valid = false;
-            if (it + 1 == nb_iter) scatter_results(h, false, false, false);
-            CUDA_CHECK(cudaStreamSynchronize(h->stream));
-            if (cb && cb(user, it + 1, 0.0, 0.0)) { canceled = true; break; }
-        }
+        try { lloyd_loop(h, nb_iter, cb, user); } catch (const CanceledError&) { canceled = true; }
         CUDA_CHECK(cudaMemcpyAsync(x_inout, h->x.p, sizeof(double) * (size_t)S * h->dim, cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        h->has_results = false;
         if (canceled) throw CanceledError("canceled by the progress callback");
+    });
+}
+
+int b200cvt_set_stream(b200cvt_handle h, void* stream) {
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+        h->stream = (cudaStream_t)stream;
+    });
+}
+
+int b200cvt_get_cumulative(b200cvt_handle h, double* ms_out, uint64_t* evals_out, int reset) {
+    return guarded([&] {
+        if (!h || !ms_out) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        sync_stream(h);
+        for (int i = 0; i < 4; ++i) ms_out[i] = h->cum_ms[i];
+        if (evals_out) *evals_out = h->cum_evals;
+        if (reset) { for (int i = 0; i < 5; ++i) h->cum_ms[i] = 0.0; h->cum_evals = 0; }
+    });
+}
+
+int b200cvt_measure_peaks(int device, double* fp32_tflops, double* fp64_tflops, double* copy_gbs) {
+    return guarded([&] {
+        if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+        measure_peaks(fp32_tflops, fp64_tflops, copy_gbs);
     });
 }
 

@@ -204,20 +204,19 @@ clip_kernel(ClipArgs a) {
                     }
                 if (lane < npairs) row[lane] = v;
             } else {
+                // rows are powers of two long (cap is), so the tail [npairs, n2) is free: pad it, then
+                // bitonic-sort n2 entries in place (the row stays L1/L2 resident)
                 u32 n2 = 64; while (n2 < npairs) n2 <<= 1;
-                // bitonic sort in place in global memory (L1/L2 resident row), virtual padding with NONE
+                for (u32 t = npairs + lane; t < n2; t += 32) row[t] = B200_NONE;
+                __syncwarp();
                 for (u32 k = 2; k <= n2; k <<= 1)
                     for (u32 j = k >> 1; j > 0; j >>= 1) {
                         for (u32 t = lane; t < n2; t += 32) {
                             u32 p = t ^ j;
                             if (p > t) {
-                                u32 vt = t < npairs ? row[t] : B200_NONE;
-                                u32 vp = p < npairs ? row[p] : B200_NONE;
+                                u32 vt = row[t], vp = row[p];
                                 bool up = ((t & k) == 0);
-                                if ((vt > vp) == up) {
-                                    if (t < npairs) row[t] = vp;
-                                    if (p < npairs) row[p] = vt;
-                                }
+                                if ((vt > vp) == up) { row[t] = vp; row[p] = vt; }
                             }
                         }
                         __syncwarp();

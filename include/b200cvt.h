@@ -126,14 +126,25 @@ int b200cvt_set_partition(b200cvt_handle h, uint32_t rank, uint32_t nranks);
 /* Seeds already in device memory (S x dim doubles); same effect as b200cvt_set_seeds. */
 int b200cvt_set_seeds_device(b200cvt_handle h, const double* d_x, uint32_t S);
 
-/* One Lloyd evaluation on the owned Morton slice, device-resident:
- * kNN + candidate pairs + clip + x <- mg/m. The updated slice is written, in SORTED order,
- * to d_slice_out (ceil(S/nranks) x dim doubles, zero padded). stream: cudaStream_t or NULL. */
-int b200cvt_lloyd_step_device(b200cvt_handle h, double* d_slice_out, void* stream);
+/* The one exchange of the sharded path: an all-gather of each rank's updated
+ * slice. The library packs its slice into d_slice (chunk_doubles doubles: ceil(S/nranks) x dim
+ * values, then ceil(S/nranks) scalars), calls cb(user) — which must all-gather d_slice of every
+ * rank into d_all (rank-major) on the device, e.g. torch.distributed.all_gather_into_tensor
+ * over NCCL, and return 0 once d_all is complete — and unpacks d_all. Both buffers are owned
+ * by the caller (torch tensors in bench.py). */
+typedef int (*b200cvt_exchange_cb)(void* user);
+uint64_t b200cvt_exchange_chunk_doubles(int dim, uint32_t S, uint32_t nranks);
+int b200cvt_set_exchange(b200cvt_handle h, double* d_slice, double* d_all, uint64_t chunk_doubles,
+                         b200cvt_exchange_cb cb, void* user);
 
-/* After the allgather of the slices (sorted order, nranks*ceil(S/nranks) x dim doubles):
- * scatters them back to the original seed order and makes them the current seeds. */
-int b200cvt_commit_sorted_device(b200cvt_handle h, const double* d_all_sorted, void* stream);
+/* point_is_locked_ (G/voronoi/CVT.h:375-410) for the device-resident loops; NULL unlocks all. */
+int b200cvt_set_locked(b200cvt_handle h, const uint8_t* locked_or_null, uint32_t S);
+
+/* Lloyd_iterations / Newton_iterations on the seeds already resident on the device
+ * (b200cvt_set_seeds[_device]); with a partition every rank must call them collectively. */
+int b200cvt_lloyd_device(b200cvt_handle h, uint32_t nb_iter, b200cvt_progress_cb cb, void* user);
+int b200cvt_newton_device(b200cvt_handle h, uint32_t nb_iter, uint32_t m, b200cvt_progress_cb cb, void* user,
+                          uint32_t* info_out);
 
 /* Copies the current seeds (original order) to device or host memory. */
 int b200cvt_get_seeds_device(b200cvt_handle h, double* d_x_out);
@@ -142,6 +153,15 @@ int b200cvt_get_seeds(b200cvt_handle h, double* x_out);
 /* Device timing of the phases of the last evaluation, milliseconds (CUDA events):
  * [0] sort+grid, [1] kNN, [2] candidate pairs, [3] clip+integrate, [4] update/reduce, [5] total. */
 int b200cvt_get_timings(b200cvt_handle h, float* ms_out /* 6 entries */);
+/* Runs the handle's kernels on the caller's stream (cudaStream_t; e.g. torch's current stream),
+ * so that the caller's CUDA events bracket them. */
+int b200cvt_set_stream(b200cvt_handle h, void* stream);
+/* Cumulative device time per phase over all evaluations since the last reset, milliseconds:
+ * [0] sort+grid, [1] kNN, [2] candidate pairs, [3] clip+integrate (incl. enlarged re-clips). */
+int b200cvt_get_cumulative(b200cvt_handle h, double* ms_out /* 4 */, uint64_t* evals_out, int reset);
+/* Roofline denominators measured on the device: non-tensor FP32 and FP64 FMA
+ * throughput (TFLOP/s) and a STREAM-style copy (GB/s, read+write). Any pointer may be NULL. */
+int b200cvt_measure_peaks(int device, double* fp32_tflops, double* fp64_tflops, double* copy_gbs);
 /* Kernel launches issued by this handle since creation (bench.py gpu_launches). */
 uint64_t b200cvt_launch_count(b200cvt_handle h);
 

@@ -52,6 +52,7 @@ def _lib():
         L.ref_rdt.restype = C.c_uint
         L.ref_rdt.argtypes = [C.c_void_p, C.c_int, _up, C.c_uint, _dp, C.c_uint, _up]
         L.ref_nb_threads.restype = C.c_int
+        L.ref_counters.argtypes = [C.c_void_p, _up, _up]
         _LIB = L
     return _LIB
 
@@ -115,6 +116,11 @@ class RefCVT:
 
     def newton(self, n, m=7):
         return _lib().ref_newton(self.h, n, m)
+
+    def counters(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        _lib().ref_counters(self.h, C.byref(a), C.byref(b))
+        return dict(funcgrad=a.value, newiteration=b.value)
 
     def update_delaunay(self):
         return _lib().ref_update_delaunay(self.h)

@@ -55,11 +55,29 @@ namespace {
         }
     }
 
+    /* counts evaluations and iterations; everything else is the stock class */
+    class CountingCVT : public CentroidalVoronoiTesselation {
+    public:
+        CountingCVT(Mesh* mesh, coord_index_t dim, const std::string& delaunay)
+            : CentroidalVoronoiTesselation(mesh, dim, delaunay) {}
+        void funcgrad(index_t n, double* x, double& f, double* g) override {
+            ++nb_funcgrad;
+            CentroidalVoronoiTesselation::funcgrad(n, x, f, g);
+            last_f = f;
+        }
+        void newiteration() override {
+            ++nb_newiteration;
+            CentroidalVoronoiTesselation::newiteration();
+        }
+        unsigned nb_funcgrad = 0, nb_newiteration = 0;
+        double last_f = 0.0;
+    };
+
     struct Ctx {
         Mesh mesh;
         coord_index_t dim = 3;
         bool volumetric = false;
-        CentroidalVoronoiTesselation* cvt = nullptr;
+        CountingCVT* cvt = nullptr;
         ~Ctx() { delete cvt; }
     };
 
@@ -157,7 +175,7 @@ extern "C" {
             Attribute<double> w(c->mesh.vertices.attributes(), "weight");
             for(index_t v = 0; v < nv; ++v) w[v] = weights[v];
         }
-        c->cvt = new CentroidalVoronoiTesselation(&c->mesh, coord_index_t(dim), "NN");
+        c->cvt = new CountingCVT(&c->mesh, coord_index_t(dim), "NN");
         c->cvt->set_volumetric(c->volumetric);
         return c;
     }
@@ -196,6 +214,13 @@ extern "C" {
         double t0 = Stopwatch::now();
         c->cvt->Newton_iterations(nb_iter, m);
         return Stopwatch::now() - t0;
+    }
+
+    /* evaluations (funcgrad calls) and newiteration callbacks since creation */
+    void ref_counters(void* h, unsigned* nb_funcgrad, unsigned* nb_newiteration) {
+        Ctx* c = static_cast<Ctx*>(h);
+        *nb_funcgrad = c->cvt->nb_funcgrad;
+        *nb_newiteration = c->cvt->nb_newiteration;
     }
 
     /* delaunay->set_vertices on the current points; returns seconds */

@@ -1,0 +1,82 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built from
+/root/reference by oracle/Makefile.ref). Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Every array is an output of the reference's own classes (GEO::Delaunay "NN",
+GEO::RestrictedVoronoiDiagram, GEO::CentroidalVoronoiTesselation) driven single-threaded
+through oracle/ref_driver.cpp on procedural inputs from graphitethree_b200/shapes.py.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from graphitethree_b200 import shapes  # noqa: E402
+from oracle.ref import RefCVT  # noqa: E402
+
+
+def case(V, F, X, weights=None, lloyd_iters=5, newton_iters=4):
+    out = dict(V=V, F=F, X=X)
+    if weights is not None:
+        out["weights"] = weights
+
+    # only one CentroidalVoronoiTesselation may exist at a time (instance_, CVT.cpp:53-70), and
+    # neighbour-list sizes are sticky (delaunay.cpp:260-268): one fresh object per quantity
+    def fresh(x):
+        r = RefCVT(V, F, weights=weights, multithread=False)
+        r.set_points(x)
+        return r
+    r = fresh(X); r.update_delaunay()
+    out["knn_idx"], out["knn_cnt"] = r.neighbors(20)
+    out["mg"], out["m"], _ = r.centroids(False)
+    r.close()
+    r = fresh(X); r.update_delaunay()
+    out["f"], out["g"], _ = r.funcgrad(True)
+    out["f"] = np.float64(out["f"])
+    r.close()
+    r = fresh(X); r.update_delaunay()
+    out["f_seed"], _, cnt, pairs = r.polygons(True, want_pairs=True, pairs_cap=64 * X.shape[0])
+    out["pairs_exact"] = pairs
+    r.close()
+    r = fresh(X); r.lloyd(lloyd_iters)
+    out["x_lloyd"] = r.points()
+    out["lloyd_iters"] = np.int32(lloyd_iters)
+    r.close()
+    # Newton from the Lloyd result (the order remesh_smooth uses, mesh_remesh.cpp:96-106)
+    r = fresh(out["x_lloyd"]); r.newton(newton_iters, 7)
+    out["x_newton"] = r.points()
+    out["newton_iters"] = np.int32(newton_iters)
+    r.close()
+    r = fresh(out["x_newton"]); r.update_delaunay()
+    out["f_after_newton"] = np.float64(r.funcgrad(True)[0])
+    r.close()
+    r = fresh(out["x_lloyd"]); r.update_delaunay()
+    tri, vtx = r.rdt(0)
+    out["rdt_tri"] = tri
+    r.close()
+    return out
+
+
+def main():
+    V, F = shapes.icosphere(6)
+    np.savez_compressed(os.path.join(HERE, "sphere_s150.npz"), **case(V, F, shapes.sample_surface(V, F, 150, 3)))
+    V, F = shapes.box_surface(6)
+    w = 1.0 + V[:, 0] + 0.5 * V[:, 1]
+    np.savez_compressed(os.path.join(HERE, "box_weighted_s100.npz"), **case(V, F, shapes.sample_surface(V, F, 100, 5), weights=w))
+    V, F = shapes.icosphere(6)
+    V6 = shapes.lift_anisotropic(V, F, 0.04)
+    np.savez_compressed(os.path.join(HERE, "sphere6d_s120.npz"), **case(V6, F, shapes.sample_surface(V6, F, 120, 7)))
+    V, F = shapes.trefoil_tube(48, 10)
+    np.savez_compressed(os.path.join(HERE, "trefoil_s200.npz"), **case(V, F, shapes.sample_surface(V, F, 200, 9)))
+    for n in sorted(os.listdir(HERE)):
+        if n.endswith(".npz"):
+            print(n, os.path.getsize(os.path.join(HERE, n)))
+
+
+if __name__ == "__main__":
+    main()

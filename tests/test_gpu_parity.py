@@ -1,0 +1,356 @@
+"""GPU parity suite (pytest -m gpu): the CUDA path, called through the C-ABI, against the
+oracle on the same seeded inputs, against the golden vectors generated from the reference,
+and — at BASELINE.json's full sizes — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): kNN lists bit-exact (ties flagged); per-seed mass,
+centroid, energy, gradient within 1e-9 relative.
+
+Seeds whose cell is truncated to the 20 stored neighbours in Lloyd mode (flag EXHAUSTED) are
+"flagged near-degenerate configurations": there the reference's result depends on its facet
+flood-fill order (and on its thread count); parity is asserted on every seed that is neither
+flagged nor a kNN neighbour of a flagged seed, and the flagged fraction is bounded.
+"""
+import glob
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from graphitethree_b200 import capi, shapes, sharding
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    return {k: z[k] for k in z.files}
+
+
+def handle_for(V, F, weights=None):
+    h = capi.Handle(V.shape[1])
+    h.set_mesh(V, F, weights=weights)
+    return h
+
+
+def tainted(V, F, x, weights=None, gpu_flags=None):
+    """Seeds whose Lloyd-mode (k = 20 truncated) result is not defined by geometry alone: the flagged seeds
+    (neighbour list exhausted before the radius test passed) and every seed whose true restricted cell meets
+    a facet that a flagged seed's truncated cell also meets — there the reference's flood-fill may or may not
+    reach the pair (generic_RVD.h:1385-1418), depending on its facet order and thread count."""
+    eL = port.surface_eval(V, F, x, 0, False, weights=weights, want_pairs=True)
+    exh = (eL.flags & port.FLAG_EXHAUSTED).astype(bool)
+    if gpu_flags is not None:
+        # the two flag sets differ only where the candidate pair sets differ (false candidates on the GPU,
+        # flood-fill reach in the reference): both mark truncated cells
+        gexh = (gpu_flags & capi.FLAG_EXHAUSTED).astype(bool)
+        assert (gexh != exh).mean() <= 0.02, "flag sets differ on %.1f%% of the seeds" % (100 * (gexh != exh).mean())
+        exh = exh | gexh
+    t = exh.copy()
+    if exh.any():
+        facets = np.zeros(F.shape[0], dtype=bool)
+        facets[eL.pairs[exh[eL.pairs[:, 0]], 1]] = True
+        eX = port.surface_eval(V, F, x, 0, True, weights=weights, want_pairs=True)
+        t[eX.pairs[facets[eX.pairs[:, 1]], 0]] = True
+        t[eL.pairs[facets[eL.pairs[:, 1]], 0]] = True
+    return t, eL
+
+
+def assert_close(a, b, mask=None, what=""):
+    if mask is not None:
+        a, b = a[mask], b[mask]
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err <= RTOL, "%s: relative error %.3e" % (what, err)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_against_reference_golden(built, path):
+    G = load(path)
+    V, F, X = G["V"], G["F"], G["X"]
+    w = G.get("weights")
+    h = handle_for(V, F, w)
+    h.set_seeds(X)
+    idx, cnt, sqd, fl = h.knn(20)
+    assert np.array_equal(idx, G["knn_idx"]) and np.array_equal(cnt, G["knn_cnt"])
+    # exact cells (check_SR): no exemption at all
+    h.set_seeds(X)
+    f, g = h.funcgrad(True)
+    assert abs(f - float(G["f"])) <= RTOL * abs(float(G["f"]))
+    assert_close(g, G["g"], what="gradient")
+    assert (h.flags() & (capi.FLAG_EXHAUSTED | capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    if w is None:
+        assert_close(h.seed_energy(), G["f_seed"], what="per-seed energy")
+    # Lloyd mode (k = 20 truncation): parity away from truncated cells
+    h.set_seeds(X)
+    mg, m = h.centroids(False)
+    t, e = tainted(V, F, X, w, h.flags())
+    ok = ~t
+    assert ok.sum() > 0
+    assert_close(m, G["m"], ok, "mass")
+    assert_close(mg, G["mg"], ok, "mass*centroid")
+    # random sampling of a coarse mesh: truncated cells are common, yet few seeds actually differ
+    assert (np.abs(m - G["m"]) > RTOL * G["m"].max()).mean() <= 0.10
+    # iterations from the reference's own Lloyd result (regular sampling)
+    x0 = G["x_lloyd"]
+    xg = h.lloyd(x0, 3)
+    xo, fo = port.lloyd(V, F, x0, 3, weights=w)
+    if (fo & port.FLAG_EXHAUSTED).sum() == 0:
+        assert np.abs(xg - xo).max() <= 1e-10
+    xn, info = h.newton(x0, int(G["newton_iters"]), 7)
+    assert info["iters"] == int(G["newton_iters"]) + 1
+    assert np.abs(xn - G["x_newton"]).max() <= 1e-8
+    h.set_seeds(xn)
+    f2, _ = h.funcgrad(True)
+    assert abs(f2 - float(G["f_after_newton"])) <= 1e-8 * abs(float(G["f_after_newton"]))
+    h.close()
+
+
+def test_knn_bit_exact_and_edge_cases(built):
+    rng = np.random.default_rng(5)
+    V, F = shapes.noise_sphere(30)
+    for S in (2, 7, 21, 22, 500, 20000):
+        X = shapes.sample_surface(V, F, S, S)
+        h = capi.Handle(3)
+        h.set_seeds(X)                       # kNN needs no mesh
+        for k in (20, 5, 33, 70):
+            idx, cnt, sqd, fl = h.knn(k)
+            pidx, pcnt, psqd, ptie = port.knn(X, k)
+            assert np.array_equal(cnt, pcnt)
+            clean = (ptie == 0)
+            assert np.array_equal(idx[clean], pidx[clean])
+            assert np.array_equal(sqd[clean], psqd[clean])           # bit-equal FP64 distances
+            assert np.array_equal((fl & capi.FLAG_TIE).astype(bool), ptie.astype(bool))
+        q = rng.standard_normal((50, 3))
+        assert np.array_equal(h.nearest(q), port.nearest(X, q))
+        h.close()
+    # duplicated seeds (delaunay_nn.cpp:123-134) and exact ties on a lattice
+    X = shapes.sample_surface(V, F, 300, 1)
+    X[200] = X[17]
+    X[250] = X[17]
+    h = capi.Handle(3)
+    h.set_seeds(X)
+    idx, cnt, sqd, fl = h.knn(20)
+    pidx, pcnt, psqd, ptie = port.knn(X, 20)
+    assert np.array_equal(cnt, pcnt) and cnt[200] == 0 and cnt[250] == 0
+    assert np.array_equal(sqd, psqd)
+    g = np.stack(np.meshgrid(np.arange(6.), np.arange(6.), np.arange(6.), indexing="ij"), -1).reshape(-1, 3)
+    h.set_seeds(g)
+    idx, cnt, sqd, fl = h.knn(20)
+    pidx, pcnt, psqd, ptie = port.knn(g, 20)
+    assert np.array_equal(sqd, psqd) and (fl & capi.FLAG_TIE).all()   # distances equal, order among ties flagged
+    h.close()
+
+
+@pytest.mark.parametrize("shape,S", [("icosphere", 3000), ("trefoil", 4000), ("cad", 2500), ("noise", 5000)])
+def test_per_seed_parity_random_and_regular_sampling(built, shape, S):
+    if shape == "icosphere":
+        V, F = shapes.icosphere(25)
+    elif shape == "trefoil":
+        V, F = shapes.trefoil_tube(300, 24)
+    elif shape == "cad":
+        V, F = shapes.cad_like(14)
+    else:
+        V, F = shapes.noise_sphere(40)
+    X = shapes.sample_surface(V, F, S, 21)
+    h = handle_for(V, F)
+    for stage, x in (("random", X), ("regular", port.lloyd(V, F, X, 6)[0])):
+        h.set_seeds(x)
+        idx, cnt, _, _ = h.knn(20)
+        h.set_seeds(x)
+        mg, m = h.centroids(False)
+        fl = h.flags()
+        t, e = tainted(V, F, x, None, fl)
+        exh = (fl & capi.FLAG_EXHAUSTED).astype(bool)
+        ok = ~t
+        differ = np.abs(m - e.m) > RTOL * e.m.max()
+        if stage == "regular":
+            assert exh.mean() < 0.02 and ok.mean() > 0.9 and differ.mean() < 0.005
+        else:
+            assert differ.mean() < 0.05          # truncation artefacts of the random initial sampling
+        assert_close(m, e.m, ok, stage + " mass")
+        assert_close(mg, e.mg, ok, stage + " mass*centroid")
+        # exact cells: every seed, no exemption; accumulate-into semantics (CVT.cpp:149-150)
+        h.set_seeds(x)
+        g0 = np.ones((S, 3))
+        f, g = h.funcgrad(True, g=g0.copy(), f0=2.0)
+        e2 = port.surface_eval(V, F, x, 1, True)
+        assert abs((f - 2.0) - e2.f) <= RTOL * e2.f
+        assert_close(g - 1.0, e2.g, what=stage + " gradient")
+        assert_close(h.seed_energy(), e2.f_seed, what=stage + " per-seed energy")
+        assert (h.flags() & (capi.FLAG_EXHAUSTED | capi.FLAG_KMAX | capi.FLAG_POLY_OVERFLOW)).sum() == 0
+        h.set_seeds(x)
+        mgx, mx = h.centroids(True)
+        ex = port.surface_eval(V, F, x, 0, True)
+        assert_close(mx, ex.m, what=stage + " exact mass")
+        assert_close(mgx, ex.mg, what=stage + " exact mass*centroid")
+    h.close()
+
+
+def test_c1_lloyd_trajectory_stepwise(built):
+    """C1: 40 500-triangle icosphere, 10 000 seeds, 30 Lloyd iterations. Each GPU iterate is checked
+    against one oracle step from the previous GPU iterate."""
+    V, F = shapes.icosphere(45)
+    X = shapes.sample_surface(V, F, 10000, 1)
+    h = handle_for(V, F)
+    traj = [X]
+    h.lloyd(X, 30, callback=lambda u, it, f, g: traj.append(h.get_seeds()) or 0)
+    assert len(traj) == 31
+    for k in (0, 1, 4, 12, 29):
+        xo, fo = port.lloyd(V, F, traj[k], 1)
+        t, _ = tainted(V, F, traj[k])
+        ok = ~t
+        assert np.abs(traj[k + 1] - xo)[ok].max() <= 1e-9
+        if k >= 4:
+            assert ok.mean() > 0.97
+    # determinism: same input, same bits
+    x1 = h.lloyd(X, 5)
+    x2 = h.lloyd(X, 5)
+    assert np.array_equal(x1, x2)
+    h.close()
+
+
+def test_newton_trajectory_and_locked_points(built):
+    V, F = shapes.icosphere(20)
+    X0 = shapes.sample_surface(V, F, 2000, 3)
+    X, _ = port.lloyd(V, F, X0, 5)
+    h = handle_for(V, F)
+    hist = []
+    xn, info = h.newton(X, 6, 7, callback=lambda u, it, f, g: hist.append((f, g)) or 0)
+    xo, oi = port.newton(V, F, X, 6, 7)
+    assert info["iters"] == oi["iters"] == 7 and info["nfev"] == oi["nfev"]
+    assert np.abs(np.array([a for a, _ in hist]) - oi["f"]).max() <= 1e-9 * oi["f"][0]
+    assert np.abs(np.array([b for _, b in hist]) - oi["gnorm"]).max() <= 1e-7 * oi["gnorm"][0]
+    assert np.abs(xn - xo).max() <= 1e-8
+    locked = np.zeros(2000, dtype=np.uint8)
+    locked[::3] = 1
+    xl = h.lloyd(X0, 3, locked=locked)
+    assert np.array_equal(xl[::3], X0[::3]) and not np.array_equal(xl[1::3], X0[1::3])
+    xo, _ = port.lloyd(V, F, X0, 1, locked=locked)
+    x1 = h.lloyd(X0, 1, locked=locked)
+    assert np.array_equal(x1[::3], xo[::3])
+    xn, info = h.newton(X, 3, 7, locked=locked)
+    xo, oi = port.newton(V, F, X, 3, 7, locked=locked)
+    assert np.array_equal(xn[::3], X[::3]) and np.abs(xn - xo).max() <= 1e-8
+    # cancel from the progress callback (TaskCanceled)
+    with pytest.raises(capi.B200CVTError) as ei:
+        h.lloyd(X, 10, callback=lambda u, it, f, g: 1 if it == 2 else 0)
+    assert ei.value.code == 5
+    h.close()
+
+
+def test_error_behaviour(built):
+    with pytest.raises(capi.B200CVTError) as ei:
+        capi.Handle(4)
+    assert ei.value.code == 1
+    h = capi.Handle(3)
+    X = np.random.default_rng(0).random((100, 3))
+    h.set_seeds(X)
+    with pytest.raises(capi.B200CVTError) as ei:
+        h.centroids(False)
+    assert ei.value.code == 3                       # no mesh
+    with pytest.raises(capi.B200CVTError) as ei:
+        h.knn(500)
+    assert ei.value.code == 1
+    V, F = shapes.icosphere(4)
+    bad = F.copy()
+    bad[0, 0] = 10 ** 6
+    with pytest.raises(capi.B200CVTError) as ei:
+        h.set_mesh(V, bad)
+    assert ei.value.code == 1
+    h.close()
+
+
+def test_full_size_properties_c2(built):
+    """C2 size: 2 M-triangle noise sphere, 200 k seeds. The oracle is too slow here; check
+    size-independent properties instead."""
+    V, F = shapes.noise_sphere(316)
+    S = 200000
+    X = shapes.sample_surface(V, F, S, 1)
+    P = V[F.astype(np.int64)]
+    area = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+    h = handle_for(V, F)
+    x = h.lloyd(X, 3)
+    h.set_seeds(x)
+    mg, m = h.centroids(True)
+    assert (h.flags() & (capi.FLAG_KMAX | capi.FLAG_POLY_OVERFLOW)).sum() == 0
+    assert abs(m.sum() - area.sum()) <= 1e-10 * area.sum()                       # cells tile the surface
+    assert np.abs(mg.sum(0) - (area[:, None] * P.mean(1)).sum(0)).max() <= 1e-10 * area.sum()
+    h.set_seeds(x)
+    f, g = h.funcgrad(True)
+    assert np.abs(g - 2.0 * (m[:, None] * x - mg)).max() <= 1e-12 * np.abs(g).max() + 1e-15   # g = 2 m (x - c)
+    assert abs(h.seed_energy().sum() - f) <= 1e-12 * f
+    # Lloyd step == mg/m of the truncated cells; fixed seeds of a second call give the same bits
+    h.set_seeds(x)
+    mgl, ml = h.centroids(False)
+    x1 = h.lloyd(x, 1)
+    assert np.array_equal(x1, (1.0 / ml)[:, None] * mgl)
+    # kNN: ascending exact distances, and brute force on a sample
+    h.set_seeds(x)
+    idx, cnt, sqd, fl = h.knn(20)
+    assert (cnt == 20).all() and (np.diff(sqd, axis=1) >= 0).all()
+    for i in np.random.default_rng(0).integers(0, S, 64):
+        d = x - x[i]
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        o = np.lexsort((np.arange(S), d2))[1:21]
+        assert np.array_equal(np.sort(d2[o]), sqd[i])
+        if not (fl[i] & capi.FLAG_TIE):
+            assert np.array_equal(o.astype(np.uint32), idx[i])
+    # energy decreases along Lloyd
+    h.set_seeds(X)
+    f0, _ = h.funcgrad(True)
+    assert f < f0
+    h.close()
+
+
+def test_sharded_lloyd_two_partitions_one_gpu(built):
+    """The partition + pack/exchange/unpack path of the C library, with two handles on one GPU
+    standing in for two ranks (threads + a barrier play the all-gather)."""
+    import torch
+    V, F = shapes.icosphere(20)
+    X = shapes.sample_surface(V, F, 3001, 5)
+    S, dim, world = X.shape[0], 3, 2
+    chunk = sharding.chunk_doubles(dim, S, world)
+    shared = torch.zeros(chunk * world, dtype=torch.float64, device="cuda")
+    barrier = threading.Barrier(world)
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            h = handle_for(V, F)
+            h.set_partition(rank, world)
+            sl = torch.zeros(chunk, dtype=torch.float64, device="cuda")
+            al = torch.zeros(chunk * world, dtype=torch.float64, device="cuda")
+
+            def exchange():
+                shared[rank * chunk:(rank + 1) * chunk].copy_(sl)
+                torch.cuda.synchronize()
+                barrier.wait()
+                al.copy_(shared)
+                torch.cuda.synchronize()
+                barrier.wait()
+                return 0
+            h.set_exchange(sl.data_ptr(), al.data_ptr(), chunk, exchange)
+            xd = torch.from_numpy(X).cuda()
+            h.set_seeds_device(xd.data_ptr(), S)
+            h.lloyd_device(4)
+            info = h.newton_device(2, 7)
+            results[rank] = (h.get_seeds(), info)
+            h.close()
+        except Exception as ex:   # pragma: no cover
+            errors.append(ex)
+            barrier.abort()
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    h = handle_for(V, F)
+    x1 = h.lloyd(X, 4)
+    x1, info = h.newton(x1, 2, 7)
+    h.close()
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][0], x1)          # sharding does not change a single bit
+    assert results[0][1] == info

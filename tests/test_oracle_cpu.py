@@ -1,0 +1,112 @@
+"""CPU suite: the plain-C oracle against (i) golden vectors generated from the unmodified
+reference (tests/golden/make_golden.py), (ii) the reference itself when oracle/_ref is built,
+(iii) analytic known answers. No GPU needed."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from graphitethree_b200 import shapes
+from oracle import port, ref
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_matches_reference_golden(path):
+    G = load(path)
+    V, F, X = G["V"], G["F"], G["X"]
+    w = G.get("weights")
+    idx, cnt, sqd, tie = port.knn(X, 20)
+    assert tie.sum() == 0
+    assert np.array_equal(idx, G["knn_idx"]) and np.array_equal(cnt, G["knn_cnt"])
+    e = port.surface_eval(V, F, X, 0, False, weights=w)
+    assert np.array_equal(e.m, G["m"]) and np.array_equal(e.mg, G["mg"])          # bit-exact (same traversal order)
+    e = port.surface_eval(V, F, X, 1, True, weights=w, want_pairs=True)
+    assert e.f == float(G["f"]) and np.array_equal(e.g, G["g"])
+    if w is None:
+        assert np.array_equal(e.f_seed, G["f_seed"])
+    assert np.array_equal(e.pairs, G["pairs_exact"])
+    x, _ = port.lloyd(V, F, X, int(G["lloyd_iters"]), weights=w)
+    assert np.array_equal(x, G["x_lloyd"])
+    xn, info = port.newton(V, F, G["x_lloyd"], int(G["newton_iters"]), 7, weights=w)
+    assert info["iters"] == int(G["newton_iters"]) + 1          # HLBFGS runs max_iter+1 iterations (HLBFGS.cpp:580-584)
+    assert np.abs(xn - G["x_newton"]).max() <= 1e-12
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_live_reference_c1_like():
+    V, F = shapes.icosphere(20)
+    X = shapes.sample_surface(V, F, 2000, 11)
+    r = ref.RefCVT(V, F, multithread=False)
+    try:
+        r.set_points(X)
+        r.update_delaunay()
+        idx, cnt = r.neighbors(20)
+        pidx, pcnt, _, tie = port.knn(X, 20)
+        assert np.array_equal(idx, pidx) and np.array_equal(cnt, pcnt) and tie.sum() == 0
+        mg, m, _ = r.centroids(False)
+        e = port.surface_eval(V, F, X, 0, False)
+        assert np.array_equal(m, e.m) and np.array_equal(mg, e.mg)
+        q = V[::7]
+        assert np.array_equal(port.nearest(X, q), np.array([r.nearest_vertex(p) for p in q], dtype=np.uint32))
+    finally:
+        r.close()
+
+
+def test_duplicate_seed_rule():
+    # delaunay_nn.cpp:123-134: the later duplicate gets no neighbour, the earlier one skips it
+    V, F = shapes.icosphere(4)
+    X = shapes.sample_surface(V, F, 60, 2)
+    X[40] = X[10]
+    idx, cnt, sqd, tie = port.knn(X, 20)
+    assert cnt[40] == 0 and cnt[10] == 19 and 40 not in idx[10, :19]
+    assert tie[10] or tie[40]
+
+
+def test_small_seed_count():
+    X = np.random.default_rng(0).random((7, 3))
+    idx, cnt, _, _ = port.knn(X, 20)
+    assert (cnt == 6).all() and (idx[:, 6:] == 0xffffffff).all()
+
+
+def test_hlbfgs_rosenbrock_known_answer():
+    # geogram/src/tests/test_HLBFGS/main.cpp: minimum f=0 at x=1
+    x, f, it, nfev = port.hlbfgs_rosenbrock(1000, 5, 1000)
+    assert f < 1e-20 and np.abs(x - 1.0).max() < 1e-9
+
+
+def test_analytic_identities_exact_cells():
+    V, F = shapes.icosphere(12)
+    X = shapes.sample_surface(V, F, 400, 4)
+    P = V[F.astype(np.int64)]
+    area = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+    ec = port.surface_eval(V, F, X, 0, True)
+    assert abs(ec.m.sum() - area.sum()) <= 1e-12 * area.sum()                      # cells tile the surface
+    cen = (area[:, None] * P.mean(1)).sum(0)
+    assert np.abs(ec.mg.sum(0) - cen).max() <= 1e-12 * area.sum()
+    eg = port.surface_eval(V, F, X, 1, True)
+    assert np.abs(eg.g - 2.0 * (ec.m[:, None] * X - ec.mg)).max() <= 1e-13         # g = 2 m (x - c)
+    # gradient against central finite differences of f
+    rng = np.random.default_rng(1)
+    d = rng.standard_normal(X.shape)
+    h = 1e-6
+    fp = port.surface_eval(V, F, X + h * d, 1, True).f
+    fm = port.surface_eval(V, F, X - h * d, 1, True).f
+    assert abs((fp - fm) / (2 * h) - (eg.g * d).sum()) <= 1e-6 * abs((eg.g * d).sum())
+
+
+def test_facet_adjacency_closed_surface():
+    V, F = shapes.icosphere(5)
+    adj = port.facet_adjacency(F)
+    assert (adj >= 0).all()
+    f = np.arange(F.shape[0])
+    for lv in range(3):
+        back = adj[adj[:, lv]]
+        assert ((back == f[:, None]).sum(1) == 1).all()
