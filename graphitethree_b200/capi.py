@@ -170,10 +170,14 @@ class Handle:
         return fs
 
     def stats(self):
-        st = np.zeros(8, dtype=np.uint64)
+        st = np.zeros(16, dtype=np.uint64)
         _check(lib().b200cvt_get_stats(self._h, st.ctypes.data_as(_qp)))
-        return dict(planes=int(st[0]), cuts=int(st[1]), triangles=int(st[2]), nonempty_pairs=int(st[3]),
-                    redo_seeds=int(st[4]), candidate_pairs=int(st[5]), pair_cap=int(st[6]), grid_cells=int(st[7]))
+        d = dict(planes=int(st[0]), cuts=int(st[1]), triangles=int(st[2]), nonempty_pairs=int(st[3]),
+                 redo_seeds=int(st[4]), candidate_pairs=int(st[5]), pair_cap=int(st[6]), grid_cells=int(st[7]))
+        for i, ph in enumerate(("advance", "cut", "integrate")):
+            r, l = int(st[8 + 2 * i]), int(st[9 + 2 * i])
+            d["phase_" + ph] = dict(rounds=r, lanes_per_round=(l / r if r else 0.0))
+        return d
 
     def lloyd(self, x, nb_iter, locked=None, callback=None):
         x = np.array(x, dtype=np.float64, order="C", copy=True)

@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "knn.cuh"
 #include "clip.cuh"
+#include "clip_flat.cuh"
+#include "facet_pairs.cuh"
 #include "lbfgs.cuh"
 #include "../../include/b200cvt.h"
 
@@ -150,6 +152,10 @@ __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u3
     if (flags_out) flags_out[o] = flags[s];
 }
 
+__global__ void iota_u32_kernel(u32* p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (u32)i;
+}
+
 __global__ void fill_u32_kernel(u32* p, size_t n, u32 v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -171,7 +177,7 @@ template <class T> struct DevBuf {
 };
 
 struct b200cvt_ctx {
-    int device = 0, dim = 3, volumetric = 0;
+    int device = 0, dim = 3, volumetric = 0, num_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     u64 launches = 0;
@@ -201,7 +207,16 @@ struct b200cvt_ctx {
     DevBuf<u32> redo_a, redo_b, redo_n, nbr_big, nbr_big_n;
     // pairs
     u32 pair_cap = 0;
-    DevBuf<u32> pair_cnt, pair_facet, max_cnt;
+    DevBuf<u32> pair_cnt, pair_facet, pair_mask, max_cnt;
+    DevBuf<uint2> tasks;
+    // flat pair list (seed-major, facets ascending) + per-pair contributions
+    DevBuf<u32> pair_off, flat_seed, flat_facet, slow_list;
+    DevBuf<double> contrib, facet_area, planes;
+    DevBuf<uint8_t> pstat, pclass, pclass_sorted;
+    DevBuf<u32> flat_mask, iota, order;
+    DevBuf<unsigned char> sort_tmp;
+    size_t iota_filled = 0;
+    u32 npairs = 0;
     // outputs (sorted order) and original-order staging
     DevBuf<double> out_s, out_v, s_orig, v_orig;
     DevBuf<uint8_t> flags_orig, locked;
@@ -388,22 +403,43 @@ static void run_pairs_t(b200cvt_ctx* h) {
         u32 cap = 32; while (cap < want) cap <<= 1;
         h->pair_cap = cap;
     }
-    h->pair_cnt.ensure(S);
-    h->max_cnt.ensure(1);
+    const u32 nown = h->qend() - h->qbegin();
+    h->pair_cnt.ensure((size_t)S + 1);
+    h->pair_off.ensure((size_t)nown + 2);
+    h->max_cnt.ensure(2);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->pair_cnt.p, h->pair_off.p, (int)nown + 1, h->stream);
+    h->cub_tmp.ensure(scan_bytes);
     for (int attempt = 0; attempt < 8; ++attempt) {
         h->pair_facet.ensure((size_t)S * h->pair_cap);
-        CUDA_CHECK(cudaMemsetAsync(h->pair_cnt.p, 0, sizeof(u32) * S, h->stream));
-        CUDA_CHECK(cudaMemsetAsync(h->max_cnt.p, 0, sizeof(u32), h->stream));
-        PairArgs a;
-        a.tri = h->tri.p; a.fbegin = 0; a.fend = h->T; a.xs = h->xs.p; a.cell_range = h->cell_range.p;
-        a.rank_of = h->rank_of.p; a.facet_guess = h->facet_guess.p; a.qbegin = h->qbegin(); a.qend = h->qend();
-        a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.cap = h->pair_cap; a.max_cnt = h->max_cnt.p; a.g = h->g;
-        LAUNCH(h, pairs_kernel<D>, div_up(h->T, 128), 128, 0, a);
-        u32 mx = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&mx, h->max_cnt.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        h->pair_mask.ensure((size_t)S * h->pair_cap);
+        CUDA_CHECK(cudaMemsetAsync(h->pair_cnt.p, 0, sizeof(u32) * ((size_t)S + 1), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->max_cnt.p, 0, 2 * sizeof(u32), h->stream));
+        FacetPairArgs a;
+        memset(&a, 0, sizeof(a));
+        a.tri = h->tri.p; a.T = h->T; a.xs = h->xs.p; a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.kstride = h->kstride;
+        a.planes = h->planes.p; a.has_planes = nullptr; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+        a.facet_guess = h->facet_guess.p; a.S = S; a.qbegin = h->qbegin(); a.qend = h->qend();
+        a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.pair_mask = h->pair_mask.p; a.cap = h->pair_cap;
+        a.max_cnt = h->max_cnt.p; a.stats = h->want_stats ? h->stats.p : nullptr; a.g = h->g;
+        h->tasks.ensure(std::max<size_t>((size_t)h->T * 2, 1024));
+        a.tasks = h->tasks.p; a.task_cap = (u32)std::min<size_t>(h->tasks.cap, 0xffffffffu); a.task_n = h->max_cnt.p + 1;
+        if (h->T > 0) {
+            LAUNCH(h, facet_home_kernel<D>, div_up(h->T, 128), 128, 0, a);
+            LAUNCH(h, facet_task_kernel<D>, (u32)h->num_sms * 8u, 128, 0, a);
+        }
+        // flat offsets of the owned seeds (pair_cnt[qend] is 0: only owned seeds receive pairs)
+        size_t tb = h->cub_tmp.cap;
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->pair_cnt.p + h->qbegin(), h->pair_off.p, (int)nown + 1, h->stream));
+        h->launches += 1;
+        u32 mx[2] = {0, 0}, total = 0;
+        CUDA_CHECK(cudaMemcpyAsync(mx, h->max_cnt.p, 2 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&total, h->pair_off.p + nown, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        if (mx <= h->pair_cap) return;
-        u32 cap = h->pair_cap; while (cap < mx + mx / 4) cap <<= 1;
+        if (mx[1] > h->tasks.cap) { h->tasks.ensure((size_t)mx[1] + mx[1] / 4); continue; }   // task list overflow: rerun
+        if (mx[0] <= h->pair_cap) { h->npairs = total; return; }
+        u32 mx0 = mx[0];
+        u32 cap = h->pair_cap; while (cap < mx0 + mx0 / 4) cap <<= 1;
         h->pair_cap = cap;
     }
     throw CapacityError("candidate pair rows keep overflowing");
@@ -411,9 +447,9 @@ static void run_pairs_t(b200cvt_ctx* h) {
 
 template <int D>
 static void launch_clip(b200cvt_ctx* h, ClipArgs& a) {
-    if (a.nseeds == 0) return;
+    if (a.nseeds == 0 && !a.nseeds_dev) return;
     size_t smem = (size_t)CLIP_WARPS * a.kstride * (D + 2) * sizeof(double);
-    u32 blocks = div_up(a.nseeds, CLIP_WARPS);
+    u32 blocks = a.nseeds_dev ? 148u * 4u : div_up(a.nseeds, CLIP_WARPS);
     if (h->weighted) {
         if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LAUNCH(h, (clip_kernel<D, true>), blocks, CLIP_WARPS * 32, smem, a);
@@ -433,27 +469,89 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
     if (!h->grid_valid) build_grid(h);
     CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
-    if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, false);
+    // neighbour lists + bisector tables of every seed (the facet walk may visit any seed)
+    if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true);
+    h->planes.ensure((size_t)S * h->kstride * PLANE_STRIDE(D));
+    LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
+           h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, h->planes.p);
     CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
+    h->stats.ensure(16);
+    if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 16 * sizeof(unsigned long long), h->stream));
     run_pairs_t<D>(h);
     CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
 
     h->out_s.ensure(S); h->out_v.ensure((size_t)S * D);
-    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(2);
-    h->stats.ensure(8);
-    CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 2 * sizeof(u32), h->stream));
-    if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
+    const u32 nown = h->qend() - h->qbegin();
+    const u32 np = h->npairs;
+    h->flat_seed.ensure(np); h->flat_facet.ensure(np); h->flat_mask.ensure(np); h->pclass.ensure(np);
+    h->pstat.ensure(np); h->slow_list.ensure(nown);
+    h->contrib.ensure((size_t)np * (D + 1));
+    const size_t cstride = h->contrib.cap / (D + 1);
+    if (nown > 0) {
+        CompactArgs ca;
+        ca.pair_cnt = h->pair_cnt.p; ca.pair_facet = h->pair_facet.p; ca.pair_mask = h->pair_mask.p; ca.cap = h->pair_cap;
+        ca.pair_off = h->pair_off.p; ca.qbegin = h->qbegin(); ca.nown = nown;
+        ca.flat_seed = h->flat_seed.p; ca.flat_facet = h->flat_facet.p; ca.flat_mask = h->flat_mask.p; ca.pclass = h->pclass.p;
+        LAUNCH(h, compact_pairs_kernel, div_up(nown, 8), 256, 0, ca);
+    }
+    if (np > 0) {
+        h->pclass_sorted.ensure(np); h->order.ensure(np); h->iota.ensure(np);
+        if (h->iota_filled < h->iota.cap) {
+            LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
+            h->iota_filled = h->iota.cap;
+        }
+        ClipFlatArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.xs = h->xs.p; fa.nbr = h->nbr.p; fa.nbr_n = h->nbr_n.p; fa.kstride = h->kstride; fa.planes = h->planes.p;
+        fa.tri = h->tri.p; fa.triw = h->weighted ? h->triw.p : nullptr; fa.facet_area = h->facet_area.p;
+        fa.flat_seed = h->flat_seed.p; fa.flat_facet = h->flat_facet.p; fa.npairs_dev = h->pair_off.p + nown;
+        fa.mode = mode; fa.contrib = h->contrib.p; fa.cstride = cstride; fa.pstat = h->pstat.p;
+        fa.flat_mask = h->flat_mask.p; fa.order = h->order.p;
+        fa.stats = h->want_stats ? h->stats.p : nullptr;
+        // group the pairs by the number of bisectors that may cut them (stable: seed order kept inside a class)
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h->pclass.p, h->pclass_sorted.p, h->iota.p, h->order.p, (int)np, 0, 3, h->stream);
+        h->sort_tmp.ensure(sort_bytes);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, sort_bytes, h->pclass.p, h->pclass_sorted.p, h->iota.p, h->order.p, (int)np, 0, 3,
+                                                   h->stream));
+        h->launches += 3;
+        const int VW = D + (h->weighted ? 1 : 0);
+        const size_t smem = (size_t)CLIPF_WARPS * CLIPF_MAXV * VW * 32 * sizeof(double);
+        const u32 blocks = div_up(np, CLIPF_WARPS * 32);
+        if (h->weighted) {
+            CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(h, (clip_cut_kernel<D, true>), blocks, CLIPF_WARPS * 32, smem, fa);
+        } else {
+            CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(h, (clip_cut_kernel<D, false>), blocks, CLIPF_WARPS * 32, smem, fa);
+        }
+    }
     ClipArgs c;
     memset(&c, 0, sizeof(c));
     c.xs = h->xs.p; c.nbr = h->nbr.p; c.nbr_n = h->nbr_n.p; c.kstride = h->kstride; c.nbr_by_slot = 0;
     c.tri = h->tri.p; c.triw = h->weighted ? h->triw.p : nullptr;
     c.pair_cnt = h->pair_cnt.p; c.pair_facet = h->pair_facet.p; c.cap = h->pair_cap;
-    c.seed_list = nullptr; c.nseeds = h->qend() - h->qbegin(); c.qbegin = h->qbegin();
+    c.seed_list = nullptr; c.nseeds = nown; c.qbegin = h->qbegin();
     c.mode = mode; c.check_SR = check_SR; c.S = S;
     c.out_s = h->out_s.p; c.out_v = h->out_v.p; c.flags = h->flags.p;
     c.redo_list = check_SR ? h->redo_a.p : nullptr; c.redo_n = h->redo_n.p;
     c.stats = h->want_stats ? h->stats.p : nullptr;
-    launch_clip<D>(h, c);
+    if (nown > 0) {
+        ReduceArgs ra;
+        ra.pair_off = h->pair_off.p; ra.qbegin = h->qbegin(); ra.nown = nown;
+        ra.contrib = h->contrib.p; ra.cstride = cstride; ra.pstat = h->pstat.p;
+        ra.nbr_n = h->nbr_n.p; ra.kstride = h->kstride; ra.check_SR = check_SR; ra.S = S;
+        ra.out_s = h->out_s.p; ra.out_v = h->out_v.p; ra.flags = h->flags.p;
+        ra.slow_list = h->slow_list.p; ra.slow_n = h->redo_n.p + 2;
+        ra.redo_list = h->redo_a.p; ra.redo_n = h->redo_n.p;
+        LAUNCH(h, reduce_pairs_kernel<D>, div_up(nown, 256), 256, 0, ra);
+        // seeds with a pair the in-place fast path gave up on: warp-per-seed kernel, same neighbour table
+        ClipArgs sl = c;
+        sl.seed_list = h->slow_list.p; sl.nseeds = 0; sl.nseeds_dev = h->redo_n.p + 2;
+        launch_clip<D>(h, sl);
+    }
 
     if (check_SR) {
         // enlarge_neighborhood loop (generic_RVD.h:2179-2197), batched over the seeds that need it
@@ -668,6 +766,7 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
         CUDA_CHECK(cudaSetDevice(device));
         b200cvt_ctx* h = new b200cvt_ctx;
         h->device = device; h->dim = dim; h->volumetric = volumetric;
+        CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
         *out = h;
@@ -685,6 +784,8 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->nbr_big.release(); h->nbr_big_n.release(); h->pair_cnt.release(); h->pair_facet.release(); h->max_cnt.release();
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
+    h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release(); h->pclass.release(); h->pclass_sorted.release();
+    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -732,6 +833,11 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         }
         h->facet_guess.ensure(ne);
         LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)ne, B200_NONE);
+        h->facet_area.ensure(ne);
+        if (ne > 0) {
+            if (D == 3) LAUNCH(h, facet_area_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
+            else LAUNCH(h, facet_area_kernel<6>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
+        }
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         h->has_mesh = true; h->grid_valid = false; h->knn_valid = false; h->has_results = false; h->pair_cap = 0;
     });
@@ -747,7 +853,7 @@ int b200cvt_set_seeds(b200cvt_handle h, const double* x, uint32_t S) {
         if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
         set_seeds_common(h, S);
         build_grid(h);
-        run_knn_main(h, 20, false, false);
+        run_knn_main(h, 20, false, true);
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });
 }
@@ -870,14 +976,16 @@ int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out) {
 
 // stats: [0] planes tested [1] planes that cut [2] integration triangles [3] non-empty pairs
 //        [4] seeds re-clipped with an enlarged neighbourhood [5] candidate pairs [6] pair row capacity [7] grid cells
+//        [8..13] clip state machine: (rounds, lanes served) of the advance / cut / integrate phases  [14..15] reserved
 int b200cvt_get_stats(b200cvt_handle h, uint64_t* out) {
     return guarded([&] {
         if (!h || !out) throw ArgError("null argument");
         CUDA_CHECK(cudaSetDevice(h->device));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long st[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (h->stats.p && h->want_stats) CUDA_CHECK(cudaMemcpy(st, h->stats.p, sizeof(st), cudaMemcpyDeviceToHost));
         for (int i = 0; i < 4; ++i) out[i] = st[i];
+        for (int i = 8; i < 16; ++i) out[i] = st[i];
         out[4] = h->host_stats[4];
         u64 total = 0;
         if (h->has_results && h->cnt_orig.p) {

@@ -26,7 +26,7 @@
 #include "knn.cuh"
 
 #define CLIP_WARPS 4
-#define CLIP_MAXV 16
+#define CLIP_MAXV 24
 #define B200CVT_KMAX_DEV 124u
 
 // ---------------------------------------------------------------------------------------
@@ -139,6 +139,7 @@ struct ClipArgs {
     const u32* pair_cnt; u32* pair_facet; u32 cap;
     const u32* seed_list;      // optional sorted positions (redo pass); NULL: [qbegin,qend)
     u32 nseeds;                // number of seeds processed (qend-qbegin or list length)
+    const u32* nseeds_dev;     // optional: list length read from device memory instead
     u32 qbegin;
     int mode;                  // 0: m, mg   1: f_seed, g
     int check_SR;
@@ -162,7 +163,8 @@ clip_kernel(ClipArgs a) {
     double* pl_d = pl_n + (size_t)a.kstride * D;
     double* pl_dij = pl_d + a.kstride;
 
-    for (u32 si = blockIdx.x * CLIP_WARPS + w; si < a.nseeds; si += gridDim.x * CLIP_WARPS) {
+    const u32 nseeds = a.nseeds_dev ? *a.nseeds_dev : a.nseeds;
+    for (u32 si = blockIdx.x * CLIP_WARPS + w; si < nseeds; si += gridDim.x * CLIP_WARPS) {
         const u32 s = a.seed_list ? a.seed_list[si] : a.qbegin + si;
         double pi[D];
 #pragma unroll

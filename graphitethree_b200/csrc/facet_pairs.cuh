@@ -1,0 +1,267 @@
+// facet_pairs.cuh — candidate (facet, seed) pairs AND their classification, one thread per facet.
+//
+// Replaces the facet-driven double flood-fill of
+//   GEOGen::RestrictedVoronoiDiagram::compute_surfacic_with_seeds_priority (generic_RVD.h:1318-1424)
+// and its 1-NN start (find_seed_near_facet, generic_RVD.h:2010-2070) by a walk on the bisector
+// table of the kNN graph (clip_flat.cuh: plane_table_kernel):
+//
+//  1. home seed s0 of the facet = a seed whose cell contains the facet centroid: start from the
+//     seed found for this facet in the previous evaluation and hop to any listed neighbour that
+//     is closer to the centroid (any s0 gives a correct candidate set; a near one a small set).
+//  2. For a facet with corners c_i and ANY seed s0, a seed s whose Voronoi cell meets the facet
+//     has |c_i - s| <= |c_i - s0| for some corner i (the half-space {x: |x-s| <= |x-s0|} meets the
+//     triangle iff it contains a corner), i.e. corner i is NOT strictly on s0's side of the bisector
+//     (s0, s); and then |s - s0| <= 2 max_i |c_i - s0|. So one scan of s0's bisectors in list order,
+//     up to squared distance 4.1 max_i |c_i - s0|^2, with the side test of clip_by_plane_fast on the
+//     three corners, yields at once (a) every candidate seed and (b) the classification of the
+//     pair (facet, s0): the bisectors that may cut it (bit mask), "cell contains the facet" (no
+//     bit), "facet outside the cell" (some bisector has all corners outside).
+//  3. Each candidate s gets the same scan with its own bisectors (classification of (facet, s)).
+//
+// If s0's list ends before the distance bound, candidates beyond the list are possible: the
+// facet falls back to the uniform-grid scan of every seed in the union of the corner balls.
+// Pairs are appended to per-seed rows {facet, mask}; compact_pairs_kernel sorts each row.
+#pragma once
+#include "common.cuh"
+#include "knn.cuh"
+#include "clip_flat.cuh"
+
+#define PMASK_SR_OK 0x80000000u   // the radius test passed on the unclipped facet before the list ended
+#define PMASK_BITS 0x7fffffffu
+
+struct FacetPairArgs {
+    const double* tri;        // [T][3][D] facet corners (facets Morton-sorted once per mesh)
+    u32 T;
+    const void* xs;
+    const u32* nbr; const u32* nbr_n; u32 kstride;
+    const double* planes;     // [S][kstride][PLANE_STRIDE]
+    const uint8_t* has_planes; // optional [S]: 1 if the seed's rows of nbr/planes are valid (sharded runs)
+    const uint2* cell_range;
+    const u32* rank_of;
+    u32* facet_guess;         // [T] original index of the last home seed (B200_NONE: none)
+    u32 S;
+    u32 qbegin, qend;         // owned sorted range
+    u32* pair_cnt;            // [S] sorted order
+    u32* pair_facet;          // [S][cap]
+    u32* pair_mask;           // [S][cap]
+    u32 cap;
+    u32* max_cnt;             // device scalar: max row length seen (overflow detection)
+    uint2* tasks; u32 task_cap; u32* task_n;   // candidate (seed, facet) tasks of kernel A for kernel B
+    unsigned long long* stats; // optional: [14] facets that took the grid fallback
+    GridParams g;
+};
+
+// scan of seed s's bisectors against the facet corners. Returns the mask of bisectors that may cut
+// (| PMASK_SR_OK); *empty = some bisector has all corners outside; *cand = bisectors with a corner
+// not strictly inside (candidate neighbours); *hop = first bisector with the facet centroid outside
+// (the neighbour is closer to the centroid than s), -1 if none.
+// The side values only feed conservative decisions (a rounding margin is applied), so FMA is used.
+template <int D, bool HOME>
+__device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2, const double* pi, const double* prow, u32 nn,
+                                              bool* empty, u32* cand, int* hop) {
+    constexpr int PS = PLANE_STRIDE(D);
+    double R2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) R2 = fmax(R2, dist2<D>(pi, v[i]));
+    const double R2lim = 4.1 * R2;
+    u32 mask = 0, cm = 0;
+    bool emp = false;
+    if (HOME) *hop = -1;
+    for (u32 jj = 0; jj < nn; ++jj) {
+        const double* pl = prow + (size_t)jj * PS;
+        const double dij = pl[D + 1];
+        // radius test on the unclipped facet (generic_RVD.h:2155-2174): clipping only shrinks R2, so every
+        // bisector the reference tests is visited
+        if (dij > R2lim) { mask |= PMASK_SR_OK; break; }
+        double nj[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) nj[c] = pl[c];
+        const double d = pl[D];
+        // rounding margin of a side value 2 q.n - d for any point q of the facet: |q.n| <= (|q|^2 + |n|^2) / 2
+        const double margin = 1e-12 * (fabs(d) + vmax2 + dij);
+        double tk[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double l = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) l = fma(v[i][c], nj[c], l);
+            tk[i] = fma(2.0, l, -d);
+        }
+        if (HOME && tk[0] + tk[1] + tk[2] < 0.0) { *hop = (int)jj; break; }
+        if (tk[0] > margin && tk[1] > margin && tk[2] > margin) continue;   // clearly inside: cannot touch any clipped polygon
+        cm |= 1u << jj;
+        if (tk[0] < -margin && tk[1] < -margin && tk[2] < -margin) emp = true;   // clearly outside: removes the polygon
+        else mask |= 1u << jj;
+    }
+    *empty = emp;
+    if (HOME) *cand = cm;
+    return mask;
+}
+
+template <int D>
+__device__ __forceinline__ void emit_pair(const FacetPairArgs& a, u32 s, u32 f, u32 mask) {
+    if (s < a.qbegin || s >= a.qend) return;
+    const u32 slot = atomicAdd(&a.pair_cnt[s], 1u);
+    if (slot < a.cap) {
+        a.pair_facet[(size_t)s * a.cap + slot] = f;
+        a.pair_mask[(size_t)s * a.cap + slot] = mask;
+    } else atomicMax(a.max_cnt, slot + 1);
+}
+
+// every owned seed inside the union of the balls B(c_i, |c_i - s0|), from the uniform grid
+template <int D>
+__device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const double (*v)[D], double vmax2, u32 s0, u32 f) {
+    constexpr int PS = PLANE_STRIDE(D);
+    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    double r2[3], lo3[3], hi3[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) { lo3[ax] = 1e300; hi3[ax] = -1e300; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r2[i] = dist2<D>(v[i], xs[s0].p) * (1.0 + 1e-12);
+        const double rr = sqrt(r2[i]) * (1.0 + 1e-12);
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) { lo3[ax] = fmin(lo3[ax], v[i][ax] - rr); hi3[ax] = fmax(hi3[ax], v[i][ax] + rr); }
+    }
+    int lo[3], hi[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) { lo[ax] = grid_coord(a.g, lo3[ax], ax); hi[ax] = grid_coord(a.g, hi3[ax], ax); }
+    for (int cz = lo[2]; cz <= hi[2]; ++cz)
+        for (int cy = lo[1]; cy <= hi[1]; ++cy)
+            for (int cx = lo[0]; cx <= hi[0]; ++cx) {
+                const uint2 rg = a.cell_range[morton_encode(a.g, cx, cy, cz)];
+                const u32 sb = max(rg.x, a.qbegin), se = min(rg.y, a.qend);
+                for (u32 s = sb; s < se; ++s) {
+                    double ps[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
+                    const bool in = dist2<D>(v[0], ps) <= r2[0] || dist2<D>(v[1], ps) <= r2[1] || dist2<D>(v[2], ps) <= r2[2];
+                    if (!in) continue;
+                    const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
+                    bool empty = false;
+                    const u32 mask = classify_facet<D, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                    if (!empty) emit_pair<D>(a, s, f, mask);
+                }
+            }
+}
+
+// kernel A: one thread per facet — home seed, classification of (facet, home), candidate tasks
+template <int D>
+__global__ void __launch_bounds__(128, 4)
+facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
+    constexpr int PS = PLANE_STRIDE(D);
+    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    u32 cand = 0, s0 = 0;
+    if (f < a.T) {
+        double v[3][D];
+        const double* t = a.tri + (size_t)f * 3 * D;
+        double vmax2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double q2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { v[i][c] = t[i * D + c]; q2 += v[i][c] * v[i][c]; }
+            vmax2 = fmax(vmax2, q2);
+        }
+        // home seed: previous answer (or a grid search), then hops while a listed neighbour is closer to the centroid
+        {
+            const u32 guess = a.facet_guess[f];
+            if (guess != B200_NONE) s0 = a.rank_of[guess];
+            else {
+                double gc[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
+                s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
+            }
+        }
+        bool certified = false, empty0 = false;
+        u32 mask0 = 0;
+        for (int it = 0; it < 32; ++it) {
+            if (a.has_planes && !a.has_planes[s0]) break;
+            double p0[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) p0[c] = xs[s0].p[c];
+            const u32 nn0 = min(min(a.nbr_n[s0], a.kstride), 31u);
+            int hop = -1;
+            mask0 = classify_facet<D, true>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
+            if (hop >= 0) { s0 = a.nbr[(size_t)s0 * a.kstride + hop]; cand = 0; continue; }
+            // the scan reached the distance bound (or the list holds every other seed): s0 is the nearest seed of
+            // the centroid and every candidate is in the list
+            certified = (mask0 & PMASK_SR_OK) || (nn0 + 1 >= a.S);
+            break;
+        }
+        if (certified) {
+            a.facet_guess[f] = (u32)xs[s0].orig;
+            if (!empty0) emit_pair<D>(a, s0, f, mask0);
+        } else {
+            // s0's list ends inside the distance bound (or s0 has no table): exact nearest seed from the grid,
+            // candidates from the grid
+            cand = 0;
+            double gc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
+            s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
+            a.facet_guess[f] = (u32)xs[s0].orig;
+            if (a.stats) atomicAdd(&a.stats[14], 1ull);
+            double vv[3][D];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < D; ++c) vv[i][c] = v[i][c];
+            grid_candidates<D>(a, vv, vmax2, s0, f);
+        }
+    }
+    // candidate tasks (seed, facet), appended with one atomic per warp
+    const u32 nc = __popc(cand);
+    u32 incl = nc;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const u32 o = __shfl_up_sync(B200_FULL, incl, m);
+        if (lane >= m) incl += o;
+    }
+    const u32 total = __shfl_sync(B200_FULL, incl, 31);
+    if (total == 0) return;
+    u32 base = 0;
+    if (lane == 31) base = atomicAdd(a.task_n, total);
+    base = __shfl_sync(B200_FULL, base, 31);
+    u32 pos = base + incl - nc;
+    while (cand) {
+        const int jj = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (pos < a.task_cap) a.tasks[pos] = make_uint2(a.nbr[(size_t)s0 * a.kstride + jj], f);
+        ++pos;
+    }
+}
+
+// kernel B: one thread per candidate task — classification of (facet, candidate) with the candidate's bisectors
+template <int D>
+__global__ void __launch_bounds__(128, 4)
+facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
+    constexpr int PS = PLANE_STRIDE(D);
+    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    const u32 ntask = min(*a.task_n, a.task_cap);
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < ntask; e += gridDim.x * blockDim.x) {
+        const uint2 tk = a.tasks[e];
+        const u32 s = tk.x, f = tk.y;
+        if (s < a.qbegin || s >= a.qend) continue;
+        double v[3][D];
+        const double* t = a.tri + (size_t)f * 3 * D;
+        double vmax2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double q2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { v[i][c] = t[i * D + c]; q2 += v[i][c] * v[i][c]; }
+            vmax2 = fmax(vmax2, q2);
+        }
+        double ps[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
+        const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
+        bool empty = false;
+        const u32 mask = classify_facet<D, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+        if (!empty) emit_pair<D>(a, s, f, mask);
+    }
+}

@@ -101,7 +101,7 @@ int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_
  * flags (S), per-seed energy (S; funcgrad only), candidate (facet,seed) pair counts (S). */
 int b200cvt_get_flags(b200cvt_handle h, uint8_t* flags_out);
 int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out);
-int b200cvt_get_stats(b200cvt_handle h, uint64_t* stats_out /* 8 entries, see b200cvt.cu */);
+int b200cvt_get_stats(b200cvt_handle h, uint64_t* stats_out /* 16 entries, see b200cvt.cu */);
 
 /* Replaces: CentroidalVoronoiTesselation::Lloyd_iterations (G/voronoi/CVT.cpp:133-167).
  * x_inout: S x dim seeds, updated in place. locked_or_null: S bytes (point_is_locked_).
