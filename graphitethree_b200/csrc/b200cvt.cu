@@ -197,10 +197,12 @@ struct b200cvt_ctx {
     DevBuf<u32> rank_of;
     DevBuf<uint2> cell_range;
     GridParams g;
+    DevBuf<u32> mtab; int mtab_bits[3] = {-1, -1, -1};
     // kNN
     u32 k = 20, kstride = 20;
     bool knn_valid = false;
-    DevBuf<u32> nbr, nbr_n;
+    DevBuf<u32> nbr, nbr_n, nbr_prev;   // nbr_prev: lists of the previous evaluation, original indices, rows by original index
+    bool prev_valid = false;
     DevBuf<double> sqd;
     DevBuf<uint8_t> flags;            // sorted order
     // redo (check_SR) tables
@@ -318,6 +320,21 @@ static void choose_grid(b200cvt_ctx* h, const double lo[3], const double hi[3]) 
     for (int a = 0; a < 3; ++a) g.lo[a] = lo[a] - 1e-9 * maxext;
     g.h = cell; g.inv_h = 1.0 / cell;
     g.ncells = 1u << g.total_bits;
+    // per-axis Morton bit tables (re-uploaded only when the bit layout changes)
+    if (!h->mtab.p || h->mtab_bits[0] != g.bits[0] || h->mtab_bits[1] != g.bits[1] || h->mtab_bits[2] != g.bits[2]) {
+        std::vector<u32> tab(3 * 1024, 0);
+        GridParams t = g; t.mtab = nullptr;
+        for (int c = 0; c < 1024; ++c) {
+            if (c < (1 << g.bits[0])) tab[c] = morton_encode(t, c, 0, 0);
+            if (c < (1 << g.bits[1])) tab[1024 + c] = morton_encode(t, 0, c, 0);
+            if (c < (1 << g.bits[2])) tab[2048 + c] = morton_encode(t, 0, 0, c);
+        }
+        h->mtab.ensure(3 * 1024);
+        CUDA_CHECK(cudaMemcpyAsync(h->mtab.p, tab.data(), sizeof(u32) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        for (int a = 0; a < 3; ++a) h->mtab_bits[a] = g.bits[a];
+    }
+    g.mtab = h->mtab.p;
 }
 
 template <int D>
@@ -387,7 +404,13 @@ static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds) {
     a.k = k; a.kstride = h->kstride; a.S = S;
     a.qbegin = all_seeds ? 0 : h->qbegin(); a.qend = all_seeds ? S : h->qend();
     a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.sqd = want_sqd ? h->sqd.p : nullptr; a.flags = h->flags.p; a.g = h->g;
+    if (k == 20 && all_seeds) {
+        // the evaluation path: seeds move little between evaluations, the old lists bound the new search radius
+        h->nbr_prev.ensure((size_t)S * 20);
+        a.prev_in = h->prev_valid ? h->nbr_prev.p : nullptr; a.prev_out = h->nbr_prev.p; a.prev_stride = 20;
+    }
     if (h->dim == 3) launch_knn<3>(h, a, a.qend - a.qbegin); else launch_knn<6>(h, a, a.qend - a.qbegin);
+    if (k == 20 && all_seeds) h->prev_valid = true;
     h->knn_valid = true;
 }
 
@@ -627,7 +650,7 @@ static void upload_locked(b200cvt_ctx* h, const uint8_t* locked, u32 S) {
 }
 
 static void set_seeds_common(b200cvt_ctx* h, u32 S) {
-    if (S != h->S) { h->pair_cap = 0; }
+    if (S != h->S) { h->pair_cap = 0; h->prev_valid = false; }
     h->S = S;
     h->has_seeds = true;
     h->grid_valid = false; h->knn_valid = false; h->has_results = false;
@@ -785,7 +808,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
     h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release(); h->pclass.release(); h->pclass_sorted.release();
-    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
+    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -803,9 +826,7 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         CUDA_CHECK(cudaSetDevice(h->device));
         const int D = h->dim;
         const int per = 3;
-        std::vector<double> soup((size_t)ne * 3 * D);
-        std::vector<double> sw;
-        if (weights) sw.resize((size_t)ne * 3);
+        // pass 1: validate, bounding box, total area
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         double area = 0.0;
         for (u32 f = 0; f < ne; ++f) {
@@ -814,14 +835,47 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
                 u32 v = elems[(size_t)f * per + lv];
                 if (v >= nv) throw ArgError("element references a vertex out of range");
                 p[lv] = vertices + (size_t)v * stride;
-                for (int c = 0; c < D; ++c) soup[((size_t)f * 3 + lv) * D + c] = p[lv][c];
-                if (weights) sw[(size_t)f * 3 + lv] = weights[v];
                 for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[lv][a]); hi[a] = std::max(hi[a], p[lv][a]); }
             }
             double e1[3], e2[3];
             for (int a = 0; a < 3; ++a) { e1[a] = p[1][a] - p[0][a]; e2[a] = p[2][a] - p[0][a]; }
             double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
             area += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+        }
+        // pass 2: facets in Morton order of their centroids (10 bits per axis), so that the facets one warp walks
+        // share home seeds and bisector rows. The reference reorders the caller's mesh for the same reason
+        // (mesh_partition Hilbert sort, RVD.cpp:2390-2395); here only the device copy is permuted.
+        std::vector<std::pair<u32, u32>> order(ne);
+        {
+            double maxext = 0.0;
+            for (int a = 0; a < 3; ++a) maxext = std::max(maxext, hi[a] - lo[a]);
+            const double sc = maxext > 0.0 ? 1023.999 / maxext : 0.0;
+            for (u32 f = 0; f < ne; ++f) {
+                u32 q[3];
+                for (int a = 0; a < 3; ++a) {
+                    double c = 0.0;
+                    for (int lv = 0; lv < 3; ++lv) c += vertices[(size_t)elems[(size_t)f * 3 + lv] * stride + a];
+                    double t = (c * (1.0 / 3.0) - lo[a]) * sc;
+                    q[a] = (u32)std::min(1023.0, std::max(0.0, t));
+                }
+                u32 code = 0;
+                for (int b = 0; b < 10; ++b)
+                    code |= (((q[0] >> b) & 1u) << (3 * b)) | (((q[1] >> b) & 1u) << (3 * b + 1)) | (((q[2] >> b) & 1u) << (3 * b + 2));
+                order[f] = std::make_pair(code, f);
+            }
+            std::sort(order.begin(), order.end());
+        }
+        std::vector<double> soup((size_t)ne * 3 * D);
+        std::vector<double> sw;
+        if (weights) sw.resize((size_t)ne * 3);
+        for (u32 i = 0; i < ne; ++i) {
+            const u32 f = order[i].second;
+            for (int lv = 0; lv < per; ++lv) {
+                const u32 v = elems[(size_t)f * per + lv];
+                const double* p = vertices + (size_t)v * stride;
+                for (int c = 0; c < D; ++c) soup[((size_t)i * 3 + lv) * D + c] = p[c];
+                if (weights) sw[(size_t)i * 3 + lv] = weights[v];
+            }
         }
         h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = area;
         for (int a = 0; a < 3; ++a) { h->bb_lo[a] = lo[a]; h->bb_hi[a] = hi[a]; }

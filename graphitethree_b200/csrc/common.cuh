@@ -33,9 +33,13 @@ struct GridParams {
     int bits[3];
     int total_bits;
     u32 ncells;
+    const u32* mtab;   // device table [3][1024]: the Morton bits of each axis coordinate (NULL: compute)
 };
 
 __host__ __device__ inline u32 morton_encode(const GridParams& g, int cx, int cy, int cz) {
+#ifdef __CUDA_ARCH__
+    if (g.mtab) return __ldg(g.mtab + cx) | __ldg(g.mtab + 1024 + cy) | __ldg(g.mtab + 2048 + cz);
+#endif
     u32 code = 0;
     int out = 0;
     u32 x = (u32)cx, y = (u32)cy, z = (u32)cz;

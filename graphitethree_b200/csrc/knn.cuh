@@ -22,7 +22,7 @@
 struct KnnKey { u64 d; u32 id; };
 
 __device__ __forceinline__ bool key_less(u64 da, u32 ia, u64 db, u32 ib) {
-    return da < db || (da == db && ia < ib);
+    return (da < db) | ((da == db) & (ia < ib));     // no short-circuit: one predicate, no divergence
 }
 
 // compare-exchange with lane^mask; keep_min selects which of the pair this lane keeps
@@ -99,6 +99,10 @@ struct KnnArgs {
     u32* nbr_n;              // [S]
     double* sqd;             // optional [S][kstride]
     uint8_t* flags;          // [S] sorted order, OR-ed with B200CVT_FLAG_TIE
+    // temporal coherence: the neighbour lists of the previous evaluation, rows by ORIGINAL seed index, entries
+    // ORIGINAL indices. The largest new distance to the old neighbours bounds the new k-th distance, so one
+    // pass over the grid cells that meet that ball is enough. prev_in may be NULL; prev_out (optional) is written.
+    const u32* prev_in; u32* prev_out; u32 prev_stride;
     GridParams g;
 };
 
@@ -134,20 +138,54 @@ knn_kernel(KnnArgs a) {
         for (int ax = 0; ax < 3; ++ax) c0[ax] = grid_coord(a.g, pq[ax], ax);
 
         WarpTopK<NPL> top;
+        // threshold from the previous lists
+        bool have_thr = false;
+        u64 thr0_d = ~0ull;
+        if (a.prev_in && kk <= 32u && kk <= a.prev_stride) {
+            u64 dk = 0;
+            bool ok = true;
+            if ((u32)lane < kk) {
+                const u32 pid = a.prev_in[(size_t)qorig * a.prev_stride + lane];
+                ok = pid != B200_NONE;
+                if (ok) {
+                    const SeedRec<D>* rec = xs + a.rank_of[pid];
+                    double pc[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) pc[c] = rec->p[c];
+                    dk = (u64)__double_as_longlong(dist2<D>(pq, pc));
+                }
+            }
+            if (__all_sync(B200_FULL, ok)) {
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) { u64 o = __shfl_xor_sync(B200_FULL, dk, m); dk = max(dk, o); }
+                thr0_d = dk;       // kk old neighbours + the seed itself lie within this distance: >= the kq-th distance
+                have_thr = true;
+            }
+        }
         for (int r = 1;; ++r) {
             top.reset();
-            u64 thr_d = ~0ull; u32 thr_i = B200_NONE;
+            u64 thr_d = have_thr ? thr0_d : ~0ull; u32 thr_i = B200_NONE;
             int nbuf = 0;
-            const int side = 2 * r + 1;
-            const int ncell_blk = side * side * side;
+            // block of cells: the bounding box of the threshold ball, or the ring r around the query's cell
+            int blo[3], bhi[3];
+            if (have_thr) {
+                const double rad = sqrt(__longlong_as_double((long long)thr0_d)) * (1.0 + 1e-9) + 1e-300;
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) { blo[ax] = grid_coord(a.g, pq[ax] - rad, ax); bhi[ax] = grid_coord(a.g, pq[ax] + rad, ax); }
+            } else {
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) { blo[ax] = c0[ax] - r; bhi[ax] = c0[ax] + r; }
+            }
+            const int sx = bhi[0] - blo[0] + 1, sy = bhi[1] - blo[1] + 1, sz = bhi[2] - blo[2] + 1;
+            const int ncell_blk = sx * sy * sz;
             for (int cb = 0; cb < ncell_blk; cb += 32) {
                 // one cell per lane
                 int ci = cb + lane;
                 u32 start = 0, len = 0;
                 if (ci < ncell_blk) {
-                    int dz = ci / (side * side), rem = ci - dz * side * side;
-                    int dy = rem / side, dx = rem - dy * side;
-                    int cx = c0[0] + dx - r, cy = c0[1] + dy - r, cz = c0[2] + dz - r;
+                    int dz = ci / (sx * sy), rem = ci - dz * sx * sy;
+                    int dy = rem / sx, dx = rem - dy * sx;
+                    int cx = blo[0] + dx, cy = blo[1] + dy, cz = blo[2] + dz;
                     if (cx >= 0 && cy >= 0 && cz >= 0 && cx < a.g.res[0] && cy < a.g.res[1] && cz < a.g.res[2]) {
                         uint2 rg = a.cell_range[morton_encode(a.g, cx, cy, cz)];
                         start = rg.x; len = rg.y - rg.x;
@@ -201,7 +239,9 @@ knn_kernel(KnnArgs a) {
                                 nbuf -= 32;
                                 __syncwarp();
                                 top.merge(bd, bi, lane);
-                                top.get((int)kreq - 1, thr_d, thr_i);
+                                u64 nd; u32 ni;
+                                top.get((int)kreq - 1, nd, ni);
+                                if (key_less(nd, ni, thr_d, thr_i)) { thr_d = nd; thr_i = ni; }
                             }
                         }
                     }
@@ -213,8 +253,11 @@ knn_kernel(KnnArgs a) {
                 if (lane < nbuf) { bd = bufd[lane]; bi = bufi[lane]; }
                 __syncwarp();
                 top.merge(bd, bi, lane);
-                top.get((int)kreq - 1, thr_d, thr_i);
+                u64 nd; u32 ni;
+                top.get((int)kreq - 1, nd, ni);
+                if (key_less(nd, ni, thr_d, thr_i)) { thr_d = nd; thr_i = ni; }
             }
+            if (have_thr) break;     // every seed within the threshold ball was scanned
             // certified when the kreq-th distance is inside the block, or the block is the grid
             bool whole = true;
             double b = 1e300;
@@ -259,6 +302,7 @@ knn_kernel(KnnArgs a) {
             if (keep) {
                 u32 pos = nres + __popc(kmask & ((1u << lane) - 1u));
                 if (pos < kk) {
+                    if (a.prev_out && pos < a.prev_stride) a.prev_out[(size_t)qorig * a.prev_stride + pos] = ii;
                     a.nbr[orow * a.kstride + pos] = a.rank_of[ii];
                     if (a.sqd) a.sqd[orow * a.kstride + pos] = __longlong_as_double((long long)dd);
                 }
@@ -267,6 +311,7 @@ knn_kernel(KnnArgs a) {
         }
         if (nres > kk) nres = kk;
         if (dup_smaller) nres = 0;
+        if (a.prev_out) for (u32 e = nres + lane; e < a.prev_stride; e += 32) a.prev_out[(size_t)qorig * a.prev_stride + e] = B200_NONE;
         for (u32 e = nres + lane; e < a.kstride; e += 32) {
             a.nbr[orow * a.kstride + e] = B200_NONE;
             if (a.sqd) a.sqd[orow * a.kstride + e] = -1.0;

@@ -2,6 +2,9 @@
 usage: ncu_lines.py <source.csv> <function.sass (nvdisasm -g -c excerpt)> [top]"""
 import csv, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
+# several launches may be listed one after the other: keep the first
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+if len(starts) > 1: rows = rows[starts[0]:starts[1]]
 hdr = rows[1]; ix = {h: j for j, h in enumerate(hdr)}
 sass = []
 cur = None
