@@ -321,35 +321,52 @@ def main():
                            "l2": "inputs larger than L2 (facet table %d MB, re-sorted seeds every evaluation)" % (F.shape[0] * 72 // 2 ** 20),
                            "wall_s": wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
-        # roofline of the dominant kernel (clip + integrate), SURVEY.md §8(d)
+        # roofline of the dominant kernel (clip_cut_kernel), SURVEY.md §8(d). Durations are CUDA events recorded by the
+        # library on its stream around that kernel alone, accumulated over the timed region.
         try:
             fp32, fp64, copy = capi.measure_peaks(local_rank)
-            states = [X, x_final]
-            if args.small or not args.no_cpu_baseline:
-                f_lloyd = algorithmic_flops_per_seed_iteration(V, F, states, False)
-                f_newton = algorithmic_flops_per_seed_iteration(V, F, [x_final], True)
-            else:
-                f_lloyd, f_newton = 8500.0, 9500.0
-            n_newton = n_eval - LLOYD_ITERS
-            flops_step = own * (LLOYD_ITERS * f_lloyd + n_newton * f_newton)
-            clip_s = cum["clip"] * 1e-3 / args.steps
-            achieved = flops_step / clip_s / 1e12
-            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32, "unit": "TFLOP/s", "frac": achieved / fp32,
-                                "traffic": None, "kernel": "clip_kernel", "peak_source": "FMA microbenchmark on this GPU (b200cvt_measure_peaks)",
-                                "fp64_peak": fp64, "frac_fp64": achieved / fp64, "kernel_ms_per_launch": 1e3 * clip_s / n_eval,
-                                "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton},
-                                "share_of_step": cum["clip"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"])}
-            knn_bytes = own * (dim * 8 + 20 * 4 + 4) * n_eval          # read seed, write k indices + count
             peaks = {}
             try:
                 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             except Exception:
                 pass
             hbm = peaks.get("hbm_gbs", 6650.0)
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+            T = int(F.shape[0])
+            # algorithmic bytes per seed-iteration: seed 8D + kNN list 4k + (T/S)(12 idx + 12 adj + 3*8D) + outputs 8(D+1)
+            bytes_unit = 8 * dim + 4 * 20 + (T / S) * (24 + 24 * dim) + 8 * (dim + 1)
+            n_launch = max(cum["evals"], 1)
+            clip_ms = cum["clip_kernel"] / n_launch
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clip_cut_kernel")
+            except Exception:
+                pass
+            ach = bytes_unit * own / (clip_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+                                "kernel": "clip_cut_kernel", "peak_source": peak_src, "kernel_ms_per_launch": clip_ms,
+                                "algorithmic_bytes_per_seed_iteration": bytes_unit, "units_per_launch": own,
+                                "share_of_step": cum["clip_kernel"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"]),
+                                "note": "FP64 geometry: the kernel is bound by FP64/issue rate, not HBM; see roofline_flops"}
+            states = [X, x_final]
+            if args.small or not args.no_cpu_baseline:
+                f_lloyd = algorithmic_flops_per_seed_iteration(V, F, states, False)
+                f_newton = algorithmic_flops_per_seed_iteration(V, F, [x_final], True)
+            else:
+                f_lloyd, f_newton = 10400.0, 10670.0
+            n_newton = n_eval - LLOYD_ITERS
+            flops_step = own * (LLOYD_ITERS * f_lloyd + n_newton * f_newton)
+            tf = flops_step / (cum["clip_kernel"] * 1e-3 / args.steps) / 1e12
+            tf_phase = flops_step / (cum["clip"] * 1e-3 / args.steps) / 1e12
+            line["roofline_flops"] = {"kernel": "clip_cut_kernel", "achieved": tf, "unit": "TFLOP/s", "fp32_peak": fp32, "fp64_peak": fp64,
+                                      "frac_fp32": tf / fp32, "frac_fp64": tf / fp64, "achieved_whole_clip_phase": tf_phase,
+                                      "peak_source": "FMA microbenchmark on this GPU (b200cvt_measure_peaks), non-tensor",
+                                      "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton}}
+            knn_bytes = S * (dim * 8 + 20 * 4 + 4) * n_eval          # read seed, write k indices + count (every rank: all seeds)
             knn_gbs = knn_bytes / (cum["knn"] * 1e-3 / args.steps) / 1e9
             line["roofline_knn"] = {"bound": "hbm", "achieved": knn_gbs, "peak": hbm, "unit": "GB/s", "frac": knn_gbs / hbm,
-                                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "copy_gbs_here": copy, "traffic": None}
-            line["phase_ms_per_evaluation"] = {k: cum[k] / max(cum["evals"], 1) for k in ("sort", "knn", "pairs", "clip")}
+                                    "peak_source": peak_src, "copy_gbs_here": copy, "traffic": None}
+            line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
         except Exception as ex_:   # the bench value stands even if the roofline leg fails
             line["roofline"] = {"error": str(ex_)}
         # CPU baseline on the host cores, bounded sample of the same workload

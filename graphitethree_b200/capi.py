@@ -237,10 +237,10 @@ class Handle:
         _check(lib().b200cvt_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     def cumulative(self, reset=False):
-        ms = np.zeros(4)
+        ms = np.zeros(6)
         n = C.c_uint64(0)
         _check(lib().b200cvt_get_cumulative(self._h, ms.ctypes.data_as(_dp), C.byref(n), int(reset)))
-        return dict(sort=ms[0], knn=ms[1], pairs=ms[2], clip=ms[3], evals=int(n.value))
+        return dict(sort=ms[0], knn=ms[1], pairs=ms[2], clip=ms[3], clip_kernel=ms[4], evals=int(n.value))
 
     def launch_count(self):
         return int(lib().b200cvt_launch_count(self._h))

@@ -236,10 +236,11 @@ struct b200cvt_ctx {
     DevBuf<LbfgsScalars> lb_sc;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evk[2] = {nullptr, nullptr};   // around the clip kernel alone (roofline of the dominant kernel)
     bool ev_valid = false;
     u64 host_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool ev_pending = false;          // phase events recorded but not yet accumulated
-    double cum_ms[5] = {0, 0, 0, 0, 0};  // sort+grid, kNN, pairs, clip(+redo), evaluations
+    double cum_ms[6] = {0, 0, 0, 0, 0, 0};  // sort+grid, kNN+bisectors, pairs, clip phase (+redo), clip kernel alone, -
     u64 cum_evals = 0;
 
     u32 slice_len() const { return (S + nranks - 1) / nranks; }
@@ -279,6 +280,8 @@ static void sync_stream(b200cvt_ctx* h) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->cum_ms[i] += t;
         }
+        float tk = 0.f;
+        if (h->evk[0] && cudaEventElapsedTime(&tk, h->evk[0], h->evk[1]) == cudaSuccess) h->cum_ms[4] += tk;
         h->cum_evals++;
         h->ev_pending = false;
     }
@@ -488,7 +491,11 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
     if (h->volumetric) throw ArgError("volumetric evaluation is not available in this build");
     const u32 S = h->S;
-    if (!h->ev[0]) for (int i = 0; i < 6; ++i) { CUDA_CHECK(cudaEventCreate(&h->ev[i])); CUDA_CHECK(cudaEventRecord(h->ev[i], h->stream)); }
+    if (!h->ev[0]) {
+        for (int i = 0; i < 6; ++i) { CUDA_CHECK(cudaEventCreate(&h->ev[i])); CUDA_CHECK(cudaEventRecord(h->ev[i], h->stream)); }
+        for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&h->evk[i]));
+    }
+    for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventRecord(h->evk[i], h->stream));
     CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
     if (!h->grid_valid) build_grid(h);
     CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
@@ -543,6 +550,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         const int VW = D + (h->weighted ? 1 : 0);
         const size_t smem = (size_t)CLIPF_WARPS * CLIPF_MAXV * VW * 32 * sizeof(double);
         const u32 blocks = div_up(np, CLIPF_WARPS * 32);
+        CUDA_CHECK(cudaEventRecord(h->evk[0], h->stream));
         if (h->weighted) {
             CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH(h, (clip_cut_kernel<D, true>), blocks, CLIPF_WARPS * 32, smem, fa);
@@ -550,6 +558,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
             CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH(h, (clip_cut_kernel<D, false>), blocks, CLIPF_WARPS * 32, smem, fa);
         }
+        CUDA_CHECK(cudaEventRecord(h->evk[1], h->stream));
     }
     ClipArgs c;
     memset(&c, 0, sizeof(c));
@@ -569,7 +578,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         ra.out_s = h->out_s.p; ra.out_v = h->out_v.p; ra.flags = h->flags.p;
         ra.slow_list = h->slow_list.p; ra.slow_n = h->redo_n.p + 2;
         ra.redo_list = h->redo_a.p; ra.redo_n = h->redo_n.p;
-        LAUNCH(h, reduce_pairs_kernel<D>, div_up(nown, 256), 256, 0, ra);
+        LAUNCH(h, reduce_pairs_kernel<D>, div_up(nown, 8), 256, 0, ra);
         // seeds with a pair the in-place fast path gave up on: warp-per-seed kernel, same neighbour table
         ClipArgs sl = c;
         sl.seed_list = h->slow_list.p; sl.nseeds = 0; sl.nseeds_dev = h->redo_n.p + 2;
@@ -812,6 +821,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; ++i) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1147,9 +1157,9 @@ int b200cvt_get_cumulative(b200cvt_handle h, double* ms_out, uint64_t* evals_out
         if (!h || !ms_out) throw ArgError("null argument");
         CUDA_CHECK(cudaSetDevice(h->device));
         sync_stream(h);
-        for (int i = 0; i < 4; ++i) ms_out[i] = h->cum_ms[i];
+        for (int i = 0; i < 6; ++i) ms_out[i] = h->cum_ms[i];
         if (evals_out) *evals_out = h->cum_evals;
-        if (reset) { for (int i = 0; i < 5; ++i) h->cum_ms[i] = 0.0; h->cum_evals = 0; }
+        if (reset) { for (int i = 0; i < 6; ++i) h->cum_ms[i] = 0.0; h->cum_evals = 0; }
     });
 }
 

@@ -298,7 +298,13 @@ clip_cut_kernel(ClipFlatArgs a) {
         while (mask) {
             const int jj = __ffs(mask) - 1;
             mask &= mask - 1;
-            const double* pl = prow + (size_t)jj * PS;
+            double2 rowbuf[PS / 2];
+            {
+                const double2* r2 = (const double2*)(prow + (size_t)jj * PS);
+#pragma unroll
+                for (int q = 0; q < PS / 2; ++q) rowbuf[q] = __ldg(r2 + q);
+            }
+            const double* pl = (const double*)rowbuf;
             if (pl[D + 1] > 4.1 * R2) { sr_ok = true; break; }
             last_jj = jj;
             ++st_planes;
@@ -461,10 +467,12 @@ struct ReduceArgs {
     u32* redo_list; u32* redo_n;     // seeds whose neighbour list must grow (check_SR)
 };
 
+// one warp per seed: lanes take the seed's pairs round-robin (in facet order), then a fixed xor tree
 template <int D>
 __global__ void __launch_bounds__(256)
 reduce_pairs_kernel(ReduceArgs a) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= a.nown) return;
     const u32 s = a.qbegin + i;
     const u32 b = a.pair_off[i], e = a.pair_off[i + 1];
@@ -472,12 +480,18 @@ reduce_pairs_kernel(ReduceArgs a) {
 #pragma unroll
     for (int c = 0; c < D; ++c) acc_v[c] = 0.0;
     u32 ps = 0;
-    for (u32 t = b; t < e; ++t) {
+    for (u32 t = b + lane; t < e; t += 32) {
         acc_s += a.contrib[t];
 #pragma unroll
         for (int c = 0; c < D; ++c) acc_v[c] += a.contrib[(size_t)(c + 1) * a.cstride + t];
         ps |= a.pstat[t];
     }
+    acc_s = warp_sum(acc_s);
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc_v[c] = warp_sum(acc_v[c]);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) ps |= __shfl_xor_sync(B200_FULL, ps, m);
+    if (lane != 0) return;
     a.out_s[s] = acc_s;
 #pragma unroll
     for (int c = 0; c < D; ++c) a.out_v[(size_t)s * D + c] = acc_v[c];

@@ -67,8 +67,22 @@ __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2
     u32 mask = 0, cm = 0;
     bool emp = false;
     if (HOME) *hop = -1;
+    // one bisector row = PS doubles, fetched as 16-byte vectors; the next row is requested before this one is used
+    double2 rowbuf[PS / 2], nextbuf[PS / 2];
+    if (nn > 0) {
+        const double2* r2 = (const double2*)prow;
+#pragma unroll
+        for (int q = 0; q < PS / 2; ++q) nextbuf[q] = __ldg(r2 + q);
+    }
     for (u32 jj = 0; jj < nn; ++jj) {
-        const double* pl = prow + (size_t)jj * PS;
+#pragma unroll
+        for (int q = 0; q < PS / 2; ++q) rowbuf[q] = nextbuf[q];
+        if (jj + 1 < nn) {
+            const double2* r2 = (const double2*)(prow + (size_t)(jj + 1) * PS);
+#pragma unroll
+            for (int q = 0; q < PS / 2; ++q) nextbuf[q] = __ldg(r2 + q);
+        }
+        const double* pl = (const double*)rowbuf;
         const double dij = pl[D + 1];
         // radius test on the unclipped facet (generic_RVD.h:2155-2174): clipping only shrinks R2, so every
         // bisector the reference tests is visited
