@@ -152,6 +152,42 @@ __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u3
     if (flags_out) flags_out[o] = flags[s];
 }
 
+// Sharded runs. cellflag[c] = 1: an owned seed lies in cell c or one of its 26 neighbours (facets to look at);
+// cellflag[ncells + c] = 1: within two cells (seeds whose neighbour lists and bisector rows are needed).
+// One thread per owned seed that is the first of its cell.
+__global__ void mark_cells_kernel(const u32* sorted_keys, u32 qbegin, u32 qend, GridParams g, uint8_t* cellflag) {
+    const u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= qend) return;
+    const u32 key = sorted_keys[s];
+    if (s > qbegin && sorted_keys[s - 1] == key) return;
+    // decode the Morton cell id
+    int c[3] = {0, 0, 0};
+    int in = 0;
+    for (int b = 0; b < 11; ++b)
+        for (int ax = 0; ax < 3; ++ax)
+            if (b < g.bits[ax]) { c[ax] |= (int)((key >> in) & 1u) << b; ++in; }
+    for (int dz = -2; dz <= 2; ++dz) {
+        const int cz = c[2] + dz; if (cz < 0 || cz >= g.res[2]) continue;
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int cy = c[1] + dy; if (cy < 0 || cy >= g.res[1]) continue;
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int cx = c[0] + dx; if (cx < 0 || cx >= g.res[0]) continue;
+                const bool near1 = dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1;
+                const u32 cid = morton_encode(g, cx, cy, cz);
+                // two byte planes ([0, ncells) = one cell away, [ncells, 2 ncells) = two cells away): every writer
+                // stores the same value 1, so concurrent writes are harmless
+                if (near1) cellflag[cid] = 1;
+                cellflag[(size_t)g.ncells + cid] = 1;
+            }
+        }
+    }
+}
+
+__global__ void need_flags_kernel(const u32* sorted_keys, u32 S, const uint8_t* cellflag, uint8_t* has_planes) {
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) has_planes[s] = cellflag[sorted_keys[s]];
+}
+
 __global__ void iota_u32_kernel(u32* p, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (u32)i;
 }
@@ -201,6 +237,8 @@ struct b200cvt_ctx {
     // kNN
     u32 k = 20, kstride = 20;
     bool knn_valid = false;
+    DevBuf<uint8_t> cellflag, has_planes;   // sharded runs only
+    DevBuf<u32> need_list, need_n;
     DevBuf<u32> nbr, nbr_n, nbr_prev;   // nbr_prev: lists of the previous evaluation, original indices, rows by original index
     bool prev_valid = false;
     DevBuf<double> sqd;
@@ -444,7 +482,8 @@ static void run_pairs_t(b200cvt_ctx* h) {
         FacetPairArgs a;
         memset(&a, 0, sizeof(a));
         a.tri = h->tri.p; a.T = h->T; a.xs = h->xs.p; a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.kstride = h->kstride;
-        a.planes = h->planes.p; a.has_planes = nullptr; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+        a.planes = h->planes.p; a.has_planes = h->nranks > 1 ? h->has_planes.p : nullptr;
+        a.cellflag = h->nranks > 1 ? h->cellflag.p : nullptr; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
         a.facet_guess = h->facet_guess.p; a.S = S; a.qbegin = h->qbegin(); a.qend = h->qend();
         a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.pair_mask = h->pair_mask.p; a.cap = h->pair_cap;
         a.max_cnt = h->max_cnt.p; a.stats = h->want_stats ? h->stats.p : nullptr; a.g = h->g;
@@ -499,11 +538,46 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
     if (!h->grid_valid) build_grid(h);
     CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
-    // neighbour lists + bisector tables of every seed (the facet walk may visit any seed)
-    if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true);
     h->planes.ensure((size_t)S * h->kstride * PLANE_STRIDE(D));
-    LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
-           h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, h->planes.p);
+    if (h->nranks == 1) {
+        // neighbour lists + bisector tables of every seed (the facet walk may visit any seed)
+        if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true);
+        LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
+               h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, (const u32*)nullptr, h->planes.p);
+    } else {
+        // sharded: only the seeds within two grid cells of the owned Morton range get lists and bisector rows
+        const u32 nown0 = h->qend() - h->qbegin();
+        h->cellflag.ensure((size_t)h->g.ncells * 2); h->has_planes.ensure(S); h->need_list.ensure(S); h->need_n.ensure(1);
+        h->iota.ensure(S);
+        if (h->iota_filled < h->iota.cap) {
+            LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
+            h->iota_filled = h->iota.cap;
+        }
+        CUDA_CHECK(cudaMemsetAsync(h->cellflag.p, 0, (size_t)h->g.ncells * 2, h->stream));
+        if (nown0 > 0) LAUNCH(h, mark_cells_kernel, div_up(nown0, 256), 256, 0, h->keys2.p, h->qbegin(), h->qend(), h->g, h->cellflag.p);
+        LAUNCH(h, need_flags_kernel, div_up(S, 256), 256, 0, h->keys2.p, S, h->cellflag.p + h->g.ncells, h->has_planes.p);
+        size_t sel_bytes = 0;
+        cub::DeviceSelect::Flagged(nullptr, sel_bytes, h->iota.p, h->has_planes.p, h->need_list.p, h->need_n.p, (int)S, h->stream);
+        h->sort_tmp.ensure(sel_bytes);
+        CUDA_CHECK(cub::DeviceSelect::Flagged(h->sort_tmp.p, sel_bytes, h->iota.p, h->has_planes.p, h->need_list.p, h->need_n.p, (int)S, h->stream));
+        h->launches += 2;
+        h->k = 20; h->kstride = 20;
+        h->nbr.ensure((size_t)S * h->kstride); h->nbr_n.ensure(S); h->nbr_prev.ensure((size_t)S * 20);
+        KnnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+        a.query_list = h->need_list.p; a.nq_dev = h->need_n.p; a.ksize = nullptr; a.out_by_slot = 0;
+        a.k = 20; a.kstride = 20; a.S = S; a.qbegin = 0; a.qend = S;
+        a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+        // previous lists are kept per original seed; seeds that were outside the halo last time hold stale but
+        // still valid bounds (any 20 other seeds bound the 20th distance), so they stay usable once written
+        if (!h->prev_valid) CUDA_CHECK(cudaMemsetAsync(h->nbr_prev.p, 0xff, sizeof(u32) * (size_t)S * 20, h->stream));
+        a.prev_in = h->nbr_prev.p; a.prev_out = h->nbr_prev.p; a.prev_stride = 20;
+        launch_knn<D>(h, a, S);
+        h->prev_valid = true; h->knn_valid = true;
+        LAUNCH(h, plane_table_kernel<D>, (u32)h->num_sms * 16u, 256, 0,
+               h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, h->need_list.p, 0u, S, h->need_n.p, h->planes.p);
+    }
     CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
     h->stats.ensure(16);
     if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -817,7 +891,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
     h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release(); h->pclass.release(); h->pclass_sorted.release();
-    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
+    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

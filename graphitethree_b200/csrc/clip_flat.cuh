@@ -201,9 +201,10 @@ __global__ void facet_area_kernel(const double* tri, u32 T, double* area) {
 template <int D>
 __global__ void __launch_bounds__(256)
 plane_table_kernel(const void* xs_, const u32* nbr, const u32* nbr_n, u32 kstride, const u32* seed_list, u32 qbegin, u32 nseeds,
-                   double* planes) {
+                   const u32* nseeds_dev, double* planes) {
     constexpr int PS = PLANE_STRIDE(D);
     const SeedRec<D>* xs = (const SeedRec<D>*)xs_;
+    if (nseeds_dev) nseeds = *nseeds_dev;
     const size_t total = (size_t)nseeds * kstride;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const u32 i = (u32)(e / kstride), jj = (u32)(e - (size_t)i * kstride);

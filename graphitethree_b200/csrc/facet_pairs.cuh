@@ -36,6 +36,7 @@ struct FacetPairArgs {
     const u32* nbr; const u32* nbr_n; u32 kstride;
     const double* planes;     // [S][kstride][PLANE_STRIDE]
     const uint8_t* has_planes; // optional [S]: 1 if the seed's rows of nbr/planes are valid (sharded runs)
+    const uint8_t* cellflag;   // optional [ncells]: 1 = an owned seed lies in the cell or one of its 26 neighbours
     const uint2* cell_range;
     const u32* rank_of;
     u32* facet_guess;         // [T] original index of the last home seed (B200_NONE: none)
@@ -180,19 +181,30 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             vmax2 = fmax(vmax2, q2);
         }
         // home seed: previous answer (or a grid search), then hops while a listed neighbour is closer to the centroid
+        bool relevant = true;
         {
+            double gc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
             const u32 guess = a.facet_guess[f];
             if (guess != B200_NONE) s0 = a.rank_of[guess];
-            else {
-                double gc[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
-                s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
+            else s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
+            if (a.cellflag) {
+                // sharded run: a seed s whose cell meets the facet lies within 2 rho + delta of the centroid g
+                // (rho = facet radius about g, delta = distance from g to ANY seed, here the previous home).
+                // If that ball fits in the 27 cells around g's cell and none of them holds an owned seed,
+                // this rank has nothing to do with the facet.
+                const double rho = sqrt(fmax(fmax(dist2<D>(gc, v[0]), dist2<D>(gc, v[1])), dist2<D>(gc, v[2])));
+                const double R = (2.0 * rho + sqrt(dist2<D>(gc, xs[s0].p))) * (1.0 + 1e-9);
+                if (R <= a.g.h) {
+                    const u32 cid = morton_encode(a.g, grid_coord(a.g, gc[0], 0), grid_coord(a.g, gc[1], 1), grid_coord(a.g, gc[2], 2));
+                    relevant = a.cellflag[cid] != 0;
+                }
             }
         }
         bool certified = false, empty0 = false;
         u32 mask0 = 0;
-        for (int it = 0; it < 32; ++it) {
+        for (int it = 0; relevant && it < 32; ++it) {
             if (a.has_planes && !a.has_planes[s0]) break;
             double p0[D];
 #pragma unroll
@@ -206,7 +218,9 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             certified = (mask0 & PMASK_SR_OK) || (nn0 + 1 >= a.S);
             break;
         }
-        if (certified) {
+        if (!relevant) {
+            cand = 0;
+        } else if (certified) {
             a.facet_guess[f] = (u32)xs[s0].orig;
             if (!empty0) emit_pair<D>(a, s0, f, mask0);
         } else {

@@ -90,6 +90,7 @@ struct KnnArgs {
     const uint2* cell_range; // [ncells] (start, end) in sorted positions
     const u32* rank_of;      // orig -> sorted position
     const u32* query_list;   // optional: sorted positions to process (NULL: [qbegin, qend))
+    const u32* nq_dev;       // optional: number of entries of query_list, read from device memory
     const u32* ksize;        // per ORIGINAL seed list size (NULL: k)
     int out_by_slot;         // write row qi (position in query_list) instead of row q
     u32 k;                   // default list size
@@ -118,7 +119,7 @@ knn_kernel(KnnArgs a) {
     u32* cand = s_cand[w];
     u64* bufd = s_bufd[w];
     u32* bufi = s_bufi[w];
-    const u32 nq = a.qend - a.qbegin;
+    const u32 nq = a.nq_dev ? *a.nq_dev : a.qend - a.qbegin;
     for (u32 qi = blockIdx.x * KNN_WARPS + w; qi < nq; qi += gridDim.x * KNN_WARPS) {
         const u32 q = a.query_list ? a.query_list[qi] : a.qbegin + qi;
         double pq[D];
