@@ -202,7 +202,7 @@ def main():
     ex = None
     if world > 1:
         with torch.cuda.stream(stream):
-            ex = sharding.TorchExchange(dim, S, rank, world, torch.device("cuda", local_rank))
+            ex = sharding.TorchExchange(dim, S, rank, world, torch.device("cuda", local_rank), sync=False)
 
             def exchange():
                 with torch.cuda.stream(stream):

@@ -152,8 +152,8 @@ __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u3
     if (flags_out) flags_out[o] = flags[s];
 }
 
-// Sharded runs. cellflag[c] = 1: an owned seed lies in cell c or one of its 26 neighbours (facets to look at);
-// cellflag[ncells + c] = 1: within two cells (seeds whose neighbour lists and bisector rows are needed).
+// Sharded runs. cellflag[(m-1) * ncells + c] = 1: an owned seed lies within m cells of cell c, m = 1, 2, 3
+// (facet filter); seeds within two cells get neighbour lists and bisector rows.
 // One thread per owned seed that is the first of its cell.
 __global__ void mark_cells_kernel(const u32* sorted_keys, u32 qbegin, u32 qend, GridParams g, uint8_t* cellflag) {
     const u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,18 +166,19 @@ __global__ void mark_cells_kernel(const u32* sorted_keys, u32 qbegin, u32 qend, 
     for (int b = 0; b < 11; ++b)
         for (int ax = 0; ax < 3; ++ax)
             if (b < g.bits[ax]) { c[ax] |= (int)((key >> in) & 1u) << b; ++in; }
-    for (int dz = -2; dz <= 2; ++dz) {
+    for (int dz = -3; dz <= 3; ++dz) {
         const int cz = c[2] + dz; if (cz < 0 || cz >= g.res[2]) continue;
-        for (int dy = -2; dy <= 2; ++dy) {
+        for (int dy = -3; dy <= 3; ++dy) {
             const int cy = c[1] + dy; if (cy < 0 || cy >= g.res[1]) continue;
-            for (int dx = -2; dx <= 2; ++dx) {
+            for (int dx = -3; dx <= 3; ++dx) {
                 const int cx = c[0] + dx; if (cx < 0 || cx >= g.res[0]) continue;
-                const bool near1 = dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1;
+                const int m = max(max(abs(dx), abs(dy)), abs(dz));
                 const u32 cid = morton_encode(g, cx, cy, cz);
-                // two byte planes ([0, ncells) = one cell away, [ncells, 2 ncells) = two cells away): every writer
-                // stores the same value 1, so concurrent writes are harmless
-                if (near1) cellflag[cid] = 1;
-                cellflag[(size_t)g.ncells + cid] = 1;
+                // three byte planes (within one / two / three cells): every writer stores the same value 1, so
+                // concurrent writes are harmless
+                if (m <= 1) cellflag[cid] = 1;
+                if (m <= 2) cellflag[(size_t)g.ncells + cid] = 1;
+                cellflag[2 * (size_t)g.ncells + cid] = 1;
             }
         }
     }
@@ -232,12 +233,14 @@ struct b200cvt_ctx {
     DevBuf<unsigned char> xs;         // SeedRec<D>[S]
     DevBuf<u32> rank_of;
     DevBuf<uint2> cell_range;
-    GridParams g;
+    GridParams g, g_prev;
     DevBuf<u32> mtab; int mtab_bits[3] = {-1, -1, -1};
     // kNN
     u32 k = 20, kstride = 20;
     bool knn_valid = false;
     DevBuf<uint8_t> cellflag, has_planes;   // sharded runs only
+    DevBuf<float4> facet_ball; DevBuf<u32> facet_cell, facet_list, facet_list_n;
+    bool facet_cell_valid = false;
     DevBuf<u32> need_list, need_n;
     DevBuf<u32> nbr, nbr_n, nbr_prev;   // nbr_prev: lists of the previous evaluation, original indices, rows by original index
     bool prev_valid = false;
@@ -376,6 +379,7 @@ static void choose_grid(b200cvt_ctx* h, const double lo[3], const double hi[3]) 
         for (int a = 0; a < 3; ++a) h->mtab_bits[a] = g.bits[a];
     }
     g.mtab = h->mtab.p;
+    if (memcmp(&g, &h->g_prev, sizeof(GridParams)) != 0) { h->facet_cell_valid = false; h->g_prev = g; }
 }
 
 template <int D>
@@ -483,12 +487,27 @@ static void run_pairs_t(b200cvt_ctx* h) {
         memset(&a, 0, sizeof(a));
         a.tri = h->tri.p; a.T = h->T; a.xs = h->xs.p; a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.kstride = h->kstride;
         a.planes = h->planes.p; a.has_planes = h->nranks > 1 ? h->has_planes.p : nullptr;
-        a.cellflag = h->nranks > 1 ? h->cellflag.p : nullptr; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+        a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
         a.facet_guess = h->facet_guess.p; a.S = S; a.qbegin = h->qbegin(); a.qend = h->qend();
         a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.pair_mask = h->pair_mask.p; a.cap = h->pair_cap;
         a.max_cnt = h->max_cnt.p; a.stats = h->want_stats ? h->stats.p : nullptr; a.g = h->g;
         h->tasks.ensure(std::max<size_t>((size_t)h->T * 2, 1024));
         a.tasks = h->tasks.p; a.task_cap = (u32)std::min<size_t>(h->tasks.cap, 0xffffffffu); a.task_n = h->max_cnt.p + 1;
+        if (h->T > 0 && h->nranks > 1) {
+            // the facets that can meet the cell of an owned seed
+            h->facet_cell.ensure(h->T); h->facet_list.ensure(h->T); h->facet_list_n.ensure(1);
+            if (!h->facet_cell_valid) {
+                LAUNCH(h, facet_cell_kernel<D>, div_up(h->T, 256), 256, 0, h->tri.p, h->T, h->g, h->facet_cell.p);
+                h->facet_cell_valid = true;
+            }
+            CUDA_CHECK(cudaMemsetAsync(h->facet_list_n.p, 0, sizeof(u32), h->stream));
+            FacetFilterArgs fl;
+            fl.ball = h->facet_ball.p; fl.facet_cell = h->facet_cell.p; fl.T = h->T; fl.cellflag = h->cellflag.p;
+            fl.cell_range = h->cell_range.p; fl.facet_guess = h->facet_guess.p; fl.rank_of = h->rank_of.p; fl.xs = h->xs.p;
+            fl.g = h->g; fl.list = h->facet_list.p; fl.list_n = h->facet_list_n.p;
+            LAUNCH(h, facet_filter_kernel<D>, div_up(h->T, 256), 256, 0, fl);
+            a.facet_list = h->facet_list.p; a.facet_list_n = h->facet_list_n.p;
+        }
         if (h->T > 0) {
             LAUNCH(h, facet_home_kernel<D>, div_up(h->T, 128), 128, 0, a);
             LAUNCH(h, facet_task_kernel<D>, (u32)h->num_sms * 8u, 128, 0, a);
@@ -547,13 +566,13 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     } else {
         // sharded: only the seeds within two grid cells of the owned Morton range get lists and bisector rows
         const u32 nown0 = h->qend() - h->qbegin();
-        h->cellflag.ensure((size_t)h->g.ncells * 2); h->has_planes.ensure(S); h->need_list.ensure(S); h->need_n.ensure(1);
+        h->cellflag.ensure((size_t)h->g.ncells * 3); h->has_planes.ensure(S); h->need_list.ensure(S); h->need_n.ensure(1);
         h->iota.ensure(S);
         if (h->iota_filled < h->iota.cap) {
             LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
             h->iota_filled = h->iota.cap;
         }
-        CUDA_CHECK(cudaMemsetAsync(h->cellflag.p, 0, (size_t)h->g.ncells * 2, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->cellflag.p, 0, (size_t)h->g.ncells * 3, h->stream));
         if (nown0 > 0) LAUNCH(h, mark_cells_kernel, div_up(nown0, 256), 256, 0, h->keys2.p, h->qbegin(), h->qend(), h->g, h->cellflag.p);
         LAUNCH(h, need_flags_kernel, div_up(S, 256), 256, 0, h->keys2.p, S, h->cellflag.p + h->g.ncells, h->has_planes.p);
         size_t sel_bytes = 0;
@@ -742,7 +761,9 @@ static void set_seeds_common(b200cvt_ctx* h, u32 S) {
 static void run_exchange(b200cvt_ctx* h) {
     if (!h->xcb || !h->x_slice || !h->x_all) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
     if (h->x_chunk < (u64)h->slice_len() * (h->dim + 1)) throw ArgError("exchange buffers too small");
-    sync_stream(h);
+    // the callback enqueues the all-gather on the handle's stream when the caller supplied it (b200cvt_set_stream);
+    // with a private stream the library has to drain it first and the callback must return with the data in place
+    if (h->own_stream) sync_stream(h);
     if (h->xcb(h->xuser) != 0) throw std::runtime_error("exchange callback failed");
     h->exchanges++;
 }
@@ -891,7 +912,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
     h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release(); h->pclass.release(); h->pclass_sorted.release();
-    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
+    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -971,6 +992,11 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         }
         h->facet_guess.ensure(ne);
         LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)ne, B200_NONE);
+        h->facet_ball.ensure(ne); h->facet_cell_valid = false;
+        if (ne > 0) {
+            if (D == 3) LAUNCH(h, facet_ball_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+            else LAUNCH(h, facet_ball_kernel<6>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+        }
         h->facet_area.ensure(ne);
         if (ne > 0) {
             if (D == 3) LAUNCH(h, facet_area_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);

@@ -36,7 +36,7 @@ struct FacetPairArgs {
     const u32* nbr; const u32* nbr_n; u32 kstride;
     const double* planes;     // [S][kstride][PLANE_STRIDE]
     const uint8_t* has_planes; // optional [S]: 1 if the seed's rows of nbr/planes are valid (sharded runs)
-    const uint8_t* cellflag;   // optional [ncells]: 1 = an owned seed lies in the cell or one of its 26 neighbours
+    const u32* facet_list; const u32* facet_list_n;   // optional: the facets to process (sharded runs), count on the device
     const uint2* cell_range;
     const u32* rank_of;
     u32* facet_guess;         // [T] original index of the last home seed (B200_NONE: none)
@@ -165,11 +165,13 @@ template <int D>
 __global__ void __launch_bounds__(128, 4)
 facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
     constexpr int PS = PLANE_STRIDE(D);
-    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
     u32 cand = 0, s0 = 0;
-    if (f < a.T) {
+    const u32 nf = a.facet_list ? *a.facet_list_n : a.T;
+    const u32 f = (e < nf) ? (a.facet_list ? a.facet_list[e] : e) : 0u;
+    if (e < nf) {
         double v[3][D];
         const double* t = a.tri + (size_t)f * 3 * D;
         double vmax2 = 0.0;
@@ -181,7 +183,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             vmax2 = fmax(vmax2, q2);
         }
         // home seed: previous answer (or a grid search), then hops while a listed neighbour is closer to the centroid
-        bool relevant = true;
+        const bool relevant = true;
         {
             double gc[D];
 #pragma unroll
@@ -189,18 +191,6 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             const u32 guess = a.facet_guess[f];
             if (guess != B200_NONE) s0 = a.rank_of[guess];
             else s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
-            if (a.cellflag) {
-                // sharded run: a seed s whose cell meets the facet lies within 2 rho + delta of the centroid g
-                // (rho = facet radius about g, delta = distance from g to ANY seed, here the previous home).
-                // If that ball fits in the 27 cells around g's cell and none of them holds an owned seed,
-                // this rank has nothing to do with the facet.
-                const double rho = sqrt(fmax(fmax(dist2<D>(gc, v[0]), dist2<D>(gc, v[1])), dist2<D>(gc, v[2])));
-                const double R = (2.0 * rho + sqrt(dist2<D>(gc, xs[s0].p))) * (1.0 + 1e-9);
-                if (R <= a.g.h) {
-                    const u32 cid = morton_encode(a.g, grid_coord(a.g, gc[0], 0), grid_coord(a.g, gc[1], 1), grid_coord(a.g, gc[2], 2));
-                    relevant = a.cellflag[cid] != 0;
-                }
-            }
         }
         bool certified = false, empty0 = false;
         u32 mask0 = 0;
@@ -292,4 +282,91 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
         const u32 mask = classify_facet<D, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
         if (!empty) emit_pair<D>(a, s, f, mask);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// sharded runs: which facets can meet the cell of an owned seed at all
+// ---------------------------------------------------------------------------------------
+// once per mesh: bounding ball of every facet about its centroid, in float (radius inflated for the rounding)
+template <int D>
+__global__ void facet_ball_kernel(const double* tri, u32 T, float4* ball) {
+    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= T) return;
+    const double* t = tri + (size_t)f * 3 * D;
+    double v[3][D], gc[D];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) v[i][c] = t[i * D + c];
+    double gmax = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) { gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0); gmax = fmax(gmax, fabs(gc[c])); }
+    // the grid lives in the first three coordinates; distances in D dimensions are not smaller
+    double rho = sqrt(fmax(fmax(dist2<D>(gc, v[0]), dist2<D>(gc, v[1])), dist2<D>(gc, v[2])));
+    rho = rho * (1.0 + 1e-6) + 4e-7 * gmax + 1e-30;
+    ball[f] = make_float4((float)gc[0], (float)gc[1], (float)gc[2], __double2float_ru(rho));
+}
+
+// once per grid: the grid cell of every facet centroid
+template <int D>
+__global__ void facet_cell_kernel(const double* tri, u32 T, GridParams g, u32* facet_cell) {
+    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= T) return;
+    const double* t = tri + (size_t)f * 3 * D;
+    double gc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gc[c] = (t[c] + t[D + c] + t[2 * D + c]) * (1.0 / 3.0);
+    facet_cell[f] = morton_encode(g, grid_coord(g, gc[0], 0), grid_coord(g, gc[1], 1), grid_coord(g, gc[2], 2));
+}
+
+struct FacetFilterArgs {
+    const float4* ball; const u32* facet_cell; u32 T;
+    const uint8_t* cellflag;      // [3][ncells]: an owned seed within 1 / 2 / 3 cells
+    const uint2* cell_range;
+    const u32* facet_guess; const u32* rank_of; const void* xs;
+    GridParams g;
+    u32* list; u32* list_n;
+};
+
+// A seed s whose cell meets facet f lies within R = 2 rho + delta of the centroid g (rho = facet radius about g,
+// delta = distance from g to ANY seed). A ball of radius R <= m h about g stays within m cells of g's cell, so
+// the facet is irrelevant to this rank if no owned seed lies within m cells. Level 1 uses static data only
+// (a non-empty home cell bounds delta by sqrt(3) h); level 2 uses the facet's previous home seed.
+template <int D>
+__global__ void __launch_bounds__(256)
+facet_filter_kernel(FacetFilterArgs a) {
+    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool rel = false;
+    if (f < a.T) {
+        const u32 cid = a.facet_cell[f];
+        const float4 b = a.ball[f];
+        const uint8_t* f1 = a.cellflag; const uint8_t* f2 = f1 + a.g.ncells; const uint8_t* f3 = f2 + a.g.ncells;
+        const double h = a.g.h;
+        const uint2 rg = a.cell_range[cid];
+        // (D > 3: the grid only sees the first three coordinates and the float ball only stores those, so neither
+        // bound on delta holds in the facet's own space: every facet stays relevant)
+        if (D > 3) rel = true;
+        else if (!f3[cid] && (double)b.w <= 0.6 * h && rg.y > rg.x) rel = false;
+        else {
+            const u32 guess = a.facet_guess[f];
+            rel = true;
+            if (guess != B200_NONE) {
+                const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+                const SeedRec<D>* r = xs + a.rank_of[guess];
+                const double qx = r->p[0] - (double)b.x, qy = r->p[1] - (double)b.y, qz = r->p[2] - (double)b.z;
+                const double d2 = qx * qx + qy * qy + qz * qz;
+                const double R = (2.0 * (double)b.w + sqrt(d2)) * (1.0 + 1e-6);
+                if (R <= h) rel = f1[cid] != 0;
+                else if (R <= 2.0 * h) rel = f2[cid] != 0;
+                else if (R <= 3.0 * h) rel = f3[cid] != 0;
+            }
+        }
+    }
+    const u32 m = __ballot_sync(B200_FULL, rel);
+    if (m == 0) return;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(a.list_n, (u32)__popc(m));
+    base = __shfl_sync(B200_FULL, base, 0);
+    if (rel) a.list[base + __popc(m & ((1u << lane) - 1u))] = f;
 }

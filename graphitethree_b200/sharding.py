@@ -50,8 +50,11 @@ def unpack_all(all_chunks, S, dim, nranks, order):
 class TorchExchange:
     """The all-gather of the sharded path over torch.distributed (NCCL on GPUs, gloo on CPU)."""
 
-    def __init__(self, dim, S, rank, nranks, device):
+    def __init__(self, dim, S, rank, nranks, device, sync=True):
+        """sync=False: the library runs on torch's current stream (Handle.set_stream), so the collective is
+        ordered on the device and the host does not wait for it."""
         import torch
+        self.sync = sync
         self.torch = torch
         self.chunk = chunk_doubles(dim, S, nranks)
         self.slice = torch.zeros(self.chunk, dtype=torch.float64, device=device)
@@ -62,7 +65,7 @@ class TorchExchange:
     def __call__(self):
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.all, self.slice)
-        if self.all.is_cuda:
+        if self.all.is_cuda and self.sync:
             self.torch.cuda.current_stream().synchronize()
         self.count += 1
         return 0

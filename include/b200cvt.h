@@ -130,8 +130,11 @@ int b200cvt_set_seeds_device(b200cvt_handle h, const double* d_x, uint32_t S);
  * slice. The library packs its slice into d_slice (chunk_doubles doubles: ceil(S/nranks) x dim
  * values, then ceil(S/nranks) scalars), calls cb(user) — which must all-gather d_slice of every
  * rank into d_all (rank-major) on the device, e.g. torch.distributed.all_gather_into_tensor
- * over NCCL, and return 0 once d_all is complete — and unpacks d_all. Both buffers are owned
- * by the caller (torch tensors in bench.py). */
+ * over NCCL, and return 0 — and unpacks d_all. If the caller gave the handle its stream
+ * (b200cvt_set_stream) the callback only has to ENQUEUE the collective so that it is ordered on
+ * that stream (no host synchronisation); with the handle's private stream the library drains it
+ * before the call and d_all must be complete when cb returns. Both buffers are owned by the
+ * caller (torch tensors in bench.py). */
 typedef int (*b200cvt_exchange_cb)(void* user);
 uint64_t b200cvt_exchange_chunk_doubles(int dim, uint32_t S, uint32_t nranks);
 int b200cvt_set_exchange(b200cvt_handle h, double* d_slice, double* d_all, uint64_t chunk_doubles,
