@@ -1,0 +1,225 @@
+/*
+ * dropin_check.cpp — drives the SAME remeshing job twice through the reference's own C++ API:
+ * once with the stock GEO::CentroidalVoronoiTesselation (CPU) and once with
+ * GEO::CentroidalVoronoiTesselationB200 (geogram_b200.h), then compares what BASELINE.json's north_star
+ * asks for: seeds after the Lloyd / Newton iterations, the restricted-Delaunay triangle sets
+ * (CentroidalVoronoiTesselation::compute_surface, i.e. RestrictedVoronoiDiagram::compute_RDT on each run's seeds)
+ * and the two-sided Hausdorff distance between the two remeshes relative to the bounding-box diagonal.
+ *
+ * usage: dropin_check mesh.bin seeds.bin nb_Lloyd nb_Newton m [rvd_only]
+ *   mesh.bin : u32 nv, u32 nf, u32 dim, f64 vertices[nv*dim], u32 triangles[nf*3]
+ *   seeds.bin: u32 S, u32 dim, f64 x[S*dim]
+ * prints one JSON line. Used by tests/test_gpu_dropin.py (GPU box) — test infrastructure around the adapter.
+ */
+#include "geogram_b200.h"
+
+#include <geogram/basic/command_line.h>
+#include <geogram/basic/command_line_args.h>
+#include <geogram/basic/logger.h>
+#include <geogram/basic/process.h>
+#include <geogram/basic/stopwatch.h>
+#include <geogram/mesh/mesh_distance.h>
+#include <geogram/mesh/mesh_geometry.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <type_traits>
+#include <vector>
+
+using namespace GEO;
+
+namespace {
+
+    bool read_all(const char* path, std::vector<unsigned char>& buf) {
+        FILE* f = fopen(path, "rb");
+        if(f == nullptr) {
+            return false;
+        }
+        fseek(f, 0, SEEK_END);
+        long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(size_t(n));
+        bool ok = fread(buf.data(), 1, size_t(n), f) == size_t(n);
+        fclose(f);
+        return ok;
+    }
+
+    void load_mesh(const std::vector<unsigned char>& buf, Mesh& M) {
+        const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf.data());
+        uint32_t nv = hdr[0], nf = hdr[1], dim = hdr[2];
+        const double* V = reinterpret_cast<const double*>(buf.data() + 12);
+        const uint32_t* T = reinterpret_cast<const uint32_t*>(buf.data() + 12 + sizeof(double) * size_t(nv) * dim);
+        M.clear();
+        M.vertices.set_dimension(dim);
+        M.vertices.create_vertices(nv);
+        for(uint32_t v = 0; v < nv; ++v) {
+            for(uint32_t c = 0; c < dim; ++c) {
+                M.vertices.point_ptr(v)[c] = V[size_t(v) * dim + c];
+            }
+        }
+        M.facets.create_triangles(nf);
+        for(uint32_t f = 0; f < nf; ++f) {
+            for(uint32_t lv = 0; lv < 3; ++lv) {
+                M.facets.set_vertex(f, lv, T[size_t(f) * 3 + lv]);
+            }
+        }
+        M.facets.connect();
+    }
+
+    typedef std::array<index_t, 3> Tri;
+
+    /* triangles of RestrictedVoronoiDiagram::compute_RDT in simple mode: indices ARE seed indices (RVD.cpp:2352-2370) */
+    std::set<Tri> triangle_set(const vector<index_t>& tris) {
+        std::set<Tri> s;
+        for(index_t f = 0; f + 2 < tris.size(); f += 3) {
+            Tri t = {{tris[f], tris[f + 1], tris[f + 2]}};
+            /* rotate so that the smallest vertex comes first (orientation kept) */
+            index_t k = index_t(std::min_element(t.begin(), t.end()) - t.begin());
+            Tri r = {{t[k], t[(k + 1) % 3], t[(k + 2) % 3]}};
+            s.insert(r);
+        }
+        return s;
+    }
+
+    struct Run {
+        std::vector<double> x_lloyd, x_final;
+        Mesh surface;
+        vector<index_t> rdt;
+        double t_lloyd = 0.0, t_newton = 0.0;
+        bool on_gpu = false;
+    };
+
+    template <class CVT_T>
+    void run(Mesh& M, index_t S, index_t dim, const double* seeds, index_t nl, index_t nn, index_t m, Run& out) {
+        CVT_T cvt(&M, coord_index_t(dim), "NN");
+        cvt.set_points(S, seeds);
+        double t0 = Stopwatch::now();
+        cvt.Lloyd_iterations(nl);
+        out.t_lloyd = Stopwatch::now() - t0;
+        out.x_lloyd.assign(cvt.embedding(0), cvt.embedding(0) + size_t(S) * dim);
+        if(nn > 0) {
+            t0 = Stopwatch::now();
+            cvt.Newton_iterations(nn, m);
+            out.t_newton = Stopwatch::now() - t0;
+        }
+        out.x_final.assign(cvt.embedding(0), cvt.embedding(0) + size_t(S) * dim);
+        cvt.RVD()->delete_threads();
+        cvt.set_use_RVC_centroids(false);   /* vertices of the remesh = the seeds, so that the triangle sets are comparable */
+        cvt.compute_surface(&out.surface, false);
+        vector<double> emb;
+        cvt.RVD()->compute_RDT(out.rdt, emb, RestrictedVoronoiDiagram::RDTMode(0));
+        if constexpr (std::is_same<CVT_T, CentroidalVoronoiTesselationB200>::value) {
+            out.on_gpu = cvt.last_call_on_gpu();
+        }
+    }
+
+    double max_abs_diff(const std::vector<double>& a, const std::vector<double>& b) {
+        double d = 0.0;
+        for(size_t i = 0; i < a.size(); ++i) {
+            d = std::max(d, std::fabs(a[i] - b[i]));
+        }
+        return d;
+    }
+}
+
+int main(int argc, char** argv) {
+    if(argc < 6) {
+        fprintf(stderr, "usage: %s mesh.bin seeds.bin nb_Lloyd nb_Newton m\n", argv[0]);
+        return 2;
+    }
+    GEO::initialize(GEO::GEOGRAM_INSTALL_NONE);
+    CmdLine::import_arg_group("standard");
+    CmdLine::import_arg_group("algo");
+    CmdLine::import_arg_group("opt");
+    CmdLine::import_arg_group("remesh");
+    CmdLine::set_arg("log:quiet", "true");
+    Logger::instance()->set_quiet(true);
+    b200_register();
+
+    std::vector<unsigned char> mb, sb;
+    if(!read_all(argv[1], mb) || !read_all(argv[2], sb)) {
+        fprintf(stderr, "cannot read inputs\n");
+        return 2;
+    }
+    const index_t nl = index_t(atoi(argv[3])), nn = index_t(atoi(argv[4])), m = index_t(atoi(argv[5]));
+    const uint32_t* sh = reinterpret_cast<const uint32_t*>(sb.data());
+    const index_t S = sh[0], dim = sh[1];
+    const double* seeds = reinterpret_cast<const double*>(sb.data() + 8);
+
+    Run ref, b200;
+    {
+        Mesh M;
+        load_mesh(mb, M);
+        run<CentroidalVoronoiTesselation>(M, S, dim, seeds, nl, nn, m, ref);
+    }
+    {
+        Mesh M;
+        load_mesh(mb, M);
+        try {
+            run<CentroidalVoronoiTesselationB200>(M, S, dim, seeds, nl, nn, m, b200);
+        } catch(const std::exception& e) {
+            printf("{\"error\": \"%s\"}\n", e.what());
+            return 1;
+        }
+    }
+
+    /* the "B200NN" Delaunay backend through the reference factory, compared list by list with "NN" */
+    index_t nn_mismatch = 0, nn_rows = 0;
+    {
+        Delaunay_var d_ref = Delaunay::create(coord_index_t(dim), "NN");
+        Delaunay_var d_gpu = Delaunay::create(coord_index_t(dim), "B200NN");
+        d_ref->set_stores_neighbors(true);
+        d_gpu->set_stores_neighbors(true);
+        d_ref->set_vertices(S, ref.x_lloyd.data());
+        d_gpu->set_vertices(S, ref.x_lloyd.data());
+        vector<index_t> a, b;
+        for(index_t i = 0; i < S; ++i) {
+            d_ref->get_neighbors(i, a);
+            d_gpu->get_neighbors(i, b);
+            ++nn_rows;
+            if(a.size() != b.size() || !std::equal(a.begin(), a.end(), b.begin())) {
+                ++nn_mismatch;
+            }
+        }
+    }
+
+    std::set<Tri> ta = triangle_set(ref.rdt), tb = triangle_set(b200.rdt);
+    size_t only_ref = 0, only_b200 = 0;
+    for(const Tri& t : ta) {
+        if(tb.find(t) == tb.end()) {
+            ++only_ref;
+        }
+    }
+    for(const Tri& t : tb) {
+        if(ta.find(t) == ta.end()) {
+            ++only_b200;
+        }
+    }
+    double diag = bbox_diagonal(ref.surface);
+    double h_ab = 0.0, h_ba = 0.0;
+    if(ref.surface.facets.nb() > 0 && b200.surface.facets.nb() > 0) {
+        double sampling = 0.01 * diag;
+        h_ab = mesh_one_sided_Hausdorff_distance(ref.surface, b200.surface, sampling);
+        h_ba = mesh_one_sided_Hausdorff_distance(b200.surface, ref.surface, sampling);
+    }
+    printf(
+        "{\"seeds\": %u, \"dim\": %u, \"lloyd\": %u, \"newton\": %u, \"on_gpu\": %s, "
+        "\"max_abs_dx_lloyd\": %.3e, \"max_abs_dx_final\": %.3e, "
+        "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
+        "\"ref_vertices\": %u, \"b200_vertices\": %u, "
+        "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"bbox_diagonal\": %.6e, "
+        "\"nn_rows\": %u, \"nn_mismatch\": %u, "
+        "\"t_ref_lloyd\": %.4f, \"t_ref_newton\": %.4f, \"t_b200_lloyd\": %.4f, \"t_b200_newton\": %.4f, \"ref_threads\": %u}\n",
+        S, dim, nl, nn, b200.on_gpu ? "true" : "false",
+        max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
+        ta.size(), tb.size(), only_ref, only_b200,
+        ref.surface.vertices.nb(), b200.surface.vertices.nb(),
+        h_ab, h_ba, diag, nn_rows, nn_mismatch,
+        ref.t_lloyd, ref.t_newton, b200.t_lloyd, b200.t_newton, unsigned(Process::maximum_concurrent_threads())
+    );
+    return 0;
+}

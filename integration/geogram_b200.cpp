@@ -1,0 +1,448 @@
+/*
+ * geogram_b200.cpp — adapter classes of geogram_b200.h over the C-ABI (include/b200cvt.h).
+ * See INTEGRATION.md. Host-side glue only: no geometry is computed here.
+ */
+#include "geogram_b200.h"
+
+#include <geogram/basic/command_line.h>
+#include <geogram/basic/logger.h>
+#include <geogram/basic/progress.h>
+#include <geogram/basic/stopwatch.h>
+#include <geogram/mesh/mesh_remesh.h>
+
+#include <stdexcept>
+#include <vector>
+
+namespace {
+
+    using namespace GEO;
+
+    /* precondition failures of the reference are geo_assert(); here the C-ABI reports them as a status */
+    void check(int status, const char* what) {
+        if(status == B200CVT_OK) {
+            return;
+        }
+        if(status == B200CVT_ERR_CANCELED) {
+            throw TaskCanceled();
+        }
+        std::string msg = std::string(what) + ": " + b200cvt_last_error();
+        Logger::err("B200") << msg << std::endl;
+        throw std::runtime_error(msg);
+    }
+
+    unsigned long long hash_bytes(unsigned long long h, const void* p, size_t n) {
+        /* word-wise multiply-xorshift: only used to notice that the caller edited the mesh */
+        const unsigned long long* w = static_cast<const unsigned long long*>(p);
+        size_t nw = n / 8;
+        for(size_t i = 0; i < nw; ++i) {
+            h = (h ^ w[i]) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+        }
+        const unsigned char* b = static_cast<const unsigned char*>(p) + nw * 8;
+        for(size_t i = 0; i < n % 8; ++i) {
+            h = (h ^ b[i]) * 0x100000001B3ull;
+        }
+        return h;
+    }
+}
+
+namespace GEO {
+
+    /************************ Delaunay backend ************************/
+
+    Delaunay_B200NN::Delaunay_B200NN(coord_index_t dimension) :
+        Delaunay_NearestNeighbors(dimension), h_(nullptr), tree_valid_(false) {
+        check(b200cvt_create(-1, int(dimension), 0, &h_), "b200cvt_create");
+    }
+
+    Delaunay_B200NN::~Delaunay_B200NN() {
+        b200cvt_destroy(h_);
+    }
+
+    void Delaunay_B200NN::set_vertices(index_t nb_vertices, const double* vertices) {
+        Delaunay::set_vertices(nb_vertices, vertices);   /* borrows the pointer (delaunay.cpp:210-213) */
+        tree_valid_ = false;
+        /* update_neighbors() (delaunay.cpp:260-274): sizes are reset to the default when the number of seeds changes and are
+         * sticky otherwise */
+        if(nb_vertices != neighbors_.nb_arrays()) {
+            neighbors_.init(nb_vertices, default_nb_neighbors_);
+            for(index_t i = 0; i < nb_vertices; ++i) {
+                neighbors_.resize_array(i, default_nb_neighbors_, false);
+            }
+        }
+        index_t kmax = 0;
+        for(index_t i = 0; i < nb_vertices; ++i) {
+            kmax = std::max(kmax, neighbors_.array_size(i));
+        }
+        kmax = std::max(kmax, default_nb_neighbors_);
+        if(nb_vertices < 2) {
+            return;
+        }
+        index_t k = std::min(kmax, nb_vertices - 1);
+        if(k > B200CVT_KMAX) {
+            /* lists larger than the GPU cap: the reference path */
+            ensure_tree();
+            Delaunay::update_neighbors();
+            return;
+        }
+        check(b200cvt_set_seeds(h_, vertices, nb_vertices), "b200cvt_set_seeds");
+        std::vector<uint32_t> idx(size_t(nb_vertices) * k), cnt(nb_vertices);
+        check(b200cvt_knn(h_, k, idx.data(), cnt.data(), nullptr, nullptr), "b200cvt_knn");
+        for(index_t i = 0; i < nb_vertices; ++i) {
+            index_t want = std::min(neighbors_.array_size(i), nb_vertices - 1);
+            /* a later duplicate is disconnected whatever the list size (delaunay_nn.cpp:123-134) */
+            index_t n = (cnt[i] == 0) ? 0 : std::min<index_t>(want, cnt[i]);
+            neighbors_.set_array(i, n, idx.data() + size_t(i) * k, false);
+        }
+    }
+
+    void Delaunay_B200NN::ensure_tree() const {
+        std::lock_guard<std::mutex> lock(tree_mutex_);
+        if(!tree_valid_) {
+            const_cast<Delaunay_B200NN*>(this)->nn_search()->set_points(nb_vertices(), vertex_ptr(0));
+            tree_valid_ = true;
+        }
+    }
+
+    void Delaunay_B200NN::enlarge_neighborhood(index_t i, index_t nb) {
+        ensure_tree();
+        Delaunay_NearestNeighbors::enlarge_neighborhood(i, nb);
+    }
+
+    index_t Delaunay_B200NN::nearest_vertex(const double* p) const {
+        ensure_tree();
+        return Delaunay_NearestNeighbors::nearest_vertex(p);
+    }
+
+    index_t Delaunay_B200NN::get_neighbors_internal(index_t v, index_t nb_neighbors, index_t* neighbors) const {
+        ensure_tree();
+        return Delaunay_NearestNeighbors::get_neighbors_internal(v, nb_neighbors, neighbors);
+    }
+
+    void b200_register() {
+        static bool done = false;
+        if(!done) {
+            geo_register_Delaunay_creator(Delaunay_B200NN, "B200NN");
+            done = true;
+        }
+    }
+
+    /************************ RVD ************************/
+
+    RestrictedVoronoiDiagramB200::RestrictedVoronoiDiagramB200(Delaunay* delaunay, Mesh* mesh) :
+        RestrictedVoronoiDiagram(
+            delaunay, mesh, (mesh->vertices.nb() > 0) ? mesh->vertices.point_ptr(0) : nullptr, mesh->vertices.dimension()
+        ),
+        h_(nullptr), check_SR_(false), mesh_hash_(0), mesh_uploaded_(false), nb_gpu_calls_(0) {
+        ref_ = RestrictedVoronoiDiagram::create(delaunay, mesh);   /* also forces set_stores_neighbors(true), RVD.cpp:2552 */
+        has_weights_ = mesh->vertices.attributes().is_defined("weight");
+        if(has_weights_) {
+            vertex_weight_.bind(mesh->vertices.attributes(), "weight");
+        }
+        if(dimension_ == 3 || dimension_ == 6) {
+            check(b200cvt_create(-1, int(dimension_), 0, &h_), "b200cvt_create");
+        }
+    }
+
+    RestrictedVoronoiDiagramB200::~RestrictedVoronoiDiagramB200() {
+        if(h_ != nullptr) {
+            b200cvt_destroy(h_);
+        }
+    }
+
+    bool RestrictedVoronoiDiagramB200::gpu_eligible() const {
+        return h_ != nullptr && !volumetric_ && !ref_->exact_predicates() && mesh_->facets.nb() > 0 &&
+            mesh_->facets.are_simplices() && facets_begin_ == 0 && facets_end_ == mesh_->facets.nb() &&
+            delaunay_ != nullptr && delaunay_->nb_vertices() > 0;
+    }
+
+    b200cvt_handle RestrictedVoronoiDiagramB200::handle() {
+        const index_t nv = mesh_->vertices.nb(), nf = mesh_->facets.nb(), stride = mesh_->vertices.dimension();
+        std::vector<uint32_t> tri(size_t(nf) * 3);
+        for(index_t f = 0; f < nf; ++f) {
+            for(index_t lv = 0; lv < 3; ++lv) {
+                tri[size_t(f) * 3 + lv] = mesh_->facets.vertex(f, lv);
+            }
+        }
+        std::vector<double> weights;
+        if(has_weights_) {
+            weights.resize(nv);
+            for(index_t v = 0; v < nv; ++v) {
+                weights[v] = vertex_weight_[v];
+            }
+        }
+        unsigned long long hsh = hash_bytes(0x243F6A8885A308D3ull + nv, mesh_->vertices.point_ptr(0), sizeof(double) * size_t(nv) * stride);
+        hsh = hash_bytes(hsh, tri.data(), sizeof(uint32_t) * tri.size());
+        if(has_weights_) {
+            hsh = hash_bytes(hsh, weights.data(), sizeof(double) * weights.size());
+        }
+        if(!mesh_uploaded_ || hsh != mesh_hash_) {
+            check(
+                b200cvt_set_mesh(h_, mesh_->vertices.point_ptr(0), nv, stride, tri.data(), nullptr, nf,
+                                 has_weights_ ? weights.data() : nullptr),
+                "b200cvt_set_mesh"
+            );
+            mesh_hash_ = hsh;
+            mesh_uploaded_ = true;
+        }
+        return h_;
+    }
+
+    void RestrictedVoronoiDiagramB200::upload_seeds() {
+        check(b200cvt_set_seeds(handle(), delaunay_->vertex_ptr(0), delaunay_->nb_vertices()), "b200cvt_set_seeds");
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_centroids_on_surface(double* mg, double* m) {
+        if(!gpu_eligible()) {
+            ref_->compute_centroids_on_surface(mg, m);
+            return;
+        }
+        upload_seeds();
+        check(b200cvt_centroids(h_, check_SR_ ? 1 : 0, mg, m), "b200cvt_centroids");
+        ++nb_gpu_calls_;
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_CVT_func_grad_on_surface(double& f, double* g) {
+        if(!gpu_eligible()) {
+            ref_->compute_CVT_func_grad_on_surface(f, g);
+            return;
+        }
+        upload_seeds();
+        check(b200cvt_funcgrad(h_, check_SR_ ? 1 : 0, &f, g), "b200cvt_funcgrad");
+        ++nb_gpu_calls_;
+    }
+
+    /* ---- state setters: kept in sync with the delegate ---- */
+
+    void RestrictedVoronoiDiagramB200::set_delaunay(Delaunay* delaunay) {
+        RestrictedVoronoiDiagram::set_delaunay(delaunay);
+        ref_->set_delaunay(delaunay);
+    }
+
+    void RestrictedVoronoiDiagramB200::set_volumetric(bool x) {
+        volumetric_ = x;
+        ref_->set_volumetric(x);
+    }
+
+    void RestrictedVoronoiDiagramB200::set_check_SR(bool x) {
+        check_SR_ = x;
+        ref_->set_check_SR(x);
+    }
+
+    void RestrictedVoronoiDiagramB200::set_exact_predicates(bool x) {
+        ref_->set_exact_predicates(x);
+    }
+
+    bool RestrictedVoronoiDiagramB200::exact_predicates() const {
+        return ref_->exact_predicates();
+    }
+
+    void RestrictedVoronoiDiagramB200::set_facets_range(index_t facets_begin, index_t facets_end) {
+        facets_begin_ = facets_begin;
+        facets_end_ = facets_end;
+        ref_->set_facets_range(facets_begin, facets_end);
+    }
+
+    void RestrictedVoronoiDiagramB200::set_tetrahedra_range(index_t tets_begin, index_t tets_end) {
+        tets_begin_ = tets_begin;
+        tets_end_ = tets_end;
+        ref_->set_tetrahedra_range(tets_begin, tets_end);
+    }
+
+    /* ---- everything off the hot path: the unmodified reference ---- */
+
+    bool RestrictedVoronoiDiagramB200::compute_initial_sampling_on_surface(double* p, index_t nb_points, bool verbose) {
+        return ref_->compute_initial_sampling_on_surface(p, nb_points, verbose);
+    }
+
+    bool RestrictedVoronoiDiagramB200::compute_initial_sampling_in_volume(double* p, index_t nb_points, bool verbose) {
+        return ref_->compute_initial_sampling_in_volume(p, nb_points, verbose);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_centroids_in_volume(double* mg, double* m) {
+        ref_->compute_centroids_in_volume(mg, m);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_CVT_func_grad_in_volume(double& f, double* g) {
+        ref_->compute_CVT_func_grad_in_volume(f, g);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_integration_simplex_func_grad(double& f, double* g, IntegrationSimplex* F) {
+        ref_->compute_integration_simplex_func_grad(f, g, F);
+    }
+
+    void RestrictedVoronoiDiagramB200::project_points_on_surface(index_t nb_points, double* points, vec3* nearest, bool do_project) {
+        ref_->project_points_on_surface(nb_points, points, nearest, do_project);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_RDT(
+        vector<index_t>& simplices, vector<double>& embedding, RDTMode mode, const vector<bool>& seed_is_locked, MeshFacetsAABB* AABB
+    ) {
+        ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_RVD(Mesh& M, coord_index_t dim, bool cell_borders_only, bool integration_simplices) {
+        ref_->compute_RVD(M, dim, cell_borders_only, integration_simplices);
+    }
+
+    void RestrictedVoronoiDiagramB200::compute_RVC(index_t i, Mesh& M, Mesh& result, bool copy_symbolic_info) {
+        ref_->compute_RVC(i, M, result, copy_symbolic_info);
+    }
+
+    void RestrictedVoronoiDiagramB200::for_each_polyhedron(RVDPolyhedronCallback& callback, bool symbolic, bool connected_comp_priority,
+                                                           bool parallel) {
+        ref_->for_each_polyhedron(callback, symbolic, connected_comp_priority, parallel);
+    }
+
+    void RestrictedVoronoiDiagramB200::for_each_polygon(RVDPolygonCallback& callback, bool symbolic, bool connected_comp_priority,
+                                                        bool parallel) {
+        ref_->for_each_polygon(callback, symbolic, connected_comp_priority, parallel);
+    }
+
+    void RestrictedVoronoiDiagramB200::create_threads() {
+        /* the GPU path has no host threads and never reorders the caller's mesh (RVD.cpp:2390-2395 does);
+         * the delegate creates its own on demand */
+    }
+
+    void RestrictedVoronoiDiagramB200::delete_threads() {
+        ref_->delete_threads();
+    }
+
+    GEOGen::PointAllocator* RestrictedVoronoiDiagramB200::point_allocator() {
+        return ref_->point_allocator();
+    }
+
+    /************************ CVT ************************/
+
+    CentroidalVoronoiTesselationB200::CentroidalVoronoiTesselationB200(Mesh* mesh, coord_index_t dimension, const std::string& delaunay) :
+        CentroidalVoronoiTesselation(mesh, dimension, delaunay), canceled_(false), last_on_gpu_(false) {
+        for(int i = 0; i < 4; ++i) {
+            newton_info_[i] = 0;
+        }
+        /* the base constructor created the reference RVD; swap in the adapter (which keeps its own reference delegate) */
+        RVD_ = new RestrictedVoronoiDiagramB200(delaunay_, mesh);
+    }
+
+    CentroidalVoronoiTesselationB200::~CentroidalVoronoiTesselationB200() {
+    }
+
+    RestrictedVoronoiDiagramB200* CentroidalVoronoiTesselationB200::rvd_b200() {
+        return dynamic_cast<RestrictedVoronoiDiagramB200*>(RVD_.get());
+    }
+
+    int CentroidalVoronoiTesselationB200::progress_trampoline(void* user, uint32_t, double, double) {
+        CentroidalVoronoiTesselationB200* self = static_cast<CentroidalVoronoiTesselationB200*>(user);
+        try {
+            self->newiteration();      /* progress_->next() may throw TaskCanceled; it must not cross the C boundary */
+        } catch(const TaskCanceled&) {
+            self->canceled_ = true;
+            return 1;
+        }
+        return 0;
+    }
+
+    void CentroidalVoronoiTesselationB200::Lloyd_iterations(index_t nb_iter) {
+        RestrictedVoronoiDiagramB200* rvd = rvd_b200();
+        const index_t nb = nb_points();
+        last_on_gpu_ = false;
+        if(rvd != nullptr && nb > 0) {
+            delaunay_->set_vertices(nb, points_.data());
+        }
+        if(rvd == nullptr || nb == 0 || !rvd->gpu_eligible()) {
+            CentroidalVoronoiTesselation::Lloyd_iterations(nb_iter);
+            return;
+        }
+        RVD_->set_check_SR(false);
+        if(progress_ != nullptr) {
+            progress_->reset(nb_iter);
+        }
+        cur_iter_ = 0;
+        nb_iter_ = nb_iter;
+        std::vector<uint8_t> locked;
+        if(point_is_locked_.size() != 0) {
+            locked.resize(nb);
+            for(index_t i = 0; i < nb; ++i) {
+                locked[i] = point_is_locked_[i] ? 1 : 0;
+            }
+        }
+        canceled_ = false;
+        int status = b200cvt_lloyd(
+            rvd->handle(), nb_iter, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this
+        );
+        last_on_gpu_ = true;
+        /* leave the Delaunay object as the reference loop does: attached to the current points */
+        delaunay_->set_vertices(nb, points_.data());
+        progress_ = nullptr;
+        check(status, "b200cvt_lloyd");
+    }
+
+    void CentroidalVoronoiTesselationB200::Newton_iterations(index_t nb_iter, index_t m) {
+        RestrictedVoronoiDiagramB200* rvd = rvd_b200();
+        const index_t nb = nb_points();
+        last_on_gpu_ = false;
+        if(rvd != nullptr && nb > 0) {
+            delaunay_->set_vertices(nb, points_.data());
+        }
+        if(rvd == nullptr || nb == 0 || !rvd->gpu_eligible() || !simplex_func_.is_null()) {
+            CentroidalVoronoiTesselation::Newton_iterations(nb_iter, m);
+            return;
+        }
+        RVD_->set_check_SR(true);
+        if(progress_ != nullptr) {
+            progress_->reset(nb_iter);
+        }
+        cur_iter_ = 0;
+        nb_iter_ = nb_iter;
+        std::vector<uint8_t> locked;
+        if(point_is_locked_.size() != 0) {
+            locked.resize(nb);
+            for(index_t i = 0; i < nb; ++i) {
+                locked[i] = point_is_locked_[i] ? 1 : 0;
+            }
+        }
+        canceled_ = false;
+        int status = b200cvt_newton(
+            rvd->handle(), nb_iter, m, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this,
+            newton_info_
+        );
+        last_on_gpu_ = true;
+        delaunay_->set_vertices(nb, points_.data());
+        progress_ = nullptr;
+        check(status, "b200cvt_newton");
+    }
+
+    /************************ remesh_smooth ************************/
+
+    void remesh_smooth_b200(
+        Mesh& M_in, Mesh& M_out, index_t nb_points, coord_index_t dim, index_t nb_Lloyd_iter, index_t nb_Newton_iter,
+        index_t Newton_m, bool adjust, double adjust_max_edge_distance, double adjust_border_importance
+    ) {
+        geo_argused(dim);   /* as in the reference: the dimension is the mesh's (mesh_remesh.cpp:78-82) */
+        Stopwatch W("Remesh(B200)");
+        CentroidalVoronoiTesselationB200 CVT(&M_in);
+        if(nb_points == 0) {
+            nb_points = M_in.vertices.nb();
+        }
+        CVT.compute_initial_sampling(nb_points, true);
+        try {
+            ProgressTask progress("Lloyd", 100);
+            CVT.set_progress_logger(&progress);
+            CVT.Lloyd_iterations(nb_Lloyd_iter);
+        } catch(const TaskCanceled&) {
+        }
+        if(nb_Newton_iter != 0) {
+            try {
+                ProgressTask progress("Newton", 100);
+                CVT.set_progress_logger(&progress);
+                CVT.Newton_iterations(nb_Newton_iter, Newton_m);
+            } catch(const TaskCanceled&) {
+            }
+        }
+        CVT.RVD()->delete_threads();
+        CVT.set_use_RVC_centroids(CmdLine::get_arg_bool("remesh:RVC_centroids"));
+        CVT.compute_surface(&M_out, CmdLine::get_arg_bool("remesh:multi_nerve"));
+        if(adjust) {
+            mesh_adjust_surface(M_out, M_in, adjust_max_edge_distance, false, adjust_border_importance);
+        }
+    }
+}

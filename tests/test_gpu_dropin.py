@@ -1,0 +1,69 @@
+"""GPU drop-in test (pytest -m gpu): the reference's own C++ API with the adapter classes of integration/geogram_b200.h
+(CentroidalVoronoiTesselationB200 / RestrictedVoronoiDiagramB200 / Delaunay "B200NN") against the stock classes, through
+integration/_build/dropin_check (built in the container by __graft_entry__.build(), travels to the GPU box).
+
+BASELINE.json north_star: after N Lloyd iterations the restricted-Delaunay triangle sets must be identical except at flagged
+near-degenerate configurations, and the Hausdorff distance to the reference remesh must be within 1e-6 of the bounding-box
+diagonal. Both remeshes are extracted by the reference's own compute_RDT / compute_surface from each run's seeds.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from graphitethree_b200 import shapes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "integration", "_build", "dropin_check")
+
+
+def write_inputs(tmp_path, V, F, X):
+    mp, sp = str(tmp_path / "mesh.bin"), str(tmp_path / "seeds.bin")
+    with open(mp, "wb") as f:
+        f.write(np.array([V.shape[0], F.shape[0], V.shape[1]], dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(V, dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(F, dtype=np.uint32).tobytes())
+    with open(sp, "wb") as f:
+        f.write(np.array([X.shape[0], X.shape[1]], dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(X, dtype=np.float64).tobytes())
+    return mp, sp
+
+
+def run_check(tmp_path, V, F, X, nl, nn, m=7):
+    if not os.path.exists(EXE):
+        pytest.fail("integration/_build/dropin_check is missing: run __graft_entry__.build() where /root/reference exists")
+    mp, sp = write_inputs(tmp_path, V, F, X)
+    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    print(r)
+    return r
+
+
+def test_dropin_lloyd_rdt_identical_c1_like(tmp_path):
+    # C1-like: icosphere 20 480 triangles (Graphite's create_sphere at 5 splits), 5 000 seeds, 30 Lloyd iterations
+    V, F = shapes.icosphere_split(5)
+    X = shapes.sample_surface(V, F, 5000, 1)
+    r = run_check(tmp_path, V, F, X, 30, 0)
+    assert r["on_gpu"]
+    assert r["nn_mismatch"] == 0                         # "B200NN" Delaunay backend == "NN", list by list
+    assert r["max_abs_dx_lloyd"] <= 1e-9
+    assert r["ref_triangles"] == r["b200_triangles"] and r["only_ref"] == 0 and r["only_b200"] == 0
+    assert r["ref_triangles"] == 2 * 5000 - 4            # closed genus-0 remesh: Euler characteristic 2
+    tol = 1e-6 * r["bbox_diagonal"]
+    assert r["hausdorff_ref_to_b200"] <= tol and r["hausdorff_b200_to_ref"] <= tol
+
+
+def test_dropin_lloyd_newton_trefoil(tmp_path):
+    V, F = shapes.trefoil_tube(400, 40)
+    X = shapes.sample_surface(V, F, 4000, 3)
+    r = run_check(tmp_path, V, F, X, 5, 10)
+    assert r["on_gpu"]
+    assert r["max_abs_dx_lloyd"] <= 1e-9
+    assert r["max_abs_dx_final"] <= 1e-7                 # 11 L-BFGS iterations of accumulated round-off
+    assert r["only_ref"] == 0 and r["only_b200"] == 0
+    tol = 1e-6 * r["bbox_diagonal"]
+    assert r["hausdorff_ref_to_b200"] <= tol and r["hausdorff_b200_to_ref"] <= tol
