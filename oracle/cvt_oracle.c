@@ -577,6 +577,394 @@ static void surfacic_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 pai
     free(seed_stamp); free(facet_marked); free(fstack); free(sstack); free(P);
 }
 
+/* ------------------------------------------------------------------------- */
+/* Volumetric mode: GEOGen::ConvexCell ("Polyhedron") in dual form            */
+/* G/voronoi/generic_RVD_cell.h, generic_RVD_cell.cpp (DIM = 3 only here)     */
+/* ------------------------------------------------------------------------- */
+
+#define CELL_END 0xffffffffu            /* END_OF_LIST / NO_TRIANGLE */
+enum { CTRI_USED = 0, CTRI_CONFLICT = 1, CTRI_FREE = 2 };
+
+/* ConvexCell::Triangle (generic_RVD_cell.h:95-131): the dual of a polyhedron vertex */
+typedef struct { u32 v[3]; u32 t[3]; u32 next; int status; double p[3]; } orc_ctri;
+/* ConvexCell::Vertex (:133-142): the dual of a polyhedron face; id > 0: bisector with seed id-1,
+ * id < 0: tet-tet face with tet -id-1, id == 0: mesh border */
+typedef struct { int64_t id; int32_t t; } orc_cvert;
+typedef struct {
+    orc_ctri* tri; u32 nt, tcap;
+    orc_cvert* vert; u32 nv, vcap;
+    u32 first_free; int dirty;
+} orc_cell;
+
+static const u32 c_plus1[3] = {1, 2, 0}, c_minus1[3] = {2, 0, 1};
+
+static void cell_clear(orc_cell* C) { C->first_free = CELL_END; C->nt = 0; C->nv = 0; C->dirty = 0; }   /* :201-207 */
+static u32 cell_create_vertex(orc_cell* C) {                                                            /* :863-867 */
+    C->dirty = 1;
+    if (C->nv == C->vcap) { C->vcap = C->vcap ? 2 * C->vcap : 64; C->vert = (orc_cvert*)realloc(C->vert, sizeof(orc_cvert) * C->vcap); }
+    C->vert[C->nv].id = -1; C->vert[C->nv].t = -1;
+    if (C->nv + 1 > orc_cell_high_water[1]) orc_cell_high_water[1] = C->nv + 1;
+    return C->nv++;
+}
+static u32 orc_cell_high_water[2] = {0, 0};   /* most triangle slots / planes one cell ever used (sizing of the GPU cell) */
+void orc_cell_high_water_get(u32* out, int reset) { out[0] = orc_cell_high_water[0]; out[1] = orc_cell_high_water[1]; if (reset) orc_cell_high_water[0] = orc_cell_high_water[1] = 0; }
+static u32 cell_create_triangle(orc_cell* C) {                                                          /* :663-672, grow :1324-1328 */
+    if (C->first_free == CELL_END) {
+        if (C->nt == C->tcap) { C->tcap = C->tcap ? 2 * C->tcap : 64; C->tri = (orc_ctri*)realloc(C->tri, sizeof(orc_ctri) * C->tcap); }
+        orc_ctri* T = &C->tri[C->nt];
+        T->next = CELL_END; T->status = CTRI_FREE;
+        for (int i = 0; i < 3; ++i) { T->v[i] = CELL_END; T->t[i] = CELL_END; }
+        C->first_free = C->nt++;
+        if (C->nt > orc_cell_high_water[0]) orc_cell_high_water[0] = C->nt;
+    }
+    u32 r = C->first_free;
+    C->first_free = C->tri[r].next;
+    C->tri[r].status = CTRI_USED;
+    return r;
+}
+static u32 cell_find_vertex(const orc_cell* C, u32 t, u32 v) {                                          /* :425-439 */
+    return (u32)((C->tri[t].v[1] == v) | ((C->tri[t].v[2] == v) * 2));
+}
+static u32 cell_adjacent_index(const orc_cell* C, u32 t1, u32 t2) {                                     /* :448-465 */
+    return (u32)((C->tri[t1].t[1] == t2) | ((C->tri[t1].t[2] == t2) * 2));
+}
+static void cell_init_v_to_t(orc_cell* C) {                                                             /* :640-652 */
+    C->dirty = 0;
+    for (u32 v = 0; v < C->nv; ++v) C->vert[v].t = -1;
+    for (u32 t = 0; t < C->nt; ++t)
+        if (C->tri[t].status == CTRI_USED)
+            for (int iv = 0; iv < 3; ++iv) C->vert[C->tri[t].v[iv]].t = (int32_t)t;
+}
+static int32_t cell_vertex_triangle(orc_cell* C, u32 v) { if (C->dirty) cell_init_v_to_t(C); return C->vert[v].t; }
+typedef struct { u32 t, v; } orc_corner;
+static void cell_next_around_vertex(const orc_cell* C, orc_corner* c) {                                 /* :631-636 */
+    u32 t2 = C->tri[c->t].t[c_plus1[c->v]];
+    u32 v = C->tri[c->t].v[c->v];
+    c->v = cell_find_vertex(C, t2, v);
+    c->t = t2;
+}
+
+/* ConvexCell::initialize_from_mesh_tetrahedron — generic_RVD_cell.cpp:208-282 (non-symbolic part) */
+static void cell_init_from_tet(orc_cell* C, const double* V, const u32* T, const int32_t* tadj, u32 t) {
+    static const u32 tv[4][3] = {{2, 1, 3}, {3, 0, 2}, {0, 3, 1}, {2, 0, 1}};
+    cell_clear(C);
+    for (int lf = 0; lf < 4; ++lf) {
+        u32 v = cell_create_vertex(C);
+        int32_t ta = tadj[4 * (size_t)t + lf];
+        C->vert[v].id = (ta < 0) ? 0 : -(int64_t)ta - 1;
+    }
+    for (int lv = 0; lv < 4; ++lv) {
+        u32 k = cell_create_triangle(C);
+        for (int i = 0; i < 3; ++i) { C->tri[k].v[i] = tv[lv][i]; C->tri[k].t[i] = tv[lv][i]; }
+        memcpy(C->tri[k].p, V + 3 * (size_t)T[4 * (size_t)t + lv], sizeof(double) * 3);
+    }
+}
+
+/* ConvexCell::clip_by_plane<3>, fast predicates — generic_RVD_cell.h:281-334 with
+ * find_furthest_point_linear_scan (:1041-1060), signed_bisector_distance (:1074-1086),
+ * propagate_conflict_list (:1105-1143), Vertex::side_fast (generic_RVD_vertex.h:1017-1027),
+ * find_triangle_on_border (:1226-1242), triangulate_hole (:894-966), Vertex::intersect_geom
+ * (generic_RVD_vertex.h:976-1006), merge_into_free_list (:1310-1322). */
+static void cell_clip_by_plane(orc_cell* C, const double* pi, const double* pj, u32 j, orc_counters* cn, u32** stack, u32* stack_cap) {
+    u32 new_v = cell_create_vertex(C);
+    C->vert[new_v].id = (int64_t)j + 1;
+    cn->planes++;
+    /* Phase I: furthest point, then flood-fill of the conflict zone */
+    u32 furthest = CELL_END; double fd = 0.0;
+    for (u32 t = 0; t < C->nt; ++t) {
+        if (C->tri[t].status != CTRI_USED) continue;
+        const double* q = C->tri[t].p;
+        double d = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            d += (q[c] - pj[c]) * (q[c] - pj[c]);
+            d -= (q[c] - pi[c]) * (q[c] - pi[c]);
+        }
+        cn->plane_vertex++;
+        if (d < fd) { furthest = t; fd = d; }
+    }
+    if (!(fd < 0)) return;
+    u32 cbegin = CELL_END, cend = CELL_END;
+#define APPEND_CONFLICT(tt) do { C->tri[tt].next = cbegin; C->tri[tt].status = CTRI_CONFLICT; cbegin = (tt); if (cend == CELL_END) cend = (tt); } while (0)
+    u32 sn = 0;
+    if (*stack_cap == 0) { *stack_cap = 256; *stack = (u32*)malloc(sizeof(u32) * 256); }
+    (*stack)[sn++] = furthest;
+    APPEND_CONFLICT(furthest);
+    while (sn > 0) {
+        u32 t = (*stack)[--sn];
+        for (u32 e = 0; e < 3; ++e) {
+            u32 nb = C->tri[t].t[e];
+            if (C->tri[nb].status == CTRI_CONFLICT) continue;
+            const double* q = C->tri[nb].p;
+            double r = 0.0;
+            for (int c = 0; c < 3; ++c) {
+                r += (pj[c] - q[c]) * (pj[c] - q[c]);
+                r -= (pi[c] - q[c]) * (pi[c] - q[c]);
+            }
+            cn->intersections++;   /* flood-fill side tests */
+            if (r < 0.0) {
+                if (sn == *stack_cap) { *stack_cap *= 2; *stack = (u32*)realloc(*stack, sizeof(u32) * *stack_cap); }
+                (*stack)[sn++] = nb;
+                APPEND_CONFLICT(nb);
+            }
+        }
+    }
+#undef APPEND_CONFLICT
+    /* Phase II: a conflict triangle with a used neighbour */
+    u32 t1 = cbegin, e1 = 0; int found = 0;
+    do {
+        for (e1 = 0; e1 < 3; ++e1) if (C->tri[C->tri[t1].t[e1]].status == CTRI_USED) { found = 1; break; }
+        if (found) break;
+        t1 = C->tri[t1].next;
+    } while (t1 != CELL_END);
+    if (!found) { cell_clear(C); return; }
+    /* Phase III: triangulate the hole */
+    {
+        u32 t = t1, e = e1, t_adj = C->tri[t].t[e];
+        u32 new_first = CELL_END, new_prev = CELL_END;
+        do {
+            u32 v1 = C->tri[t].v[c_plus1[e]], v2 = C->tri[t].v[c_minus1[e]];
+            u32 nt = cell_create_triangle(C);
+            C->tri[nt].v[0] = new_v; C->tri[nt].v[1] = v1; C->tri[nt].v[2] = v2;
+            {   /* intersect_geom(vq1 = dual(t), vq2 = dual(adjacent(t, e)), p1 = pi, p2 = pj) */
+                const double* q1 = C->tri[t].p; const double* q2 = C->tri[C->tri[t].t[e]].p;
+                double d = 0.0, l1 = 0.0, l2 = 0.0;
+                for (int c = 0; c < 3; ++c) {
+                    double n = pi[c] - pj[c];
+                    d -= n * (pj[c] + pi[c]);
+                    l1 += q2[c] * n;
+                    l2 += q1[c] * n;
+                }
+                d = 0.5 * d;
+                l1 = fabs(l1 + d); l2 = fabs(l2 + d);
+                double l12 = l1 + l2;
+                if (l12 > 1e-30) { l1 /= l12; l2 /= l12; } else { l1 = 0.5; l2 = 0.5; }
+                for (int c = 0; c < 3; ++c) C->tri[nt].p[c] = l1 * q1[c] + l2 * q2[c];
+            }
+            C->tri[nt].t[0] = t_adj;
+            C->tri[t_adj].t[cell_adjacent_index(C, t_adj, t)] = nt;
+            e = c_plus1[e];
+            t_adj = C->tri[t].t[e];
+            while (C->tri[t_adj].status == CTRI_CONFLICT) {
+                t = t_adj;
+                e = c_minus1[cell_find_vertex(C, t, v2)];
+                t_adj = C->tri[t].t[e];
+            }
+            if (new_prev == CELL_END) new_first = nt;
+            else { C->tri[new_prev].t[1] = nt; C->tri[nt].t[2] = new_prev; }
+            new_prev = nt;
+        } while (t != t1 || e != e1);
+        C->tri[new_prev].t[1] = new_first;
+        C->tri[new_first].t[2] = new_prev;
+    }
+    /* Phase IV: conflict zone -> free list */
+    {
+        u32 cur = cbegin;
+        while (cur != cend) { C->tri[cur].status = CTRI_FREE; cur = C->tri[cur].next; }
+        C->tri[cend].status = CTRI_FREE;
+        C->tri[cend].next = C->first_free;
+        C->first_free = cbegin;
+    }
+}
+
+/* clip_by_cell_SR(index_t seed, Polyhedron& C) — G/voronoi/generic_RVD.h:2282-2347 */
+static void cell_clip_by_cell_SR(orc_rvd* R, u32 i, orc_cell* C, u32** stack, u32* stack_cap) {
+    const double* pi = R->x + (size_t)i * 3;
+    u32 jj = 0, prev_nb = 0, cur_n = 0;
+    while (cur_n < R->S - 1) {
+        cur_n = R->nbr_n[i];
+        if (cur_n == 0) return;
+        if (prev_nb == cur_n) return;
+        for (; jj < cur_n; ++jj) {
+            u32 j = R->nbr[(size_t)i * R->kcap + jj];
+            double R2 = 0.0;
+            for (u32 k = 0; k < C->nt; ++k) {
+                if (C->tri[k].status != CTRI_USED) continue;
+                double dik = distance2(pi, C->tri[k].p, 3);
+                if (dik > R2) R2 = dik;
+            }
+            const double* pj = R->x + (size_t)j * 3;
+            double dij = distance2(pi, pj, 3);
+            if (dij > 4.1 * R2) { R->cn.sr_exits++; return; }
+            cell_clip_by_plane(C, pi, pj, j, &R->cn, stack, stack_cap);
+        }
+        if (!R->check_SR) {
+            int used = 0;
+            for (u32 k = 0; k < C->nt; ++k) used |= (C->tri[k].status == CTRI_USED);
+            if (used) { R->flags[i] |= ORC_FLAG_EXHAUSTED; R->cn.exhausted++; }
+            return;
+        }
+        u32 nb = cur_n;
+        prev_nb = nb;
+        if (nb > 8) nb += nb / 8; else nb++;
+        if (nb > R->S - 1) nb = R->S - 1;
+        if (nb > R->kcap) { R->flags[i] |= ORC_FLAG_EXHAUSTED; R->cn.exhausted++; return; }
+        enlarge_neighborhood(R, i, nb);
+    }
+}
+
+/* Geom::tetra_volume<3> — G/basic/geometry.h:483-524 (vecng.h dot/cross) */
+static double tetra_volume3(const double* p1, const double* p2, const double* p3, const double* p4) {
+    double U[3], Vv[3], W[3];
+    for (int c = 0; c < 3; ++c) { U[c] = p2[c] - p1[c]; Vv[c] = p3[c] - p1[c]; W[c] = p4[c] - p1[c]; }
+    double cx = Vv[1] * W[2] - Vv[2] * W[1];
+    double cy = Vv[2] * W[0] - Vv[0] * W[2];
+    double cz = Vv[0] * W[1] - Vv[1] * W[0];
+    return fabs((U[0] * cx + U[1] * cy + U[2] * cz) / 6.0);
+}
+
+/* TetrahedronAction (generic_RVD.h:901-978) + ComputeCentroidsVolumetric (RVD.cpp:428-497), or
+ * VolumetricIntegrationSimplexAction with visit_inner_tets = false (generic_RVD.h:726-786) +
+ * ComputeCVTFuncGradVolumetric (RVD.cpp:791-876). Returns 1 if the cell is non-empty. */
+static int integrate_cell(orc_rvd* R, orc_accum* A, u32 v, orc_cell* C) {
+    const double* p0 = R->x + (size_t)v * 3;
+    u32 t0 = CELL_END;
+    for (u32 t = 0; t < C->nt; ++t) if (C->tri[t].status == CTRI_USED) { t0 = t; break; }
+    if (t0 == CELL_END) return 0;
+    for (u32 cv = 0; cv < C->nv; ++cv) {
+        int32_t ct = cell_vertex_triangle(C, cv);
+        if (ct == -1) continue;
+        int64_t adjacent = C->vert[cv].id;
+        if (A->mode == 1 && adjacent < 0) continue;            /* tet-tet face: skipped unless visit_inner_tets */
+        orc_corner c1; c1.t = (u32)ct; c1.v = cell_find_vertex(C, (u32)ct, cv);
+        if (A->mode == 0) {
+            /* facet_is_incident_to_vertex (generic_RVD.h:993-1004) */
+            orc_corner cur = c1; int inc = 0;
+            do { if (cur.t == t0) { inc = 1; break; } cell_next_around_vertex(C, &cur); } while (cur.t != c1.t || cur.v != c1.v);
+            if (inc) continue;
+        }
+        const double* v1 = C->tri[c1.t].p;
+        orc_corner c2 = c1; cell_next_around_vertex(C, &c2);
+        orc_corner c3 = c2; cell_next_around_vertex(C, &c3);
+        do {
+            const double* v2 = C->tri[c2.t].p;
+            const double* v3 = C->tri[c3.t].p;
+            R->cn.triangles++;
+            if (A->mode == 0) {
+                const double* q0 = C->tri[t0].p;
+                double cur_m = tetra_volume3(q0, v1, v2, v3);
+                double s = cur_m / 4.0;
+                A->m[v] += cur_m;
+                for (int c = 0; c < 3; ++c) A->mg[(size_t)v * 3 + c] += s * (q0[c] + v1[c] + v2[c] + v3[c]);
+            } else {
+                double mi = tetra_volume3(p0, v1, v2, v3);
+                double fi = 0.0;
+                for (int c = 0; c < 3; ++c) {
+                    double Uc = v1[c] - p0[c], Vc = v2[c] - p0[c], Wc = v3[c] - p0[c];
+                    fi += Uc * Uc + Vc * Vc + Wc * Wc;
+                    fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                }
+                fi *= (mi / 10.0);
+                A->f += fi;
+                if (A->f_seed) A->f_seed[v] += fi;
+                for (int c = 0; c < 3; ++c)
+                    A->g[(size_t)v * 3 + c] += 2.0 * mi * (0.75 * p0[c] - 0.25 * v1[c] - 0.25 * v2[c] - 0.25 * v3[c]);
+            }
+            c2 = c3;
+            cell_next_around_vertex(C, &c3);
+        } while (c3.t != c1.t || c3.v != c1.v);
+    }
+    return 1;
+}
+
+/* compute_volumetric_with_seeds_priority — G/voronoi/generic_RVD.h:1464-1597. R->T holds 4 vertex ids per tet,
+ * R->adj 4 adjacent tets per tet (-1: border; adj[4t+lf] is across the face opposite to local vertex lf). */
+static void volumetric_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 pairs_cap, u64* npairs_out) {
+    u32* seed_stamp = (u32*)malloc(sizeof(u32) * (R->S ? R->S : 1));
+    memset(seed_stamp, 0xff, sizeof(u32) * (R->S ? R->S : 1));
+    uint8_t* tet_marked = (uint8_t*)calloc(R->nt ? R->nt : 1, 1);
+    u32 ts_cap = 1024, ts_n = 0;
+    u32* tstack = (u32*)malloc(sizeof(u32) * 2 * ts_cap);
+    u32 ss_cap = 1024, ss_n = 0;
+    u32* sstack = (u32*)malloc(sizeof(u32) * ss_cap);
+    u32* fstack = NULL; u32 fstack_cap = 0;
+    orc_cell C; memset(&C, 0, sizeof(C)); C.first_free = CELL_END;
+    u64 npairs = 0;
+    for (u32 t = 0; t < R->nt; ++t) {
+        if (tet_marked[t]) continue;
+        tet_marked[t] = 1;
+        u32 s0; double d0;
+        grid_knn(&R->grid, R->V + 3 * (size_t)R->T[4 * (size_t)t], 1, &s0, &d0, NULL);   /* find_seed_near_tet :2024-2028 */
+        tstack[0] = t; tstack[1] = s0; ts_n = 1;
+        while (ts_n > 0) {
+            --ts_n;
+            u32 ct = tstack[2 * ts_n], cs = tstack[2 * ts_n + 1];
+            seed_stamp[cs] = ct;
+            sstack[0] = cs; ss_n = 1;
+            while (ss_n > 0) {
+                u32 seed = sstack[--ss_n];
+                cell_init_from_tet(&C, R->V, R->T, R->adj, ct);
+                cell_clip_by_cell_SR(R, seed, &C, &fstack, &fstack_cap);
+                R->cn.pairs++;
+                if (integrate_cell(R, A, seed, &C)) {
+                    R->cn.nonempty_pairs++;
+                    if (pairs_out && npairs < pairs_cap) { pairs_out[2 * npairs] = seed; pairs_out[2 * npairs + 1] = ct; }
+                    npairs++;
+                }
+                for (u32 v = 0; v < C.nv; ++v) {
+                    if (cell_vertex_triangle(&C, v) == -1) continue;
+                    int64_t id = C.vert[v].id;
+                    if (id > 0) {
+                        u32 ns = (u32)(id - 1);
+                        if (seed_stamp[ns] != ct) {
+                            seed_stamp[ns] = ct;
+                            if (ss_n == ss_cap) { ss_cap *= 2; sstack = (u32*)realloc(sstack, sizeof(u32) * ss_cap); }
+                            sstack[ss_n++] = ns;
+                        }
+                    } else if (id < 0) {
+                        int64_t nt = -id - 1;
+                        if (nt < (int64_t)R->nt && nt != (int64_t)ct && !tet_marked[nt]) {
+                            tet_marked[nt] = 1;
+                            if (ts_n == ts_cap) { ts_cap *= 2; tstack = (u32*)realloc(tstack, sizeof(u32) * 2 * ts_cap); }
+                            tstack[2 * ts_n] = (u32)nt; tstack[2 * ts_n + 1] = seed; ts_n++;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (npairs_out) *npairs_out = npairs;
+    free(seed_stamp); free(tet_marked); free(tstack); free(sstack); free(fstack); free(C.tri); free(C.vert);
+}
+
+/* tet adjacency as Mesh::cells.connect() produces it: adj[4t+lf] = tet sharing the face opposite to local
+ * vertex lf (MeshCellDescriptors tet_descriptor, G/mesh/mesh.cpp), -1 on the border. */
+typedef struct { u32 a, b, c, t, lf; } orc_face;
+static int face_cmp(const void* x, const void* y) {
+    const orc_face* e = (const orc_face*)x; const orc_face* g = (const orc_face*)y;
+    if (e->a != g->a) return e->a < g->a ? -1 : 1;
+    if (e->b != g->b) return e->b < g->b ? -1 : 1;
+    if (e->c != g->c) return e->c < g->c ? -1 : 1;
+    if (e->t != g->t) return e->t < g->t ? -1 : 1;
+    return 0;
+}
+int orc_tet_adjacency(u32 nt, const u32* T, int32_t* adj) {
+    orc_face* E = (orc_face*)malloc(sizeof(orc_face) * 4 * (size_t)(nt ? nt : 1));
+    for (u32 t = 0; t < nt; ++t)
+        for (u32 lf = 0; lf < 4; ++lf) {
+            u32 q[3]; int n = 0;
+            for (u32 lv = 0; lv < 4; ++lv) if (lv != lf) q[n++] = T[4 * (size_t)t + lv];
+            if (q[0] > q[1]) { u32 w = q[0]; q[0] = q[1]; q[1] = w; }
+            if (q[1] > q[2]) { u32 w = q[1]; q[1] = q[2]; q[2] = w; }
+            if (q[0] > q[1]) { u32 w = q[0]; q[0] = q[1]; q[1] = w; }
+            orc_face* e = &E[4 * (size_t)t + lf];
+            e->a = q[0]; e->b = q[1]; e->c = q[2]; e->t = t; e->lf = lf;
+            adj[4 * (size_t)t + lf] = -1;
+        }
+    qsort(E, 4 * (size_t)nt, sizeof(orc_face), face_cmp);
+    for (size_t i = 0; i + 1 < 4 * (size_t)nt; ++i)
+        if (E[i].a == E[i + 1].a && E[i].b == E[i + 1].b && E[i].c == E[i + 1].c) {
+            adj[4 * (size_t)E[i].t + E[i].lf] = (int32_t)E[i + 1].t;
+            adj[4 * (size_t)E[i + 1].t + E[i + 1].lf] = (int32_t)E[i].t;
+        }
+    free(E);
+    return 0;
+}
+
+/* RestrictedVoronoiDiagram::set_volumetric for the evaluation entry points below: elements are then tetrahedra
+ * (4 vertex ids, 4 adjacent tets each) and dim must be 3. */
+static int orc_volumetric_mode = 0;
+void orc_set_volumetric(int x) { orc_volumetric_mode = x; }
+
 /* facet adjacency as Mesh::facets.connect() produces it: adj[3f+lv] = facet sharing
  * edge (lv, lv+1), -1 on the border or for non-manifold edges (first match wins). */
 typedef struct { u32 a, b, f, lv; } orc_edge;
@@ -651,7 +1039,10 @@ int orc_surface_eval(int dim, u32 nv, const double* V, u32 nt, const u32* T, con
     rvd_init(&R, dim, nv, V, nt, T, adj, weights, S, x, k, kcap, ksize, check_SR, fl);
     orc_accum A;
     A.mode = mode; A.m = m; A.mg = mg; A.g = g; A.f_seed = f_seed; A.f = 0.0;
-    surfacic_traversal(&R, &A, pairs_out, pairs_cap, npairs);
+    if (orc_volumetric_mode) {
+        if (dim != 3) { rvd_free(&R, ksize); if (!flags) free(fl); return 2; }
+        volumetric_traversal(&R, &A, pairs_out, pairs_cap, npairs);
+    } else surfacic_traversal(&R, &A, pairs_out, pairs_cap, npairs);
     if (mode == 1 && f) *f += A.f;
     if (counters) memcpy(counters, &R.cn, sizeof(orc_counters));
     rvd_free(&R, ksize);

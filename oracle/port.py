@@ -54,6 +54,30 @@ def facet_adjacency(T):
     return adj
 
 
+def tet_adjacency(T):
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    adj = np.empty(T.shape, dtype=np.int32)
+    _lib().orc_tet_adjacency(C.c_uint32(T.shape[0]), _p(T, _up), _p(adj, _ip))
+    return adj
+
+
+def _adjacency(T):
+    """facet adjacency for triangles, tet adjacency for tetrahedra (volumetric mode)"""
+    return tet_adjacency(T) if T.shape[1] == 4 else facet_adjacency(T)
+
+
+class _Volumetric:
+    """RestrictedVoronoiDiagram::set_volumetric around one oracle call (elements with 4 ids are tetrahedra)."""
+    def __init__(self, T):
+        self.on = T.shape[1] == 4
+
+    def __enter__(self):
+        _lib().orc_set_volumetric(C.c_int(1 if self.on else 0))
+
+    def __exit__(self, *a):
+        _lib().orc_set_volumetric(C.c_int(0))
+
+
 def knn(x, k=20, ksize=None, kstride=None):
     """Neighbour lists with the semantics of Delaunay_NearestNeighbors (delaunay_nn.cpp:73-145)."""
     x = _f64(x)
@@ -85,7 +109,7 @@ def surface_eval(V, T, x, mode, check_SR, k=20, kcap=None, ksize=None, weights=N
     V, x = _f64(V), _f64(x)
     T = np.ascontiguousarray(T, dtype=np.uint32)
     if adj is None:
-        adj = facet_adjacency(T)
+        adj = _adjacency(T)
     S, dim = x.shape
     kcap = kcap or (k if not check_SR else max(4 * k, 64))
     r = SurfaceEval()
@@ -101,7 +125,8 @@ def surface_eval(V, T, x, mode, check_SR, k=20, kcap=None, ksize=None, weights=N
     cap = 64 * S if want_pairs else 0
     pairs = np.zeros((max(cap, 1), 2), dtype=np.uint32)
     npairs = C.c_uint64(0)
-    rc = _lib().orc_surface_eval(
+    with _Volumetric(T):
+      rc = _lib().orc_surface_eval(
         C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up), _p(adj, _ip),
         _p(w, _dp), C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(kcap), _p(ks, _up),
         C.c_int(int(check_SR)), C.c_int(mode), _p(r.m, _dp), _p(r.mg, _dp), C.byref(f), _p(r.g, _dp),
@@ -120,12 +145,13 @@ def lloyd(V, T, x, nb_iter, k=20, locked=None, weights=None, adj=None):
     x = np.array(x, dtype=np.float64, order="C", copy=True)
     T = np.ascontiguousarray(T, dtype=np.uint32)
     if adj is None:
-        adj = facet_adjacency(T)
+        adj = _adjacency(T)
     S, dim = x.shape
     flags = np.zeros(S, dtype=np.uint8)
     lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
     w = _f64(weights)
-    _lib().orc_lloyd(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up),
+    with _Volumetric(T):
+      _lib().orc_lloyd(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up),
                      _p(adj, _ip), _p(w, _dp), C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(nb_iter),
                      _p(lk, _bp), _p(flags, _bp))
     return x, flags
@@ -136,7 +162,7 @@ def newton(V, T, x, nb_iter, m=7, k=20, kcap=256, locked=None, weights=None, adj
     x = np.array(x, dtype=np.float64, order="C", copy=True)
     T = np.ascontiguousarray(T, dtype=np.uint32)
     if adj is None:
-        adj = facet_adjacency(T)
+        adj = _adjacency(T)
     S, dim = x.shape
     cap = nb_iter + 8
     fh = np.zeros(cap)
@@ -145,7 +171,8 @@ def newton(V, T, x, nb_iter, m=7, k=20, kcap=256, locked=None, weights=None, adj
     flags = np.zeros(S, dtype=np.uint8)
     lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
     w = _f64(weights)
-    _lib().orc_newton(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up),
+    with _Volumetric(T):
+      _lib().orc_newton(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up),
                       _p(adj, _ip), _p(w, _dp), C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(kcap),
                       C.c_uint32(nb_iter), C.c_uint32(m), _p(lk, _bp), _p(fh, _dp), _p(gh, _dp), C.c_uint32(cap),
                       C.byref(nit), C.byref(nfev), _p(flags, _bp))
