@@ -13,6 +13,7 @@
 #include "clip.cuh"
 #include "clip_flat.cuh"
 #include "facet_pairs.cuh"
+#include "clip_tet.cuh"
 #include "lbfgs.cuh"
 #include "../../include/b200cvt.h"
 
@@ -222,6 +223,7 @@ struct b200cvt_ctx {
     u32 nv = 0, T = 0;
     bool has_mesh = false, weighted = false;
     DevBuf<double> tri, triw;
+    DevBuf<uint8_t> tet_inner;         // volumetric: bit lf = face opposite to corner lf is shared with another tet
     DevBuf<u32> facet_guess;
     double bb_lo[3], bb_hi[3], mesh_measure = 0.0;
     // seeds
@@ -462,12 +464,12 @@ static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds) {
 // ---------------------------------------------------------------------------------------
 // evaluation = pairs + clip (+ neighbourhood enlargement when check_SR)
 // ---------------------------------------------------------------------------------------
-template <int D>
+template <int D, int NC>
 static void run_pairs_t(b200cvt_ctx* h) {
     const u32 S = h->S;
     if (h->pair_cap == 0) {
         double ratio = (double)h->T / (double)std::max<u32>(S, 1);
-        u32 want = (u32)(ratio * 4.0 + 24.0);
+        u32 want = NC == 4 ? (u32)(ratio * 8.0 + 32.0) : (u32)(ratio * 4.0 + 24.0);
         u32 cap = 32; while (cap < want) cap <<= 1;
         h->pair_cap = cap;
     }
@@ -497,7 +499,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
             // the facets that can meet the cell of an owned seed
             h->facet_cell.ensure(h->T); h->facet_list.ensure(h->T); h->facet_list_n.ensure(1);
             if (!h->facet_cell_valid) {
-                LAUNCH(h, facet_cell_kernel<D>, div_up(h->T, 256), 256, 0, h->tri.p, h->T, h->g, h->facet_cell.p);
+                LAUNCH(h, (facet_cell_kernel<D, NC>), div_up(h->T, 256), 256, 0, h->tri.p, h->T, h->g, h->facet_cell.p);
                 h->facet_cell_valid = true;
             }
             CUDA_CHECK(cudaMemsetAsync(h->facet_list_n.p, 0, sizeof(u32), h->stream));
@@ -509,8 +511,8 @@ static void run_pairs_t(b200cvt_ctx* h) {
             a.facet_list = h->facet_list.p; a.facet_list_n = h->facet_list_n.p;
         }
         if (h->T > 0) {
-            LAUNCH(h, facet_home_kernel<D>, div_up(h->T, 128), 128, 0, a);
-            LAUNCH(h, facet_task_kernel<D>, (u32)h->num_sms * 8u, 128, 0, a);
+            LAUNCH(h, (facet_home_kernel<D, NC>), div_up(h->T, 128), 128, 0, a);
+            LAUNCH(h, (facet_task_kernel<D, NC>), (u32)h->num_sms * 8u, 128, 0, a);
         }
         // flat offsets of the owned seeds (pair_cnt[qend] is 0: only owned seeds receive pairs)
         size_t tb = h->cub_tmp.cap;
@@ -543,11 +545,84 @@ static void launch_clip(b200cvt_ctx* h, ClipArgs& a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// volumetric evaluation (DIM = 3): candidate (tet, seed) rows from the facet walk with 4 corners, one warp per seed
+// ---------------------------------------------------------------------------------------
+static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
+    if (a.nseeds == 0 && !a.nseeds_dev) return;
+    size_t smem = (size_t)TETC_WARPS * a.kstride * 4 * sizeof(double);
+    u32 blocks = a.nseeds_dev ? 148u * 4u : div_up(a.nseeds, TETC_WARPS);
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_tet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
+}
+
+static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
+    const u32 S = h->S;
+    run_pairs_t<3, 4>(h);
+    CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+    h->out_s.ensure(S); h->out_v.ensure((size_t)S * 3);
+    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
+    const u32 nown = h->qend() - h->qbegin();
+    TetClipArgs c;
+    memset(&c, 0, sizeof(c));
+    c.xs = h->xs.p; c.nbr = h->nbr.p; c.nbr_n = h->nbr_n.p; c.kstride = h->kstride; c.nbr_by_slot = 0;
+    c.tet = h->tri.p; c.tet_inner = h->tet_inner.p;
+    c.pair_cnt = h->pair_cnt.p; c.pair_facet = h->pair_facet.p; c.cap = h->pair_cap;
+    c.seed_list = nullptr; c.nseeds = nown; c.qbegin = h->qbegin();
+    c.mode = mode; c.check_SR = check_SR; c.S = S;
+    c.out_s = h->out_s.p; c.out_v = h->out_v.p; c.flags = h->flags.p;
+    c.redo_list = check_SR ? h->redo_a.p : nullptr; c.redo_n = h->redo_n.p;
+    c.stats = h->want_stats ? h->stats.p : nullptr;
+    CUDA_CHECK(cudaEventRecord(h->evk[0], h->stream));
+    launch_clip_tet(h, c);
+    CUDA_CHECK(cudaEventRecord(h->evk[1], h->stream));
+    if (check_SR) {
+        // enlarge_neighborhood loop (generic_RVD.h:2330-2346), batched over the seeds that need it
+        u32 kbig = 40;
+        u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
+        int cur_slot = 0;
+        for (;;) {
+            u32 nredo = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            if (nredo == 0) break;
+            h->host_stats[4] += nredo;
+            kbig = std::min<u32>(kbig, B200CVT_KMAX);
+            kbig = std::min<u32>(kbig, S - 1);
+            h->nbr_big.ensure((size_t)nredo * kbig);
+            h->nbr_big_n.ensure(nredo);
+            KnnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
+            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
+            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+            launch_knn<3>(h, a, nredo);
+            int nslot = cur_slot ^ 1;
+            CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
+            TetClipArgs r = c;
+            r.nbr = h->nbr_big.p; r.nbr_n = h->nbr_big_n.p; r.kstride = kbig; r.nbr_by_slot = 1;
+            r.seed_list = cur_list; r.nseeds = nredo;
+            r.redo_list = nxt_list; r.redo_n = h->redo_n.p + nslot;
+            launch_clip_tet(h, r);
+            std::swap(cur_list, nxt_list);
+            cur_slot = nslot;
+            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) break;
+            kbig *= 2;
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
+    h->has_results = true;
+    h->has_energy = (mode == 1);
+    h->ev_valid = true;
+    h->ev_pending = true;
+}
+
 template <int D>
 static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
     if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
-    if (h->volumetric) throw ArgError("volumetric evaluation is not available in this build");
     const u32 S = h->S;
     if (!h->ev[0]) {
         for (int i = 0; i < 6; ++i) { CUDA_CHECK(cudaEventCreate(&h->ev[i])); CUDA_CHECK(cudaEventRecord(h->ev[i], h->stream)); }
@@ -600,7 +675,11 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
     h->stats.ensure(16);
     if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 16 * sizeof(unsigned long long), h->stream));
-    run_pairs_t<D>(h);
+    if (h->volumetric) {
+        if (D == 3) evaluate_volume(h, mode, check_SR);
+        return;
+    }
+    run_pairs_t<D, 3>(h);
     CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
 
     h->out_s.ensure(S); h->out_v.ensure((size_t)S * D);
@@ -885,6 +964,7 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
     return guarded([&] {
         if (!out) throw ArgError("out is NULL");
         if (dim != 3 && dim != 6) throw ArgError("dim must be 3 or 6 (other dimensions stay on the reference implementation)");
+        if (volumetric && dim != 3) throw ArgError("volumetric mode needs dim 3 (other dimensions stay on the reference implementation)");
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -904,7 +984,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->tri.release(); h->triw.release(); h->facet_guess.release(); h->x.release();
+    h->tri.release(); h->triw.release(); h->tet_inner.release(); h->facet_guess.release(); h->x.release();
     h->keys.release(); h->vals.release(); h->keys2.release(); h->vals2.release(); h->cub_tmp.release();
     h->xs.release(); h->rank_of.release(); h->cell_range.release(); h->nbr.release(); h->nbr_n.release();
     h->sqd.release(); h->flags.release(); h->redo_a.release(); h->redo_b.release(); h->redo_n.release();
@@ -923,19 +1003,19 @@ void b200cvt_destroy(b200cvt_handle h) {
 
 int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint32_t stride, const uint32_t* elems,
                      const int32_t* adjacency, uint32_t ne, const double* weights) {
-    (void)adjacency;
     return guarded([&] {
         if (!h || !vertices || !elems) throw ArgError("null argument");
         if (stride < (u32)h->dim) throw ArgError("vertex stride smaller than the dimension (geo_assert(dimension_ <= mesh->vertices.dimension()), CVT.cpp:64)");
-        if (h->volumetric) throw ArgError("volumetric meshes are not available in this build");
         CUDA_CHECK(cudaSetDevice(h->device));
         const int D = h->dim;
-        const int per = 3;
-        // pass 1: validate, bounding box, total area
+        const int per = h->volumetric ? 4 : 3;
+        // the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783)
+        if (h->volumetric) weights = nullptr;
+        // pass 1: validate, bounding box, total area / volume
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        double area = 0.0;
+        double measure = 0.0;
         for (u32 f = 0; f < ne; ++f) {
-            const double* p[3];
+            const double* p[4];
             for (int lv = 0; lv < per; ++lv) {
                 u32 v = elems[(size_t)f * per + lv];
                 if (v >= nv) throw ArgError("element references a vertex out of range");
@@ -945,9 +1025,10 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             double e1[3], e2[3];
             for (int a = 0; a < 3; ++a) { e1[a] = p[1][a] - p[0][a]; e2[a] = p[2][a] - p[0][a]; }
             double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-            area += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+            if (per == 3) measure += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+            else measure += std::fabs(cx * (p[3][0] - p[0][0]) + cy * (p[3][1] - p[0][1]) + cz * (p[3][2] - p[0][2])) / 6.0;
         }
-        // pass 2: facets in Morton order of their centroids (10 bits per axis), so that the facets one warp walks
+        // pass 2: elements in Morton order of their centroids (10 bits per axis), so that the elements one warp walks
         // share home seeds and bisector rows. The reference reorders the caller's mesh for the same reason
         // (mesh_partition Hilbert sort, RVD.cpp:2390-2395); here only the device copy is permuted.
         std::vector<std::pair<u32, u32>> order(ne);
@@ -959,8 +1040,8 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
                 u32 q[3];
                 for (int a = 0; a < 3; ++a) {
                     double c = 0.0;
-                    for (int lv = 0; lv < 3; ++lv) c += vertices[(size_t)elems[(size_t)f * 3 + lv] * stride + a];
-                    double t = (c * (1.0 / 3.0) - lo[a]) * sc;
+                    for (int lv = 0; lv < per; ++lv) c += vertices[(size_t)elems[(size_t)f * per + lv] * stride + a];
+                    double t = (c * (1.0 / per) - lo[a]) * sc;
                     q[a] = (u32)std::min(1023.0, std::max(0.0, t));
                 }
                 u32 code = 0;
@@ -970,7 +1051,7 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             }
             std::sort(order.begin(), order.end());
         }
-        std::vector<double> soup((size_t)ne * 3 * D);
+        std::vector<double> soup((size_t)ne * per * D);
         std::vector<double> sw;
         if (weights) sw.resize((size_t)ne * 3);
         for (u32 i = 0; i < ne; ++i) {
@@ -978,11 +1059,45 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             for (int lv = 0; lv < per; ++lv) {
                 const u32 v = elems[(size_t)f * per + lv];
                 const double* p = vertices + (size_t)v * stride;
-                for (int c = 0; c < D; ++c) soup[((size_t)i * 3 + lv) * D + c] = p[c];
+                for (int c = 0; c < D; ++c) soup[((size_t)i * per + lv) * D + c] = p[c];
                 if (weights) sw[(size_t)i * 3 + lv] = weights[v];
             }
         }
-        h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = area;
+        // volumetric: which faces of a tet are shared with another tet (cells.tet_adjacent != NO_CELL); face lf is opposite
+        // to corner lf. Taken from the caller's adjacency when given, else from matching sorted face triples.
+        std::vector<uint8_t> inner;
+        if (h->volumetric) {
+            inner.assign(ne, 0);
+            std::vector<uint8_t> by_elem(ne, 0);
+            if (adjacency) {
+                for (u32 t = 0; t < ne; ++t)
+                    for (int lf = 0; lf < 4; ++lf)
+                        if (adjacency[(size_t)t * 4 + lf] >= 0) by_elem[t] |= (uint8_t)(1u << lf);
+            } else {
+                struct Face { u32 a, b, c, t, lf; };
+                std::vector<Face> F((size_t)ne * 4);
+                for (u32 t = 0; t < ne; ++t)
+                    for (u32 lf = 0; lf < 4; ++lf) {
+                        u32 q[3]; int n = 0;
+                        for (u32 lv = 0; lv < 4; ++lv) if (lv != lf) q[n++] = elems[(size_t)t * 4 + lv];
+                        std::sort(q, q + 3);
+                        F[(size_t)t * 4 + lf] = Face{q[0], q[1], q[2], t, lf};
+                    }
+                std::sort(F.begin(), F.end(), [](const Face& x, const Face& y) {
+                    if (x.a != y.a) return x.a < y.a;
+                    if (x.b != y.b) return x.b < y.b;
+                    if (x.c != y.c) return x.c < y.c;
+                    return x.t < y.t;
+                });
+                for (size_t i = 0; i + 1 < F.size(); ++i)
+                    if (F[i].a == F[i + 1].a && F[i].b == F[i + 1].b && F[i].c == F[i + 1].c) {
+                        by_elem[F[i].t] |= (uint8_t)(1u << F[i].lf);
+                        by_elem[F[i + 1].t] |= (uint8_t)(1u << F[i + 1].lf);
+                    }
+            }
+            for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[order[i].second];
+        }
+        h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = measure;
         for (int a = 0; a < 3; ++a) { h->bb_lo[a] = lo[a]; h->bb_hi[a] = hi[a]; }
         h->tri.ensure(soup.size());
         CUDA_CHECK(cudaMemcpyAsync(h->tri.p, soup.data(), sizeof(double) * soup.size(), cudaMemcpyHostToDevice, h->stream));
@@ -990,15 +1105,20 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             h->triw.ensure(sw.size());
             CUDA_CHECK(cudaMemcpyAsync(h->triw.p, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice, h->stream));
         }
+        if (h->volumetric) {
+            h->tet_inner.ensure(std::max<size_t>(ne, 1));
+            if (ne > 0) CUDA_CHECK(cudaMemcpyAsync(h->tet_inner.p, inner.data(), ne, cudaMemcpyHostToDevice, h->stream));
+        }
         h->facet_guess.ensure(ne);
         LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)ne, B200_NONE);
         h->facet_ball.ensure(ne); h->facet_cell_valid = false;
         if (ne > 0) {
-            if (D == 3) LAUNCH(h, facet_ball_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
-            else LAUNCH(h, facet_ball_kernel<6>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+            if (h->volumetric) LAUNCH(h, (facet_ball_kernel<3, 4>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+            else if (D == 3) LAUNCH(h, (facet_ball_kernel<3, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+            else LAUNCH(h, (facet_ball_kernel<6, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
         }
         h->facet_area.ensure(ne);
-        if (ne > 0) {
+        if (ne > 0 && !h->volumetric) {
             if (D == 3) LAUNCH(h, facet_area_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
             else LAUNCH(h, facet_area_kernel<6>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
         }

@@ -57,13 +57,13 @@ struct FacetPairArgs {
 // not strictly inside (candidate neighbours); *hop = first bisector with the facet centroid outside
 // (the neighbour is closer to the centroid than s), -1 if none.
 // The side values only feed conservative decisions (a rounding margin is applied), so FMA is used.
-template <int D, bool HOME>
+template <int D, int NC, bool HOME>
 __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2, const double* pi, const double* prow, u32 nn,
                                               bool* empty, u32* cand, int* hop) {
     constexpr int PS = PLANE_STRIDE(D);
     double R2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) R2 = fmax(R2, dist2<D>(pi, v[i]));
+    for (int i = 0; i < NC; ++i) R2 = fmax(R2, dist2<D>(pi, v[i]));
     const double R2lim = 4.1 * R2;
     u32 mask = 0, cm = 0;
     bool emp = false;
@@ -94,18 +94,22 @@ __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2
         const double d = pl[D];
         // rounding margin of a side value 2 q.n - d for any point q of the facet: |q.n| <= (|q|^2 + |n|^2) / 2
         const double margin = 1e-12 * (fabs(d) + vmax2 + dij);
-        double tk[3];
+        double tsum = 0.0;
+        bool all_in = true, all_out = true;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NC; ++i) {
             double l = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) l = fma(v[i][c], nj[c], l);
-            tk[i] = fma(2.0, l, -d);
+            const double tk = fma(2.0, l, -d);
+            tsum += tk;
+            all_in = all_in && (tk > margin);
+            all_out = all_out && (tk < -margin);
         }
-        if (HOME && tk[0] + tk[1] + tk[2] < 0.0) { *hop = (int)jj; break; }
-        if (tk[0] > margin && tk[1] > margin && tk[2] > margin) continue;   // clearly inside: cannot touch any clipped polygon
+        if (HOME && tsum < 0.0) { *hop = (int)jj; break; }
+        if (all_in) continue;   // clearly inside: cannot touch any clipped polygon / cell
         cm |= 1u << jj;
-        if (tk[0] < -margin && tk[1] < -margin && tk[2] < -margin) emp = true;   // clearly outside: removes the polygon
+        if (all_out) emp = true;   // clearly outside: removes the element
         else mask |= 1u << jj;
     }
     *empty = emp;
@@ -124,15 +128,15 @@ __device__ __forceinline__ void emit_pair(const FacetPairArgs& a, u32 s, u32 f, 
 }
 
 // every owned seed inside the union of the balls B(c_i, |c_i - s0|), from the uniform grid
-template <int D>
+template <int D, int NC>
 __device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const double (*v)[D], double vmax2, u32 s0, u32 f) {
     constexpr int PS = PLANE_STRIDE(D);
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
-    double r2[3], lo3[3], hi3[3];
+    double r2[NC], lo3[3], hi3[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) { lo3[ax] = 1e300; hi3[ax] = -1e300; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NC; ++i) {
         r2[i] = dist2<D>(v[i], xs[s0].p) * (1.0 + 1e-12);
         const double rr = sqrt(r2[i]) * (1.0 + 1e-12);
 #pragma unroll
@@ -150,18 +154,20 @@ __device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const doubl
                     double ps[D];
 #pragma unroll
                     for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
-                    const bool in = dist2<D>(v[0], ps) <= r2[0] || dist2<D>(v[1], ps) <= r2[1] || dist2<D>(v[2], ps) <= r2[2];
+                    bool in = false;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) in = in || dist2<D>(v[i], ps) <= r2[i];
                     if (!in) continue;
                     const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
                     bool empty = false;
-                    const u32 mask = classify_facet<D, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                    const u32 mask = classify_facet<D, NC, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
                     if (!empty) emit_pair<D>(a, s, f, mask);
                 }
             }
 }
 
 // kernel A: one thread per facet — home seed, classification of (facet, home), candidate tasks
-template <int D>
+template <int D, int NC>
 __global__ void __launch_bounds__(128, 4)
 facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
     constexpr int PS = PLANE_STRIDE(D);
@@ -172,11 +178,11 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
     const u32 nf = a.facet_list ? *a.facet_list_n : a.T;
     const u32 f = (e < nf) ? (a.facet_list ? a.facet_list[e] : e) : 0u;
     if (e < nf) {
-        double v[3][D];
-        const double* t = a.tri + (size_t)f * 3 * D;
+        double v[NC][D];
+        const double* t = a.tri + (size_t)f * NC * D;
         double vmax2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NC; ++i) {
             double q2 = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) { v[i][c] = t[i * D + c]; q2 += v[i][c] * v[i][c]; }
@@ -187,7 +193,12 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
         {
             double gc[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
+            for (int c = 0; c < D; ++c) {
+                double sc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) sc += v[i][c];
+                gc[c] = sc * (1.0 / NC);
+            }
             const u32 guess = a.facet_guess[f];
             if (guess != B200_NONE) s0 = a.rank_of[guess];
             else s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
@@ -201,7 +212,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             for (int c = 0; c < D; ++c) p0[c] = xs[s0].p[c];
             const u32 nn0 = min(min(a.nbr_n[s0], a.kstride), 31u);
             int hop = -1;
-            mask0 = classify_facet<D, true>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
+            mask0 = classify_facet<D, NC, true>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
             if (hop >= 0) { s0 = a.nbr[(size_t)s0 * a.kstride + hop]; cand = 0; continue; }
             // the scan reached the distance bound (or the list holds every other seed): s0 is the nearest seed of
             // the centroid and every candidate is in the list
@@ -219,16 +230,21 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             cand = 0;
             double gc[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0);
+            for (int c = 0; c < D; ++c) {
+                double sc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) sc += v[i][c];
+                gc[c] = sc * (1.0 / NC);
+            }
             s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
             a.facet_guess[f] = (u32)xs[s0].orig;
             if (a.stats) atomicAdd(&a.stats[14], 1ull);
-            double vv[3][D];
+            double vv[NC][D];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < NC; ++i)
 #pragma unroll
                 for (int c = 0; c < D; ++c) vv[i][c] = v[i][c];
-            grid_candidates<D>(a, vv, vmax2, s0, f);
+            grid_candidates<D, NC>(a, vv, vmax2, s0, f);
         }
     }
     // candidate tasks (seed, facet), appended with one atomic per warp
@@ -254,7 +270,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
 }
 
 // kernel B: one thread per candidate task — classification of (facet, candidate) with the candidate's bisectors
-template <int D>
+template <int D, int NC>
 __global__ void __launch_bounds__(128, 4)
 facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
     constexpr int PS = PLANE_STRIDE(D);
@@ -264,11 +280,11 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
         const uint2 tk = a.tasks[e];
         const u32 s = tk.x, f = tk.y;
         if (s < a.qbegin || s >= a.qend) continue;
-        double v[3][D];
-        const double* t = a.tri + (size_t)f * 3 * D;
+        double v[NC][D];
+        const double* t = a.tri + (size_t)f * NC * D;
         double vmax2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NC; ++i) {
             double q2 = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) { v[i][c] = t[i * D + c]; q2 += v[i][c] * v[i][c]; }
@@ -279,7 +295,7 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
         for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
         const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
         bool empty = false;
-        const u32 mask = classify_facet<D, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+        const u32 mask = classify_facet<D, NC, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
         if (!empty) emit_pair<D>(a, s, f, mask);
     }
 }
@@ -288,34 +304,47 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
 // sharded runs: which facets can meet the cell of an owned seed at all
 // ---------------------------------------------------------------------------------------
 // once per mesh: bounding ball of every facet about its centroid, in float (radius inflated for the rounding)
-template <int D>
+template <int D, int NC>
 __global__ void facet_ball_kernel(const double* tri, u32 T, float4* ball) {
     const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= T) return;
-    const double* t = tri + (size_t)f * 3 * D;
-    double v[3][D], gc[D];
+    const double* t = tri + (size_t)f * NC * D;
+    double v[NC][D], gc[D];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int c = 0; c < D; ++c) v[i][c] = t[i * D + c];
     double gmax = 0.0;
 #pragma unroll
-    for (int c = 0; c < D; ++c) { gc[c] = (v[0][c] + v[1][c] + v[2][c]) * (1.0 / 3.0); gmax = fmax(gmax, fabs(gc[c])); }
+    for (int c = 0; c < D; ++c) {
+        double sc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) sc += v[i][c];
+        gc[c] = sc * (1.0 / NC); gmax = fmax(gmax, fabs(gc[c]));
+    }
     // the grid lives in the first three coordinates; distances in D dimensions are not smaller
-    double rho = sqrt(fmax(fmax(dist2<D>(gc, v[0]), dist2<D>(gc, v[1])), dist2<D>(gc, v[2])));
+    double rho2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) rho2 = fmax(rho2, dist2<D>(gc, v[i]));
+    double rho = sqrt(rho2);
     rho = rho * (1.0 + 1e-6) + 4e-7 * gmax + 1e-30;
     ball[f] = make_float4((float)gc[0], (float)gc[1], (float)gc[2], __double2float_ru(rho));
 }
 
 // once per grid: the grid cell of every facet centroid
-template <int D>
+template <int D, int NC>
 __global__ void facet_cell_kernel(const double* tri, u32 T, GridParams g, u32* facet_cell) {
     const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= T) return;
-    const double* t = tri + (size_t)f * 3 * D;
+    const double* t = tri + (size_t)f * NC * D;
     double gc[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gc[c] = (t[c] + t[D + c] + t[2 * D + c]) * (1.0 / 3.0);
+    for (int c = 0; c < 3; ++c) {
+        double sc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) sc += t[i * D + c];
+        gc[c] = sc * (1.0 / NC);
+    }
     facet_cell[f] = morton_encode(g, grid_coord(g, gc[0], 0), grid_coord(g, gc[1], 1), grid_coord(g, gc[2], 2));
 }
 

@@ -596,6 +596,8 @@ typedef struct {
     u32 first_free; int dirty;
 } orc_cell;
 
+static u32 orc_cell_high_water[2] = {0, 0};   /* most triangle slots / planes one cell ever used (sizing of the GPU cell) */
+void orc_cell_high_water_get(u32* out, int reset) { out[0] = orc_cell_high_water[0]; out[1] = orc_cell_high_water[1]; if (reset) orc_cell_high_water[0] = orc_cell_high_water[1] = 0; }
 static const u32 c_plus1[3] = {1, 2, 0}, c_minus1[3] = {2, 0, 1};
 
 static void cell_clear(orc_cell* C) { C->first_free = CELL_END; C->nt = 0; C->nv = 0; C->dirty = 0; }   /* :201-207 */
@@ -606,8 +608,6 @@ static u32 cell_create_vertex(orc_cell* C) {                                    
     if (C->nv + 1 > orc_cell_high_water[1]) orc_cell_high_water[1] = C->nv + 1;
     return C->nv++;
 }
-static u32 orc_cell_high_water[2] = {0, 0};   /* most triangle slots / planes one cell ever used (sizing of the GPU cell) */
-void orc_cell_high_water_get(u32* out, int reset) { out[0] = orc_cell_high_water[0]; out[1] = orc_cell_high_water[1]; if (reset) orc_cell_high_water[0] = orc_cell_high_water[1] = 0; }
 static u32 cell_create_triangle(orc_cell* C) {                                                          /* :663-672, grow :1324-1328 */
     if (C->first_free == CELL_END) {
         if (C->nt == C->tcap) { C->tcap = C->tcap ? 2 * C->tcap : 64; C->tri = (orc_ctri*)realloc(C->tri, sizeof(orc_ctri) * C->tcap); }

@@ -62,6 +62,39 @@ def case(V, F, X, weights=None, lloyd_iters=5, newton_iters=4):
     return out
 
 
+def volume_case(V, T, X, lloyd_iters=4, newton_iters=3):
+    """Volumetric mode (RestrictedVoronoiDiagram::set_volumetric(true)): T holds tetrahedra."""
+    out = dict(V=V, F=T, X=X, volumetric=np.int32(1))
+
+    def fresh(x):
+        r = RefCVT(V, T, volumetric=True, multithread=False)
+        r.set_points(x)
+        return r
+    r = fresh(X); r.update_delaunay()
+    out["knn_idx"], out["knn_cnt"] = r.neighbors(20)
+    out["mg"], out["m"], _ = r.centroids(False)
+    r.close()
+    r = fresh(X); r.update_delaunay()
+    out["mg_exact"], out["m_exact"], _ = r.centroids(True)
+    r.close()
+    r = fresh(X); r.update_delaunay()
+    out["f"], out["g"], _ = r.funcgrad(True)
+    out["f"] = np.float64(out["f"])
+    r.close()
+    r = fresh(X); r.lloyd(lloyd_iters)
+    out["x_lloyd"] = r.points()
+    out["lloyd_iters"] = np.int32(lloyd_iters)
+    r.close()
+    r = fresh(out["x_lloyd"]); r.newton(newton_iters, 7)
+    out["x_newton"] = r.points()
+    out["newton_iters"] = np.int32(newton_iters)
+    r.close()
+    r = fresh(out["x_newton"]); r.update_delaunay()
+    out["f_after_newton"] = np.float64(r.funcgrad(True)[0])
+    r.close()
+    return out
+
+
 def main():
     V, F = shapes.icosphere(6)
     np.savez_compressed(os.path.join(HERE, "sphere_s150.npz"), **case(V, F, shapes.sample_surface(V, F, 150, 3)))
@@ -73,6 +106,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sphere6d_s120.npz"), **case(V6, F, shapes.sample_surface(V6, F, 120, 7)))
     V, F = shapes.trefoil_tube(48, 10)
     np.savez_compressed(os.path.join(HERE, "trefoil_s200.npz"), **case(V, F, shapes.sample_surface(V, F, 200, 9)))
+    V, T = shapes.kuhn_cube(6)
+    X = np.random.default_rng(13).random((130, 3))
+    np.savez_compressed(os.path.join(HERE, "volume_cube_s130.npz"), **volume_case(V, T, X))
     for n in sorted(os.listdir(HERE)):
         if n.endswith(".npz"):
             print(n, os.path.getsize(os.path.join(HERE, n)))

@@ -22,7 +22,9 @@ from oracle import port
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("volume_")]
+GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
 def load(path):
@@ -354,3 +356,113 @@ def test_sharded_lloyd_two_partitions_one_gpu(built):
     assert np.array_equal(results[0][0], results[1][0])
     assert np.array_equal(results[0][0], x1)          # sharding does not change a single bit
     assert results[0][1] == info
+
+
+# ---------------------------------------------------------------------------------------
+# volumetric mode (C5): tetrahedra clipped as convex cells, SURVEY.md §8 rows a7 / a11
+# ---------------------------------------------------------------------------------------
+def volume_handle(V, T):
+    h = capi.Handle(3, volumetric=True)
+    h.set_mesh(V, T)
+    return h
+
+
+def untruncated(V, T, x):
+    """Seeds whose Lloyd-mode cell (20 stored neighbours, no enlargement) IS their restricted Voronoi cell: the oracle's
+    check_SR = false and check_SR = true results agree. Elsewhere the reference's result depends on which (tet, seed)
+    pairs its flood fill happens to reach (flagged near-degenerate configurations)."""
+    eL = port.surface_eval(V, T, x, 0, False)
+    eX = port.surface_eval(V, T, x, 0, True, kcap=min(256, x.shape[0] - 1))
+    same = np.abs(eL.m - eX.m) <= 1e-12 * eX.m.max()
+    return same, eL, eX
+
+
+@pytest.mark.parametrize("path", GOLDEN_VOLUME, ids=[os.path.basename(p) for p in GOLDEN_VOLUME])
+def test_volume_against_reference_golden(built, path):
+    G = load(path)
+    V, T, X = G["V"], G["F"], G["X"]
+    h = volume_handle(V, T)
+    # exact cells: no exemption
+    h.set_seeds(X)
+    mg, m = h.centroids(True)
+    assert_close(m, G["m_exact"], what="volume")
+    assert_close(mg, G["mg_exact"], what="volume*centroid")
+    assert abs(m.sum() - 1.0) <= 1e-12
+    h.set_seeds(X)
+    f, g = h.funcgrad(True)
+    assert abs(f - float(G["f"])) <= RTOL * abs(float(G["f"]))
+    assert_close(g, G["g"], what="gradient")
+    assert (h.flags() & (capi.FLAG_EXHAUSTED | capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    e = port.surface_eval(V, T, X, 1, True, kcap=X.shape[0] - 1)
+    assert_close(h.seed_energy(), e.f_seed, what="per-seed energy")
+    # Lloyd mode: parity wherever the 20-neighbour truncation does not change the cell
+    h.set_seeds(X)
+    mg, m = h.centroids(False)
+    ok, eL, eX = untruncated(V, T, X)
+    assert ok.sum() > 0
+    assert_close(m, G["m"], ok, "volume (Lloyd mode)")
+    assert_close(mg, G["mg"], ok, "volume*centroid (Lloyd mode)")
+    # Newton from the reference's Lloyd result
+    xn, info = h.newton(G["x_lloyd"], int(G["newton_iters"]), 7)
+    assert info["iters"] == int(G["newton_iters"]) + 1
+    assert np.abs(xn - G["x_newton"]).max() <= 1e-8
+    h.close()
+
+
+def test_volume_parity_with_oracle_t_over_s_10(built):
+    V, T = shapes.kuhn_cube(14)                      # 16 464 tets
+    X = np.random.default_rng(21).random((1600, 3))
+    x0, _ = port.lloyd(V, T, X, 4)                   # relaxed sampling, as after the first iterations of a run
+    h = volume_handle(V, T)
+    h.set_seeds(x0)
+    f, g = h.funcgrad(True)
+    e = port.surface_eval(V, T, x0, 1, True, kcap=256)
+    assert abs(f - e.f) <= RTOL * abs(e.f)
+    assert_close(g, e.g, what="gradient")
+    assert_close(h.seed_energy(), e.f_seed, what="per-seed energy")
+    h.set_seeds(x0)
+    mg, m = h.centroids(True)
+    ex = port.surface_eval(V, T, x0, 0, True, kcap=256)
+    assert_close(m, ex.m, what="volume")
+    assert_close(mg, ex.mg, what="volume*centroid")
+    assert np.abs(g - 2.0 * (m[:, None] * x0 - mg)).max() <= 1e-12      # g = 2 m (x - c) links rows a7 Lloyd and Newton
+    # Lloyd mode and Lloyd iterates
+    h.set_seeds(x0)
+    mgL, mL = h.centroids(False)
+    ok, eL, eX = untruncated(V, T, x0)
+    assert ok.mean() >= 0.97
+    assert_close(mL, eL.m, ok, "volume (Lloyd mode)")
+    assert_close(mgL, eL.mg, ok, "volume*centroid (Lloyd mode)")
+    if ok.all():
+        xg = h.lloyd(x0, 2)
+        xo, _ = port.lloyd(V, T, x0, 2)
+        assert np.abs(xg - xo).max() <= 1e-9
+    # Newton trajectory against the oracle: same iteration and evaluation counts
+    xn, info = h.newton(x0, 4, 7)
+    xo, io = port.newton(V, T, x0, 4, 7)
+    assert info["iters"] == io["iters"] and info["nfev"] == io["nfev"]
+    assert np.abs(xn - xo).max() <= 1e-8
+    h.close()
+
+
+def test_volume_properties_large(built):
+    # size-independent properties at a size the oracle does not finish in seconds: 196 608 tets, 20 000 seeds
+    V, T = shapes.kuhn_cube(32)
+    X = 0.02 + 0.96 * np.random.default_rng(8).random((20000, 3))
+    h = volume_handle(V, T)
+    x = h.lloyd(X, 3)
+    h.set_seeds(x)
+    mg, m = h.centroids(True)
+    assert (h.flags() & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    assert abs(m.sum() - 1.0) <= 1e-11                                   # the cells tile the unit cube
+    assert np.abs(mg.sum(0) - 0.5).max() <= 1e-11
+    h.set_seeds(x)
+    f, g = h.funcgrad(True)
+    assert np.abs(g - 2.0 * (m[:, None] * x - mg)).max() <= 1e-12
+    assert f > 0 and abs(h.seed_energy().sum() - f) <= 1e-12 * f
+    # Lloyd decreases the CVT energy
+    x2 = h.lloyd(x, 2)
+    h.set_seeds(x2)
+    f2, _ = h.funcgrad(True)
+    assert f2 < f
+    h.close()

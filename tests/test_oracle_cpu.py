@@ -10,7 +10,9 @@ import pytest
 from graphitethree_b200 import shapes
 from oracle import port, ref
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("volume_")]
+GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
 def load(path):
@@ -110,3 +112,71 @@ def test_facet_adjacency_closed_surface():
     for lv in range(3):
         back = adj[adj[:, lv]]
         assert ((back == f[:, None]).sum(1) == 1).all()
+
+
+# ---------------------------------------------------------------------------------------
+# volumetric mode (tetrahedra, GEOGen::ConvexCell restatement)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN_VOLUME, ids=[os.path.basename(p) for p in GOLDEN_VOLUME])
+def test_volume_oracle_matches_reference_golden(path):
+    G = load(path)
+    V, T, X = G["V"], G["F"], G["X"]
+    assert T.shape[1] == 4
+    e = port.surface_eval(V, T, X, 0, False)
+    assert np.array_equal(e.m, G["m"]) and np.array_equal(e.mg, G["mg"])          # bit-exact (same traversal order)
+    e = port.surface_eval(V, T, X, 0, True, kcap=129)
+    assert np.array_equal(e.m, G["m_exact"]) and np.array_equal(e.mg, G["mg_exact"])
+    e = port.surface_eval(V, T, X, 1, True, kcap=129)
+    assert e.f == float(G["f"]) and np.array_equal(e.g, G["g"])
+    x, _ = port.lloyd(V, T, X, int(G["lloyd_iters"]))
+    assert np.array_equal(x, G["x_lloyd"])
+    xn, info = port.newton(V, T, G["x_lloyd"], int(G["newton_iters"]), 7, kcap=129)
+    assert info["iters"] == int(G["newton_iters"]) + 1
+    assert np.abs(xn - G["x_newton"]).max() <= 1e-12
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_volume_oracle_matches_live_reference():
+    V, T = shapes.kuhn_cube(10)
+    X = np.random.default_rng(3).random((600, 3))
+    r = ref.RefCVT(V, T, volumetric=True, multithread=False)
+    try:
+        r.set_points(X)
+        r.update_delaunay()
+        mg, m, _ = r.centroids(False)
+        e = port.surface_eval(V, T, X, 0, False)
+        assert np.array_equal(m, e.m) and np.array_equal(mg, e.mg)
+        f, g, _ = r.funcgrad(True)
+        e = port.surface_eval(V, T, X, 1, True, kcap=256)
+        assert f == e.f and np.array_equal(g, e.g)
+    finally:
+        r.close()
+
+
+def test_volume_analytic_identities_exact_cells():
+    V, T = shapes.kuhn_cube(7)
+    X = 0.05 + 0.9 * np.random.default_rng(2).random((200, 3))
+    ec = port.surface_eval(V, T, X, 0, True, kcap=199)
+    assert abs(ec.m.sum() - 1.0) <= 1e-12                                          # cells tile the unit cube
+    assert np.abs(ec.mg.sum(0) - 0.5).max() <= 1e-12
+    eg = port.surface_eval(V, T, X, 1, True, kcap=199)
+    assert np.abs(eg.g - 2.0 * (ec.m[:, None] * X - ec.mg)).max() <= 1e-13         # g = 2 m (x - c)
+    assert abs(eg.f_seed.sum() - eg.f) <= 1e-15
+    rng = np.random.default_rng(1)
+    d = rng.standard_normal(X.shape)
+    h = 1e-6
+    fp = port.surface_eval(V, T, X + h * d, 1, True, kcap=199).f
+    fm = port.surface_eval(V, T, X - h * d, 1, True, kcap=199).f
+    assert abs((fp - fm) / (2 * h) - (eg.g * d).sum()) <= 1e-5 * abs((eg.g * d).sum())
+
+
+def test_tet_adjacency_kuhn_cube():
+    V, T = shapes.kuhn_cube(3)
+    adj = port.tet_adjacency(T)
+    # 6 n^3 tets, 4 faces each; the cube's boundary carries 2 * 6 n^2 triangles
+    assert (adj < 0).sum() == 12 * 9
+    t = np.arange(T.shape[0])
+    for lf in range(4):
+        ok = adj[:, lf] >= 0
+        back = adj[adj[ok, lf]]
+        assert ((back == t[ok, None]).sum(1) == 1).all()
