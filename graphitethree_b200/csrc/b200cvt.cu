@@ -257,8 +257,8 @@ struct b200cvt_ctx {
     // flat pair list (seed-major, facets ascending) + per-pair contributions
     DevBuf<u32> pair_off, flat_seed, flat_facet, slow_list;
     DevBuf<double> contrib, facet_area, planes;
-    DevBuf<uint8_t> pstat, pclass, pclass_sorted;
-    DevBuf<u32> flat_mask, iota, order;
+    DevBuf<uint8_t> pstat;
+    DevBuf<u32> flat_mask, iota;
     DevBuf<unsigned char> sort_tmp;
     size_t iota_filled = 0;
     u32 npairs = 0;
@@ -687,7 +687,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
     const u32 nown = h->qend() - h->qbegin();
     const u32 np = h->npairs;
-    h->flat_seed.ensure(np); h->flat_facet.ensure(np); h->flat_mask.ensure(np); h->pclass.ensure(np);
+    h->flat_seed.ensure(np); h->flat_facet.ensure(np); h->flat_mask.ensure(np);
     h->pstat.ensure(np); h->slow_list.ensure(nown);
     h->contrib.ensure((size_t)np * (D + 1));
     const size_t cstride = h->contrib.cap / (D + 1);
@@ -695,40 +695,31 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         CompactArgs ca;
         ca.pair_cnt = h->pair_cnt.p; ca.pair_facet = h->pair_facet.p; ca.pair_mask = h->pair_mask.p; ca.cap = h->pair_cap;
         ca.pair_off = h->pair_off.p; ca.qbegin = h->qbegin(); ca.nown = nown;
-        ca.flat_seed = h->flat_seed.p; ca.flat_facet = h->flat_facet.p; ca.flat_mask = h->flat_mask.p; ca.pclass = h->pclass.p;
+        ca.flat_seed = h->flat_seed.p; ca.flat_facet = h->flat_facet.p; ca.flat_mask = h->flat_mask.p;
         LAUNCH(h, compact_pairs_kernel, div_up(nown, 8), 256, 0, ca);
     }
     if (np > 0) {
-        h->pclass_sorted.ensure(np); h->order.ensure(np); h->iota.ensure(np);
-        if (h->iota_filled < h->iota.cap) {
-            LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
-            h->iota_filled = h->iota.cap;
-        }
         ClipFlatArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.xs = h->xs.p; fa.nbr = h->nbr.p; fa.nbr_n = h->nbr_n.p; fa.kstride = h->kstride; fa.planes = h->planes.p;
         fa.tri = h->tri.p; fa.triw = h->weighted ? h->triw.p : nullptr; fa.facet_area = h->facet_area.p;
         fa.flat_seed = h->flat_seed.p; fa.flat_facet = h->flat_facet.p; fa.npairs_dev = h->pair_off.p + nown;
         fa.mode = mode; fa.contrib = h->contrib.p; fa.cstride = cstride; fa.pstat = h->pstat.p;
-        fa.flat_mask = h->flat_mask.p; fa.order = h->order.p;
+        fa.flat_mask = h->flat_mask.p;
         fa.stats = h->want_stats ? h->stats.p : nullptr;
-        // group the pairs by the number of bisectors that may cut them (stable: seed order kept inside a class)
-        size_t sort_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h->pclass.p, h->pclass_sorted.p, h->iota.p, h->order.p, (int)np, 0, 3, h->stream);
-        h->sort_tmp.ensure(sort_bytes);
-        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, sort_bytes, h->pclass.p, h->pclass_sorted.p, h->iota.p, h->order.p, (int)np, 0, 3,
-                                                   h->stream));
-        h->launches += 3;
         const int VW = D + (h->weighted ? 1 : 0);
-        const size_t smem = (size_t)CLIPF_WARPS * CLIPF_MAXV * VW * 32 * sizeof(double);
-        const u32 blocks = div_up(np, CLIPF_WARPS * 32);
+        const size_t smem = (size_t)CLIPW_NW * CLIPF_MAXV * VW * 32 * sizeof(double) + CLIPW_W * sizeof(unsigned short) +
+                            CLIPW_NCNT * sizeof(u32);
+        // windows of the seed-major pair list, a few per resident block
+        const u32 per_sm = std::max<u32>(1, std::min<u32>(8, (u32)((227 * 1024) / (smem + 1024))));
+        const u32 blocks = std::min<u32>(div_up(np, CLIPW_W), (u32)h->num_sms * per_sm);
         CUDA_CHECK(cudaEventRecord(h->evk[0], h->stream));
         if (h->weighted) {
-            CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LAUNCH(h, (clip_cut_kernel<D, true>), blocks, CLIPF_WARPS * 32, smem, fa);
+            CUDA_CHECK(cudaFuncSetAttribute(clip_win_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(h, (clip_win_kernel<D, true>), blocks, CLIPW_THREADS, smem, fa);
         } else {
-            CUDA_CHECK(cudaFuncSetAttribute(clip_cut_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LAUNCH(h, (clip_cut_kernel<D, false>), blocks, CLIPF_WARPS * 32, smem, fa);
+            CUDA_CHECK(cudaFuncSetAttribute(clip_win_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(h, (clip_win_kernel<D, false>), blocks, CLIPW_THREADS, smem, fa);
         }
         CUDA_CHECK(cudaEventRecord(h->evk[1], h->stream));
     }
@@ -991,8 +982,8 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->nbr_big.release(); h->nbr_big_n.release(); h->pair_cnt.release(); h->pair_facet.release(); h->max_cnt.release();
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
-    h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release(); h->pclass.release(); h->pclass_sorted.release();
-    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->order.release(); h->sort_tmp.release();
+    h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release();
+    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

@@ -33,8 +33,7 @@
 #include "common.cuh"
 #include "clip.cuh"
 
-#define CLIPF_WARPS 4
-#define CLIPF_MAXV 12
+#define CLIPF_MAXV 11
 
 #define PSTAT_EXHAUSTED 1u
 #define PSTAT_SLOW 16u
@@ -52,7 +51,6 @@ struct CompactArgs {
     u32* flat_seed;           // [npairs] sorted position of the seed
     u32* flat_facet;          // [npairs]
     u32* flat_mask;           // [npairs]
-    uint8_t* pclass;          // [npairs] sort key of the clip kernel: min(popcount(mask bits), PCLASS_MAXCUT)
 };
 
 #define PCLASS_MAXCUT 7u
@@ -82,7 +80,6 @@ compact_pairs_kernel(CompactArgs a) {
             if (lane < n) {
                 const u32 m = (u32)v;
                 a.flat_facet[off + lane] = (u32)(v >> 32); a.flat_seed[off + lane] = s; a.flat_mask[off + lane] = m;
-                a.pclass[off + lane] = (uint8_t)min((u32)__popc(m & 0x7fffffffu), PCLASS_MAXCUT);
             }
         } else {
             // rank by counting (facet ids of one seed are distinct)
@@ -91,7 +88,6 @@ compact_pairs_kernel(CompactArgs a) {
                 u32 r = 0;
                 for (u32 u = 0; u < n; ++u) r += (row[u] < v) ? 1u : 0u;
                 a.flat_facet[off + r] = v; a.flat_seed[off + r] = s; a.flat_mask[off + r] = m;
-                a.pclass[off + r] = (uint8_t)min((u32)__popc(m & 0x7fffffffu), PCLASS_MAXCUT);
             }
         }
     }
@@ -244,212 +240,273 @@ struct ClipFlatArgs {
     size_t cstride;
     uint8_t* pstat;             // [npairs]
     const u32* flat_mask;       // [npairs] bisectors (positions in the neighbour list) that may cut the pair | PMASK_SR_OK
-    const u32* order;           // [npairs] pair indices sorted by number of masked bisectors
     unsigned long long* stats;  // optional
 };
 
 // ---------------------------------------------------------------------------------------
 // clipping of the pairs with at least one masked bisector
 // ---------------------------------------------------------------------------------------
+struct ClipStats { unsigned long long planes = 0, cuts = 0, tri = 0, ne = 0; };
+
+// one candidate pair t: clip facet f by the masked bisectors of seed s and integrate. P = this thread's polygon
+// (lane-interleaved shared memory, stride 32 doubles between consecutive values)
 template <int D, bool WEIGHTED>
-__global__ void __launch_bounds__(CLIPF_WARPS * 32)
-clip_cut_kernel(ClipFlatArgs a) {
-    // [warp][vertex][coord (+ weight)][lane]
+__device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t, double* P, ClipStats& st) {
+    constexpr int VW = D + (WEIGHTED ? 1 : 0);
+    constexpr int PS = PLANE_STRIDE(D);
+#define PV(k, c) P[((k) * VW + (c)) * 32]
+    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    const u32 s = a.flat_seed[t];
+    const u32 f = a.flat_facet[t];
+    const u32 mask_in = a.flat_mask[t];
+    u32 mask = mask_in & 0x7fffffffu;
+    double pi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) pi[c] = xs[s].p[c];
+    const u32 nn = min(min(a.nbr_n[s], a.kstride), 32u);
+    const double* prow = a.planes + (size_t)s * a.kstride * PS;
+    int n = 3;
+    double R2 = 0.0;
+    {
+        const double* tp = a.tri + (size_t)f * 3 * D;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double v[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) { v[c] = tp[i * D + c]; PV(i, c) = v[c]; }
+            if (WEIGHTED) PV(i, D) = a.triw[(size_t)f * 3 + i];
+            R2 = fmax(R2, dist2<D>(pi, v));
+        }
+    }
+    // no masked bisector: the cell contains the facet, the radius test was decided on the unclipped facet
+    bool sr_ok = (mask == 0) && (mask_in & 0x80000000u), slow = false, cut_any = false;
+    int last_jj = (mask == 0) ? (int)nn - 1 : -1;
+    // clip_by_cell_SR (generic_RVD.h:2155-2177) over the masked bisectors, increasing distance
+    while (mask) {
+        const int jj = __ffs(mask) - 1;
+        mask &= mask - 1;
+        double2 rowbuf[PS / 2];
+        {
+            const double2* r2 = (const double2*)(prow + (size_t)jj * PS);
+#pragma unroll
+            for (int q = 0; q < PS / 2; ++q) rowbuf[q] = __ldg(r2 + q);
+        }
+        const double* pl = (const double*)rowbuf;
+        if (pl[D + 1] > 4.1 * R2) { sr_ok = true; break; }
+        last_jj = jj;
+        ++st.planes;
+        double nj[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) nj[c] = pl[c];
+        const double d = pl[D];
+        // pass 1: side of every vertex (generic_RVD_polygon.h:276-297)
+        u32 pos = 0, neg = 0;
+        for (int k = 0; k < n; ++k) {
+            double l = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) l += PV(k, c) * nj[c];
+            const double tk = 2.0 * l - d;
+            pos |= (tk > 0.0 ? 1u : 0u) << k;
+            neg |= (tk < 0.0 ? 1u : 0u) << k;
+        }
+        const u32 full = (1u << n) - 1u;
+        if (pos == full) continue;                 // nothing to cut
+        ++st.cuts;
+        cut_any = true;
+        // pass 2 (generic_RVD_polygon.h:299-362). A crossing is emitted where the side changes and the
+        // previous vertex is not on the plane; a convex polygon has at most two.
+        const u32 ppos = ((pos << 1) | (pos >> (n - 1))) & full;   // bit k = side of vertex k-1
+        const u32 pneg = ((neg << 1) | (neg >> (n - 1))) & full;
+        const u32 X = (ppos | pneg) & ((pos ^ ppos) | (neg ^ pneg));
+        const int nx = __popc(X);
+        if (nx > 2 || __popc(pos) + nx > CLIPF_MAXV) { slow = true; break; }
+        double I[2][VW];
+        int kx0 = -1, kx1 = -1;
+        {
+            u32 xr = X;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int c = 0; c < VW; ++c) I[q][c] = 0.0;
+                if (xr) {
+                    const int k = __ffs(xr) - 1;
+                    xr &= xr - 1;
+                    if (q == 0) kx0 = k; else kx1 = k;
+                    const int kp = (k == 0) ? n - 1 : k - 1;
+                    double vp[VW], vc[VW];
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) { vp[c] = PV(kp, c); vc[c] = PV(k, c); }
+                    double lp = 0.0, l = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) { lp += vp[c] * nj[c]; l += vc[c] * nj[c]; }
+                    const double denom = 2.0 * (lp - l);
+                    double l1, l2;
+                    if (fabs(denom) < 1e-20) { l1 = 0.5; l2 = 0.5; }
+                    else { l1 = (d - 2.0 * l) / denom; l2 = 1.0 - l1; }
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) I[q][c] = l1 * vp[c] + l2 * vc[c];
+                }
+            }
+        }
+        int m = 0;
+        double R2n = 0.0;
+        double vc[VW], vn[VW];
+#pragma unroll
+        for (int c = 0; c < VW; ++c) { vc[c] = PV(0, c); vn[c] = 0.0; }
+        for (int k = 0; k < n; ++k) {
+            if (k + 1 < n) {
+#pragma unroll
+                for (int c = 0; c < VW; ++c) vn[c] = PV(k + 1, c);
+            }
+            if (k == kx0 || k == kx1) {
+                // m <= k + 1: at most one crossing precedes without a dropped vertex
+                double Iq[VW];
+#pragma unroll
+                for (int c = 0; c < VW; ++c) { Iq[c] = (k == kx0) ? I[0][c] : I[1][c]; PV(m, c) = Iq[c]; }
+                R2n = fmax(R2n, dist2<D>(pi, Iq));
+                ++m;
+            }
+            if ((pos >> k) & 1u) {
+                if (m != k) {
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) PV(m, c) = vc[c];
+                }
+                R2n = fmax(R2n, dist2<D>(pi, vc));
+                ++m;
+            }
+#pragma unroll
+            for (int c = 0; c < VW; ++c) vc[c] = vn[c];
+        }
+        n = m;
+        R2 = R2n;
+        if (n == 0) break;
+    }
+
+    double acc_s = 0.0, acc_v[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc_v[c] = 0.0;
+    uint8_t ps = 0;
+    if (slow) ps = PSTAT_SLOW;
+    else {
+        if (!sr_ok && n > 0 && nn > 0) {
+            // the reference goes on testing the remaining neighbours (unmasked: they cannot cut);
+            // the list is sorted, so the radius test passes for one of them iff it passes for the last
+            if (last_jj < (int)nn - 1) sr_ok = prow[(size_t)(nn - 1) * PS + D + 1] > 4.1 * R2;
+            // list used up before the radius test passed (generic_RVD.h:2179-2181)
+            if (!sr_ok) ps = PSTAT_EXHAUSTED;
+        }
+        if (n >= 3) {
+            ++st.ne;
+            if (!cut_any) {
+                double p1[VW], p2[VW], p3[VW];
+#pragma unroll
+                for (int c = 0; c < VW; ++c) { p1[c] = PV(0, c); p2[c] = PV(1, c); p3[c] = PV(2, c); }
+                ++st.tri;
+                integrate_triangle<D, WEIGHTED>(p1, p2, p3, a.facet_area[f], pi, a.mode, acc_s, acc_v);
+            } else {
+                // TriangleAction fan (generic_RVD.h:452-463)
+                double p1[VW], p2[VW], p3[VW];
+#pragma unroll
+                for (int c = 0; c < VW; ++c) { p1[c] = PV(0, c); p3[c] = PV(1, c); }
+                double ea = sqrt(dist2<D>(p1, p3));
+                for (int i = 1; i + 1 < n; ++i) {
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) { p2[c] = p3[c]; p3[c] = PV(i + 1, c); }
+                    ++st.tri;
+                    const double eb = sqrt(dist2<D>(p2, p3));
+                    const double ec = sqrt(dist2<D>(p3, p1));
+                    const double area = heron_area<D>(ea, eb, ec);
+                    ea = ec;
+                    integrate_triangle<D, WEIGHTED>(p1, p2, p3, area, pi, a.mode, acc_s, acc_v);
+                }
+            }
+        }
+    }
+    a.contrib[t] = acc_s;
+#pragma unroll
+    for (int c = 0; c < D; ++c) a.contrib[(size_t)(c + 1) * a.cstride + t] = acc_v[c];
+    a.pstat[t] = ps;
+#undef PV
+}
+
+// Pairs are taken in windows of CLIPW_W consecutive entries of the seed-major pair list (= a few dozen
+// Morton-neighbouring seeds and the facets around them: facet corners, bisector rows and the per-pair outputs of a
+// window stay in L1/L2). Inside a window the pairs are counting-sorted by class (number of bisectors that may cut
+// them) in shared memory, so that the lanes of a warp run the same number of plane iterations; each thread then
+// clips CLIPW_ROUNDS pairs, one from each quarter of the sorted window (equal work per warp).
+#define CLIPW_THREADS 128
+#define CLIPW_ROUNDS 4
+#define CLIPW_W (CLIPW_THREADS * CLIPW_ROUNDS)
+#define CLIPW_NW (CLIPW_THREADS / 32)
+#define CLIPW_NCNT (8 * CLIPW_ROUNDS * CLIPW_NW)
+
+template <int D, bool WEIGHTED>
+__global__ void __launch_bounds__(CLIPW_THREADS, (D == 3 && !WEIGHTED) ? 6 : 1)
+clip_win_kernel(ClipFlatArgs a) {
     constexpr int VW = D + (WEIGHTED ? 1 : 0);
     extern __shared__ double s_dyn[];
-    const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double* P = s_dyn + (size_t)w * (CLIPF_MAXV * VW * 32) + lane;
-#define PV(k, c) P[((k) * VW + (c)) * 32]
-    constexpr int PS = PLANE_STRIDE(D);
-    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    unsigned short* order = (unsigned short*)(s_dyn + (size_t)CLIPW_NW * CLIPF_MAXV * VW * 32);   // [CLIPW_W]
+    u32* ccnt = (u32*)(order + CLIPW_W);                                                          // [class][round][warp]
+    static_assert(CLIPW_NCNT == 32 * 4, "the counter scan below takes 4 counters per lane of one warp");
+    static_assert(CLIPW_NCNT <= CLIPW_THREADS, "one thread clears one counter");
     const u32 npairs = *a.npairs_dev;
-    unsigned long long st_planes = 0, st_cuts = 0, st_tri = 0, st_ne = 0;
-
-    for (u32 base = blockIdx.x * (CLIPF_WARPS * 32); base < npairs; base += gridDim.x * (CLIPF_WARPS * 32)) {
-        const u32 e = base + threadIdx.x;
-        if (e >= npairs) continue;
-        const u32 t = a.order[e];
-        const u32 s = a.flat_seed[t];
-        const u32 f = a.flat_facet[t];
-        const u32 mask_in = a.flat_mask[t];
-        u32 mask = mask_in & 0x7fffffffu;
-        double pi[D];
+    const u32 lt = (1u << lane) - 1u;
+    ClipStats st;
+    for (u32 base = blockIdx.x * CLIPW_W; base < npairs; base += gridDim.x * CLIPW_W) {
+        const u32 cnt = min((u32)CLIPW_W, npairs - base);
+        if (tid < CLIPW_NCNT) ccnt[tid] = 0;
+        __syncthreads();
+        // class and rank inside (class, round, warp) of every pair of the window
+        u32 pcls = 0, prank = 0;
 #pragma unroll
-        for (int c = 0; c < D; ++c) pi[c] = xs[s].p[c];
-        const u32 nn = min(min(a.nbr_n[s], a.kstride), 32u);
-        const double* prow = a.planes + (size_t)s * a.kstride * PS;
-        int n = 3;
-        double R2 = 0.0;
-        {
-            const double* tp = a.tri + (size_t)f * 3 * D;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double v[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) { v[c] = tp[i * D + c]; PV(i, c) = v[c]; }
-                if (WEIGHTED) PV(i, D) = a.triw[(size_t)f * 3 + i];
-                R2 = fmax(R2, dist2<D>(pi, v));
-            }
+        for (int r = 0; r < CLIPW_ROUNDS; ++r) {
+            const u32 idx = r * CLIPW_THREADS + tid;
+            u32 cls = 8;
+            if (idx < cnt) cls = min((u32)__popc(a.flat_mask[base + idx] & 0x7fffffffu), PCLASS_MAXCUT);
+            const u32 m = __match_any_sync(B200_FULL, cls);
+            const u32 rank = __popc(m & lt);
+            if (cls < 8 && rank == 0) ccnt[(cls * CLIPW_ROUNDS + r) * CLIPW_NW + w] = __popc(m);
+            pcls |= cls << (4 * r); prank |= rank << (8 * r);
         }
-        // no masked bisector: the cell contains the facet, the radius test was decided on the unclipped facet
-        bool sr_ok = (mask == 0) && (mask_in & 0x80000000u), slow = false, cut_any = false;
-        int last_jj = (mask == 0) ? (int)nn - 1 : -1;
-        // clip_by_cell_SR (generic_RVD.h:2155-2177) over the masked bisectors, increasing distance
-        while (mask) {
-            const int jj = __ffs(mask) - 1;
-            mask &= mask - 1;
-            double2 rowbuf[PS / 2];
-            {
-                const double2* r2 = (const double2*)(prow + (size_t)jj * PS);
+        __syncthreads();
+        if (w == 0) {
+            // exclusive scan of the counters in (class, round, warp) order = stable counting sort
+            u32 v[4], sum = 0;
 #pragma unroll
-                for (int q = 0; q < PS / 2; ++q) rowbuf[q] = __ldg(r2 + q);
+            for (int i = 0; i < 4; ++i) { v[i] = ccnt[lane * 4 + i]; sum += v[i]; }
+            u32 incl = sum;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                const u32 o = __shfl_up_sync(B200_FULL, incl, m);
+                if (lane >= m) incl += o;
             }
-            const double* pl = (const double*)rowbuf;
-            if (pl[D + 1] > 4.1 * R2) { sr_ok = true; break; }
-            last_jj = jj;
-            ++st_planes;
-            double nj[D];
+            u32 run = incl - sum;
 #pragma unroll
-            for (int c = 0; c < D; ++c) nj[c] = pl[c];
-            const double d = pl[D];
-            // pass 1: side of every vertex (generic_RVD_polygon.h:276-297)
-            u32 pos = 0, neg = 0;
-            for (int k = 0; k < n; ++k) {
-                double l = 0.0;
-#pragma unroll
-                for (int c = 0; c < D; ++c) l += PV(k, c) * nj[c];
-                const double tk = 2.0 * l - d;
-                pos |= (tk > 0.0 ? 1u : 0u) << k;
-                neg |= (tk < 0.0 ? 1u : 0u) << k;
-            }
-            const u32 full = (1u << n) - 1u;
-            if (pos == full) continue;                 // nothing to cut
-            ++st_cuts;
-            cut_any = true;
-            // pass 2 (generic_RVD_polygon.h:299-362). A crossing is emitted where the side changes and the
-            // previous vertex is not on the plane; a convex polygon has at most two.
-            const u32 ppos = ((pos << 1) | (pos >> (n - 1))) & full;   // bit k = side of vertex k-1
-            const u32 pneg = ((neg << 1) | (neg >> (n - 1))) & full;
-            const u32 X = (ppos | pneg) & ((pos ^ ppos) | (neg ^ pneg));
-            const int nx = __popc(X);
-            if (nx > 2 || __popc(pos) + nx > CLIPF_MAXV) { slow = true; break; }
-            double I[2][VW];
-            int kx0 = -1, kx1 = -1;
-            {
-                u32 xr = X;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) I[q][c] = 0.0;
-                    if (xr) {
-                        const int k = __ffs(xr) - 1;
-                        xr &= xr - 1;
-                        if (q == 0) kx0 = k; else kx1 = k;
-                        const int kp = (k == 0) ? n - 1 : k - 1;
-                        double vp[VW], vc[VW];
-#pragma unroll
-                        for (int c = 0; c < VW; ++c) { vp[c] = PV(kp, c); vc[c] = PV(k, c); }
-                        double lp = 0.0, l = 0.0;
-#pragma unroll
-                        for (int c = 0; c < D; ++c) { lp += vp[c] * nj[c]; l += vc[c] * nj[c]; }
-                        const double denom = 2.0 * (lp - l);
-                        double l1, l2;
-                        if (fabs(denom) < 1e-20) { l1 = 0.5; l2 = 0.5; }
-                        else { l1 = (d - 2.0 * l) / denom; l2 = 1.0 - l1; }
-#pragma unroll
-                        for (int c = 0; c < VW; ++c) I[q][c] = l1 * vp[c] + l2 * vc[c];
-                    }
-                }
-            }
-            int m = 0;
-            double R2n = 0.0;
-            double vc[VW], vn[VW];
-#pragma unroll
-            for (int c = 0; c < VW; ++c) { vc[c] = PV(0, c); vn[c] = 0.0; }
-            for (int k = 0; k < n; ++k) {
-                if (k + 1 < n) {
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) vn[c] = PV(k + 1, c);
-                }
-                if (k == kx0 || k == kx1) {
-                    // m <= k + 1: at most one crossing precedes without a dropped vertex
-                    double Iq[VW];
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) { Iq[c] = (k == kx0) ? I[0][c] : I[1][c]; PV(m, c) = Iq[c]; }
-                    R2n = fmax(R2n, dist2<D>(pi, Iq));
-                    ++m;
-                }
-                if ((pos >> k) & 1u) {
-                    if (m != k) {
-#pragma unroll
-                        for (int c = 0; c < VW; ++c) PV(m, c) = vc[c];
-                    }
-                    R2n = fmax(R2n, dist2<D>(pi, vc));
-                    ++m;
-                }
-#pragma unroll
-                for (int c = 0; c < VW; ++c) vc[c] = vn[c];
-            }
-            n = m;
-            R2 = R2n;
-            if (n == 0) break;
+            for (int i = 0; i < 4; ++i) { ccnt[lane * 4 + i] = run; run += v[i]; }
         }
-
-        double acc_s = 0.0, acc_v[D];
+        __syncthreads();
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc_v[c] = 0.0;
-        uint8_t ps = 0;
-        if (slow) ps = PSTAT_SLOW;
-        else {
-            if (!sr_ok && n > 0 && nn > 0) {
-                // the reference goes on testing the remaining neighbours (unmasked: they cannot cut);
-                // the list is sorted, so the radius test passes for one of them iff it passes for the last
-                if (last_jj < (int)nn - 1) sr_ok = prow[(size_t)(nn - 1) * PS + D + 1] > 4.1 * R2;
-                // list used up before the radius test passed (generic_RVD.h:2179-2181)
-                if (!sr_ok) ps = PSTAT_EXHAUSTED;
-            }
-            if (n >= 3) {
-                ++st_ne;
-                if (!cut_any) {
-                    double p1[VW], p2[VW], p3[VW];
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) { p1[c] = PV(0, c); p2[c] = PV(1, c); p3[c] = PV(2, c); }
-                    ++st_tri;
-                    integrate_triangle<D, WEIGHTED>(p1, p2, p3, a.facet_area[f], pi, a.mode, acc_s, acc_v);
-                } else {
-                    // TriangleAction fan (generic_RVD.h:452-463)
-                    double p1[VW], p2[VW], p3[VW];
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) { p1[c] = PV(0, c); p3[c] = PV(1, c); }
-                    double ea = sqrt(dist2<D>(p1, p3));
-                    for (int i = 1; i + 1 < n; ++i) {
-#pragma unroll
-                        for (int c = 0; c < VW; ++c) { p2[c] = p3[c]; p3[c] = PV(i + 1, c); }
-                        ++st_tri;
-                        const double eb = sqrt(dist2<D>(p2, p3));
-                        const double ec = sqrt(dist2<D>(p3, p1));
-                        const double area = heron_area<D>(ea, eb, ec);
-                        ea = ec;
-                        integrate_triangle<D, WEIGHTED>(p1, p2, p3, area, pi, a.mode, acc_s, acc_v);
-                    }
-                }
-            }
+        for (int r = 0; r < CLIPW_ROUNDS; ++r) {
+            const u32 cls = (pcls >> (4 * r)) & 15u, rank = (prank >> (8 * r)) & 255u;
+            if (cls < 8) order[ccnt[(cls * CLIPW_ROUNDS + r) * CLIPW_NW + w] + rank] = (unsigned short)(r * CLIPW_THREADS + tid);
         }
-        a.contrib[t] = acc_s;
-#pragma unroll
-        for (int c = 0; c < D; ++c) a.contrib[(size_t)(c + 1) * a.cstride + t] = acc_v[c];
-        a.pstat[t] = ps;
+        __syncthreads();
+        for (int r = 0; r < CLIPW_ROUNDS; ++r) {
+            const u32 p = r * CLIPW_THREADS + tid;
+            if (p < cnt) clip_one_pair<D, WEIGHTED>(a, base + order[p], P, st);
+        }
+        __syncthreads();
     }
-#undef PV
     if (a.stats) {
-        st_planes = (unsigned long long)warp_sum((double)st_planes);
-        st_cuts = (unsigned long long)warp_sum((double)st_cuts);
-        st_tri = (unsigned long long)warp_sum((double)st_tri);
-        st_ne = (unsigned long long)warp_sum((double)st_ne);
+        st.planes = (unsigned long long)warp_sum((double)st.planes);
+        st.cuts = (unsigned long long)warp_sum((double)st.cuts);
+        st.tri = (unsigned long long)warp_sum((double)st.tri);
+        st.ne = (unsigned long long)warp_sum((double)st.ne);
         if (lane == 0) {
-            atomicAdd(&a.stats[8], st_planes); atomicAdd(&a.stats[1], st_cuts);
-            atomicAdd(&a.stats[2], st_tri); atomicAdd(&a.stats[3], st_ne);
+            atomicAdd(&a.stats[8], st.planes); atomicAdd(&a.stats[1], st.cuts);
+            atomicAdd(&a.stats[2], st.tri); atomicAdd(&a.stats[3], st.ne);
         }
     }
 }

@@ -151,8 +151,11 @@ namespace GEO {
     }
 
     bool RestrictedVoronoiDiagramB200::gpu_eligible() const {
+        /* the range is NO_INDEX/NO_INDEX until set_facets_range is called (RVD.cpp:2623-2624) = the whole mesh */
+        const bool whole_mesh = (facets_begin_ == NO_INDEX && facets_end_ == NO_INDEX) ||
+            (facets_begin_ == 0 && facets_end_ == mesh_->facets.nb());
         return h_ != nullptr && !volumetric_ && !ref_->exact_predicates() && mesh_->facets.nb() > 0 &&
-            mesh_->facets.are_simplices() && facets_begin_ == 0 && facets_end_ == mesh_->facets.nb() &&
+            mesh_->facets.are_simplices() && whole_mesh &&
             delaunay_ != nullptr && delaunay_->nb_vertices() > 0;
     }
 

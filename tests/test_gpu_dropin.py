@@ -32,11 +32,14 @@ def write_inputs(tmp_path, V, F, X):
     return mp, sp
 
 
-def run_check(tmp_path, V, F, X, nl, nn, m=7):
+def run_check(tmp_path, V, F, X, nl, nn, m=7, pre=1):
+    """pre = stock Lloyd iterations that make the common start: on a raw random sampling the reference's own first
+    iteration depends on its thread count (cells that need more than 20 neighbours, check_SR = false; measured 7e-3
+    between 1, 3 and 8 threads, 5e-15 afterwards) — the flagged configurations of the parity statement."""
     if not os.path.exists(EXE):
         pytest.fail("integration/_build/dropin_check is missing: run __graft_entry__.build() where /root/reference exists")
     mp, sp = write_inputs(tmp_path, V, F, X)
-    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m)], capture_output=True, text=True, timeout=900)
+    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m), str(pre)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
     print(r)
