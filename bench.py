@@ -321,7 +321,7 @@ def main():
                            "l2": "inputs larger than L2 (facet table %d MB, re-sorted seeds every evaluation)" % (F.shape[0] * 72 // 2 ** 20),
                            "wall_s": wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
-        # roofline of the dominant kernel (clip_cut_kernel), SURVEY.md §8(d). Durations are CUDA events recorded by the
+        # roofline of the dominant kernel (clip_win_kernel), SURVEY.md §8(d). Durations are CUDA events recorded by the
         # library on its stream around that kernel alone, accumulated over the timed region.
         try:
             fp32, fp64, copy = capi.measure_peaks(local_rank)
@@ -339,12 +339,12 @@ def main():
             clip_ms = cum["clip_kernel"] / n_launch
             traffic = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clip_cut_kernel")
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clip_win_kernel")
             except Exception:
                 pass
             ach = bytes_unit * own / (clip_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                                "kernel": "clip_cut_kernel", "peak_source": peak_src, "kernel_ms_per_launch": clip_ms,
+                                "kernel": "clip_win_kernel", "peak_source": peak_src, "kernel_ms_per_launch": clip_ms,
                                 "algorithmic_bytes_per_seed_iteration": bytes_unit, "units_per_launch": own,
                                 "share_of_step": cum["clip_kernel"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"]),
                                 "note": "FP64 geometry: the kernel is bound by FP64/issue rate, not HBM; see roofline_flops"}
@@ -358,7 +358,7 @@ def main():
             flops_step = own * (LLOYD_ITERS * f_lloyd + n_newton * f_newton)
             tf = flops_step / (cum["clip_kernel"] * 1e-3 / args.steps) / 1e12
             tf_phase = flops_step / (cum["clip"] * 1e-3 / args.steps) / 1e12
-            line["roofline_flops"] = {"kernel": "clip_cut_kernel", "achieved": tf, "unit": "TFLOP/s", "fp32_peak": fp32, "fp64_peak": fp64,
+            line["roofline_flops"] = {"kernel": "clip_win_kernel", "achieved": tf, "unit": "TFLOP/s", "fp32_peak": fp32, "fp64_peak": fp64,
                                       "frac_fp32": tf / fp32, "frac_fp64": tf / fp64, "achieved_whole_clip_phase": tf_phase,
                                       "peak_source": "FMA microbenchmark on this GPU (b200cvt_measure_peaks), non-tensor",
                                       "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton}}

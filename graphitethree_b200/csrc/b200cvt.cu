@@ -277,6 +277,7 @@ struct b200cvt_ctx {
     // L-BFGS
     DevBuf<double> lb_g, lb_q, lb_px, lb_pg, lb_wa, lb_s, lb_y, lb_part;
     DevBuf<LbfgsScalars> lb_sc;
+    u32 lb_dir_blocks = 0;            // grid of the cooperative direction kernel (all blocks resident)
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};   // around the clip kernel alone (roofline of the dominant kernel)
@@ -333,6 +334,9 @@ static void sync_stream(b200cvt_ctx* h) {
 // ---------------------------------------------------------------------------------------
 // grid construction
 // ---------------------------------------------------------------------------------------
+#ifndef GRID_CELL_SURF
+#define GRID_CELL_SURF 3.0
+#endif
 static void choose_grid(b200cvt_ctx* h, const double lo[3], const double hi[3]) {
     GridParams& g = h->g;
     double ext[3], maxext = 0.0;
@@ -342,7 +346,7 @@ static void choose_grid(b200cvt_ctx* h, const double lo[3], const double hi[3]) 
     double cell;
     if (h->has_mesh && h->mesh_measure > 0.0) {
         if (h->volumetric) cell = 2.0 * cbrt(h->mesh_measure / S);   // ~8 seeds per cell
-        else cell = 3.0 * sqrt(h->mesh_measure / S);                 // ~9 seeds per occupied cell, 21-NN radius ~2.6 spacings
+        else cell = GRID_CELL_SURF * sqrt(h->mesh_measure / S);                 // ~9 seeds per occupied cell, 21-NN radius ~2.6 spacings
     } else {
         double vol = 1.0;
         for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], maxext * 1e-3);

@@ -6,14 +6,21 @@
 // More-Thuente MCSRCH/MCSTEP line search (LineSearch.cpp:10-465, SAFE_SEARCH variant).
 // All vectors (x, g, q, s/y history, line-search base point) and all scalars (f, step,
 // rho/alpha, the line-search state) live in device memory; the scalar state machine runs
-// in a single-thread kernel; the host only reads back the 4-byte status that drives control
-// flow and the (f, |g|) pair reported to the iteration callback.
+// inside the two kernels below; the host reads back one small record per function evaluation (the
+// line-search status that drives control flow and the (f, |g|) pair reported to the iteration callback).
+//
+//   lbfgs_direction_kernel : ONE cooperative launch per iteration = history update (s, y, rho), two-loop
+//                            recursion, Hessian scaling, saves of x and g, g.d, the start of MCSRCH and the
+//                            first trial point x = wa + stp d. Every level of the recursion is one fused
+//                            pass (axpy of the previous level + dot product of the next) ended by a grid
+//                            barrier: 2 bound + 4 barriers instead of ~45 launches.
+//   lbfgs_post_eval_kernel : after each function evaluation: f = sum of the per-seed energies, g.d, |g|, |x|,
+//                            then the MCSRCH decision (last block).
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 #define LBFGS_MAXM 32
-#define LBFGS_RED_BLOCKS 1024
-#define LBFGS_RED_THREADS 256
 
 struct McsState {
     double dg, dgm, dginit, dgtest, dgx, dgxm, dgy, dgym, finit, fm, ftest1, fx, fxm, fy, fym;
@@ -22,20 +29,16 @@ struct McsState {
 };
 
 struct LbfgsScalars {
-    double f;              // current function value (written by the evaluation)
-    double dot;            // last reduction result
+    // first 48 bytes = the record the host reads back after every evaluation
+    double f;              // current function value
+    double dot;            // g.d (dginit at the start of a line search, dg afterwards)
     double stp;
     double gnorm, xnorm;
-    double coef;           // coefficient for the next axpy / scale
+    int info, nfev;        // MCSRCH status (-1: evaluate x = wa + stp d and come back), evaluations of this search
     double rho[LBFGS_MAXM];
-    double alpha[LBFGS_MAXM];
     McsState L;
-    int info, nfev;
     unsigned int red_counter;
 };
-
-// epilogues executed by the last block of a reduction
-enum { RED_STORE = 0, RED_RHO, RED_ALPHA, RED_BETA, RED_YS, RED_FACTOR, RED_GNORM, RED_XNORM, RED_F, RED_STP0 };
 
 __device__ __forceinline__ double block_sum(double v, double* sm) {
     v = warp_sum(v);
@@ -50,66 +53,6 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
     return r;
 }
 
-// sum_i a[i]*b[i] (b == NULL: sum a[i]); deterministic: fixed partition, partials summed in order.
-__global__ void __launch_bounds__(LBFGS_RED_THREADS)
-reduce_kernel(u32 n, const double* a, const double* b, double* partials, LbfgsScalars* sc, int op, int i0, int i1) {
-    __shared__ double sm[32];
-    __shared__ bool last;
-    double v = 0.0;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        v += b ? a[i] * b[i] : a[i];
-    double r = block_sum(v, sm);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = r;
-        __threadfence();
-        unsigned int t = atomicAdd(&sc->red_counter, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last) {
-        __threadfence();
-        double p = 0.0;
-        for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x) p += partials[i];
-        __syncthreads();
-        double tot = block_sum(p, sm);
-        if (threadIdx.x == 0) {
-            sc->red_counter = 0;
-            sc->dot = tot;
-            switch (op) {
-            case RED_RHO:    sc->rho[i0] = 1.0 / tot; break;                       // HLBFGS.cpp:380
-            case RED_ALPHA:  sc->alpha[i0] = sc->rho[i1] * tot; sc->coef = -sc->alpha[i0]; break;   // :171-173
-            case RED_BETA:   sc->coef = sc->alpha[i0] - sc->rho[i1] * tot; break;   // :192
-            case RED_YS:     sc->coef = tot; break;                                // ys, :103
-            case RED_FACTOR: sc->coef = sc->coef / tot; break;                     // ys/yy, :108
-            case RED_GNORM:  sc->gnorm = sqrt(tot); break;
-            case RED_XNORM:  sc->xnorm = sqrt(tot); break;
-            case RED_F:      sc->f = tot; break;
-            case RED_STP0:   sc->gnorm = sqrt(tot); sc->stp = 1.0 / sc->gnorm; break; // :520-523
-            default: break;
-            }
-        }
-    }
-}
-
-// y += coef * x with coef read from the device scalars (HLBFGS_DAXPY, HLBFGS_BLAS.cpp:42-52)
-__global__ void axpy_dev_kernel(u32 n, const LbfgsScalars* sc, const double* x, double* y) {
-    const double c = sc->coef;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += c * x[i];
-}
-__global__ void scale_dev_kernel(u32 n, const LbfgsScalars* sc, double* x) {
-    const double c = sc->coef;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] *= c;
-}
-__global__ void neg_kernel(u32 n, const double* g, double* q) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) q[i] = -g[i];
-}
-// s = x - prev_x ; y = g - prev_g  (HLBFGS.cpp:375-379)
-__global__ void diff_kernel(u32 n, const double* x, const double* px, const double* g, const double* pg, double* s, double* y) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        s[i] = x[i] - px[i];
-        y[i] = g[i] - pg[i];
-    }
-}
 // x = wa + stp * s  (LineSearch.cpp:107-108)
 __global__ void step_kernel(u32 n, const LbfgsScalars* sc, const double* wa, const double* s, double* x) {
     const double stp = sc->stp;
@@ -216,7 +159,7 @@ __device__ inline void mcstep_dev(double* stx, double* fx, double* dx, double* s
 // sc->info: in -1 = resume after an evaluation, else start. Out: -1 asks for x = wa + stp*s and an
 // evaluation; any other value ends the line search. The vector parts (wa = x at start; x = wa + stp*s)
 // are separate launches.
-__global__ void mcsrch_kernel(LbfgsScalars* sc, u32 n) {
+__device__ inline void mcsrch_dev(LbfgsScalars* sc, u32 n) {
     const double ftol = 1.0e-4, xtol = 1.0e-16, gtol = 0.9, stpmin = 1.0e-20, stpmax = 1.0e+20;
     const int maxfev = 20;
     McsState* L = &sc->L;
@@ -279,7 +222,235 @@ __global__ void mcsrch_kernel(LbfgsScalars* sc, u32 n) {
     sc->info = -1;
 }
 
-__global__ void set_info_kernel(LbfgsScalars* sc, int info, double stp, int set_stp) {
-    sc->info = info;
-    if (set_stp) sc->stp = stp;
+// ---------------------------------------------------------------------------------------
+// fused direction kernel
+// ---------------------------------------------------------------------------------------
+#define LBFGS_DIR_THREADS 512
+
+struct LbfgsDirArgs {
+    u32 N;
+    int first;               // 1: first iteration (no history pair to add, step 1/|g|)
+    int M;                   // history size (0: steepest descent)
+    int cur_pos;             // slot that receives the new (s, y) pair
+    int bound;               // levels of the recursion - 1 (-1: none)
+    int st1[LBFGS_MAXM];     // history slot of level i in the first loop (i = bound .. 0)
+    int st2[LBFGS_MAXM];     // history slot of level i in the second loop (i = 0 .. bound)
+    double* x; double* g; double* q; double* px; double* pg; double* wa;
+    double* s; double* y;    // [M][N]
+    LbfgsScalars* sc;
+    double* partials;        // [2][3 * gridDim.x]
+};
+
+// Sum over the grid of up to three per-thread values: fixed partition (grid-stride), block tree, then every block
+// adds the per-block partials in the same order, so all blocks hold bit-identical totals. One grid barrier.
+// `slot` alternates between consecutive calls (a block may enter the next reduction while others still read this one).
+template <int K>
+__device__ __forceinline__ void grid_sums(cooperative_groups::grid_group& grid, double* v, double* partials, int slot,
+                                          double* sm, double* out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* mine = partials + (size_t)slot * 3 * gridDim.x;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double r = block_sum(v[j], sm);
+        if (threadIdx.x == 0) mine[(size_t)j * gridDim.x + blockIdx.x] = r;
+        __syncthreads();
+    }
+    __threadfence();
+    grid.sync();
+    if (w == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            double p = 0.0;
+            for (u32 b = lane; b < gridDim.x; b += 32) p += __ldcg(mine + (size_t)j * gridDim.x + b);
+            p = warp_sum(p);
+            if (lane == 0) sm[32 + j] = p;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) out[j] = sm[32 + j];
+    __syncthreads();
+}
+
+// HLBFGS.cpp:356-533 between two line searches, on the device (see the header of this file)
+__global__ void __launch_bounds__(LBFGS_DIR_THREADS)
+lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[40];
+    const u32 N = a.N;
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    LbfgsScalars* sc = a.sc;
+    int slot = 0;
+    double v[3], tot[3];
+    const bool hist = !a.first && a.M > 0;
+    if (!hist) {
+        // q = -g; |g|^2 (first step 1/|g|, HLBFGS.cpp:520-523) and g.q
+        v[0] = 0.0; v[1] = 0.0;
+        for (u32 i = tid; i < N; i += nth) {
+            const double gi = a.g[i], qi = -gi;
+            a.q[i] = qi; a.px[i] = a.x[i]; a.pg[i] = gi; a.wa[i] = a.x[i];
+            v[0] += gi * gi; v[1] += gi * qi;
+        }
+        grid_sums<2>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+        if (tid == 0) {
+            if (a.first) { sc->gnorm = sqrt(tot[0]); sc->stp = 1.0 / sc->gnorm; } else sc->stp = 1.0;
+            sc->dot = tot[1];
+        }
+    } else {
+        double* s_cur = a.s + (size_t)a.cur_pos * N;
+        double* y_cur = a.y + (size_t)a.cur_pos * N;
+        const int bound = a.bound;
+        // new pair s = x - prev_x, y = g - prev_g (HLBFGS.cpp:375-379); y.s (rho, :380; Hessian scaling ys, :103),
+        // y.y (:108); q = -g and the first dot product of the first loop, s_st.q with st = st1[bound]
+        {
+            const double* s0 = a.s + (size_t)a.st1[bound] * N;     // == s_cur: the newest pair comes first
+            v[0] = 0.0; v[1] = 0.0; v[2] = 0.0;
+            for (u32 i = tid; i < N; i += nth) {
+                const double gi = a.g[i];
+                const double si = a.x[i] - a.px[i], yi = gi - a.pg[i];
+                s_cur[i] = si; y_cur[i] = yi;
+                const double qi = -gi;
+                a.q[i] = qi;
+                v[0] += yi * si; v[1] += yi * yi;
+                v[2] += qi * ((s0 == s_cur) ? si : s0[i]);
+            }
+            grid_sums<3>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+        }
+        const double ys = tot[0], yy = tot[1];
+        const double rho_cur = 1.0 / ys;
+        if (tid == 0) sc->rho[a.cur_pos] = rho_cur;
+        // first loop (HLBFGS_UPDATE_First_Step, :160-176): alpha_i = rho_st (s_st.q); q -= alpha_i y_st
+        double alpha[LBFGS_MAXM];
+        double dotv = tot[2];
+        for (int i = bound; i >= 0; --i) {
+            const int st = a.st1[i];
+            const double rho = (st == a.cur_pos) ? rho_cur : sc->rho[st];
+            alpha[i] = rho * dotv;
+            const double c = -alpha[i];
+            const double* yv = a.y + (size_t)st * N;
+            v[0] = 0.0;
+            if (i > 0) {
+                const double* sn = a.s + (size_t)a.st1[i - 1] * N;
+                for (u32 k = tid; k < N; k += nth) {
+                    double qk = a.q[k];
+                    qk += c * yv[k];
+                    a.q[k] = qk;
+                    v[0] += qk * sn[k];
+                }
+            } else {
+                // last level, then the Hessian scaling q *= ys/yy (HLBFGS_UPDATE_Hessian, :90-110) and the first dot
+                // product of the second loop, y_st.q
+                const double factor = ys / yy;
+                const double* yn = a.y + (size_t)a.st2[0] * N;
+                for (u32 k = tid; k < N; k += nth) {
+                    double qk = a.q[k];
+                    qk += c * yv[k];
+                    qk *= factor;
+                    a.q[k] = qk;
+                    v[0] += yn[k] * qk;
+                }
+            }
+            grid_sums<1>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+            dotv = tot[0];
+        }
+        // second loop (HLBFGS_UPDATE_Second_Step, :178-196): q += (alpha_i - rho_st (y_st.q)) s_st
+        for (int i = 0; i <= bound; ++i) {
+            const int st = a.st2[i];
+            const double rho = (st == a.cur_pos) ? rho_cur : sc->rho[st];
+            const double c = alpha[i] - rho * dotv;
+            const double* sv = a.s + (size_t)st * N;
+            v[0] = 0.0;
+            if (i < bound) {
+                const double* yn = a.y + (size_t)a.st2[i + 1] * N;
+                for (u32 k = tid; k < N; k += nth) {
+                    double qk = a.q[k];
+                    qk += c * sv[k];
+                    a.q[k] = qk;
+                    v[0] += yn[k] * qk;
+                }
+            } else {
+                // direction complete: save x and g (:502-503), wa = x (LineSearch.cpp:84), g.q
+                for (u32 k = tid; k < N; k += nth) {
+                    double qk = a.q[k];
+                    qk += c * sv[k];
+                    a.q[k] = qk;
+                    const double gk = a.g[k], xk = a.x[k];
+                    a.px[k] = xk; a.pg[k] = gk; a.wa[k] = xk;
+                    v[0] += gk * qk;
+                }
+            }
+            grid_sums<1>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+            dotv = tot[0];
+        }
+        if (tid == 0) { sc->stp = 1.0; sc->dot = dotv; }
+    }
+    // start of MCSRCH (LineSearch.cpp:60-100): info becomes -1 when a trial point is wanted
+    if (tid == 0) {
+        sc->info = 0;
+        mcsrch_dev(sc, N);
+        __threadfence();
+    }
+    grid.sync();
+    const int info = *((volatile int*)&sc->info);
+    if (info != -1) return;
+    const double stp = *((volatile double*)&sc->stp);
+    for (u32 i = tid; i < N; i += nth) {
+        double t = a.wa[i];
+        t += stp * a.q[i];
+        a.x[i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// after a function evaluation
+// ---------------------------------------------------------------------------------------
+#define LBFGS_POST_BLOCKS 592
+#define LBFGS_POST_THREADS 256
+
+// f = sum_i fs[i] (per-seed energies, ns entries); g.q, g.g, x.x over n entries; then (resume = 1) the MCSRCH decision.
+// Deterministic: fixed partition, per-block partials added in order by the last block.
+__global__ void __launch_bounds__(LBFGS_POST_THREADS)
+lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const double* q, const double* x,
+                       double* partials, LbfgsScalars* sc, int resume) {
+    __shared__ double sm[32];
+    __shared__ bool last;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) v[0] += fs[i];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double gi = g[i], xi = x[i];
+        v[1] += gi * q[i]; v[2] += gi * gi; v[3] += xi * xi;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double r = block_sum(v[j], sm);
+        if (threadIdx.x == 0) partials[(size_t)j * gridDim.x + blockIdx.x] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&sc->red_counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double tot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double p = 0.0;
+        for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x) p += __ldcg(partials + (size_t)j * gridDim.x + i);
+        __syncthreads();
+        tot[j] = block_sum(p, sm);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sc->red_counter = 0;
+        sc->f = tot[0];
+        sc->dot = tot[1];
+        sc->gnorm = sqrt(tot[2]);
+        sc->xnorm = sqrt(tot[3]);
+        // a line search that could not start (info != -1 after the direction kernel) stays as it is
+        if (resume && sc->info == -1) mcsrch_dev(sc, n);
+    }
 }

@@ -3,13 +3,10 @@
 // funcgrad = set_vertices + compute_CVT_func_grad(check_SR=true) + constrain_points.
 // Included at the end of b200cvt.cu.
 
-static void lb_reduce(b200cvt_ctx* h, u32 n, const double* a, const double* b, int op, int i0, int i1) {
-    u32 blocks = std::min<u32>(div_up(n, LBFGS_RED_THREADS), LBFGS_RED_BLOCKS);
-    LAUNCH(h, reduce_kernel, blocks, LBFGS_RED_THREADS, 0, n, a, b, h->lb_part.p, h->lb_sc.p, op, i0, i1);
-}
 static u32 lb_blocks(u32 n) { return std::min<u32>(div_up(n, 256), 148u * 8u); }
 
-// funcgrad (CVT.cpp:323-338) on the device: seeds = h->x, result f -> scalars.f, g -> h->lb_g.
+// funcgrad (CVT.cpp:323-338) on the device: seeds = h->x, result g -> h->lb_g, per-seed energies -> newton_fs(h)
+// (summed by lbfgs_post_eval_kernel).
 // With partitioned seeds every rank evaluates its Morton slice, the (g, f_seed) slices are
 // all-gathered, and every rank then holds the full gradient and the same energy.
 template <int D>
@@ -20,7 +17,6 @@ static void newton_eval_t(b200cvt_ctx* h) {
     if (h->nranks == 1) {
         LAUNCH(h, scatter_results_kernel<D>, div_up(S, 256), 256, 0, (const SeedRec<D>*)h->xs.p, 0u, S, h->out_s.p, h->out_v.p,
                h->flags.p, h->pair_cnt.p, h->locked.p, 1, (double*)nullptr, h->lb_g.p, h->flags_orig.p, h->cnt_orig.p);
-        lb_reduce(h, S, h->out_s.p, nullptr, RED_F, 0, 0);
     } else {
         if (!h->x_slice) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
         pack_slice<D>(h, h->out_s.p, h->out_v.p);
@@ -28,12 +24,13 @@ static void newton_eval_t(b200cvt_ctx* h) {
         h->s_orig.ensure(S);
         LAUNCH(h, unpack_all_kernel<D>, div_up(S, 256), 256, 0, (const SeedRec<D>*)h->xs.p, h->x_all, S, h->slice_len(),
                h->locked.p, 1, h->lb_g.p, h->s_orig.p);
-        lb_reduce(h, S, h->s_orig.p, nullptr, RED_F, 0, 0);
     }
 }
 static void newton_eval(b200cvt_ctx* h) {
     if (h->dim == 3) newton_eval_t<3>(h); else newton_eval_t<6>(h);
 }
+
+static const double* newton_fs(b200cvt_ctx* h) { return h->nranks == 1 ? h->out_s.p : h->s_orig.p; }
 
 // HLBFGS main loop (HLBFGS.cpp:356-586) on the device-resident seeds h->x
 static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb cb, void* user, uint32_t* info_out) {
@@ -46,73 +43,68 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     h->flags_orig.ensure(S); h->cnt_orig.ensure(S);
     h->lb_g.ensure(N); h->lb_q.ensure(N); h->lb_px.ensure(N); h->lb_pg.ensure(N); h->lb_wa.ensure(N);
     h->lb_s.ensure((size_t)std::max(M, 1) * N); h->lb_y.ensure((size_t)std::max(M, 1) * N);
-    h->lb_part.ensure(LBFGS_RED_BLOCKS); h->lb_sc.ensure(1);
+    // the direction kernel needs all its blocks resident (grid barriers): one cooperative launch
+    if (h->lb_dir_blocks == 0) {
+        int per_sm = 0, coop = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+        if (!coop) throw std::runtime_error("device does not support cooperative launches");
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_direction_kernel, LBFGS_DIR_THREADS, 0));
+        if (per_sm < 1) throw std::runtime_error("lbfgs_direction_kernel does not fit on an SM");
+        h->lb_dir_blocks = (u32)h->num_sms * (u32)std::min(per_sm, 2);
+    }
+    h->lb_part.ensure(std::max<size_t>(6 * (size_t)h->lb_dir_blocks, 4 * (size_t)LBFGS_POST_BLOCKS)); h->lb_sc.ensure(1);
     CUDA_CHECK(cudaMemsetAsync(h->lb_sc.p, 0, sizeof(LbfgsScalars), h->stream));
     double* x = h->x.p; double* g = h->lb_g.p; double* q = h->lb_q.p;
-    double* px = h->lb_px.p; double* pg = h->lb_pg.p; double* wa = h->lb_wa.p;
     LbfgsScalars* sc = h->lb_sc.p;
     const u32 nb = lb_blocks(N);
     const double stpmin = 1.0e-20, stpmax = 1.0e+20;
 
     u32 iter = 0, nfev_total = 0;
-    int cur_pos = 0, bound = 0, ls_info = 0;
+    int cur_pos = 0, ls_info = 0;
     bool canceled = false;
-    struct { double f, dot, stp, gnorm, xnorm; } hs;
+    struct { double f, dot, stp, gnorm, xnorm; int info, nfev; } hs;
+    auto post_eval = [&](int resume) {
+        LAUNCH(h, lbfgs_post_eval_kernel, LBFGS_POST_BLOCKS, LBFGS_POST_THREADS, 0, S, newton_fs(h), N, g, q, x, h->lb_part.p, sc, resume);
+    };
+    newton_eval(h); nfev_total++;
+    post_eval(0);
     for (;;) {
-        if (iter == 0) { newton_eval(h); nfev_total++; }
+        LbfgsDirArgs da;
+        memset(&da, 0, sizeof(da));
+        da.N = N; da.first = (iter == 0) ? 1 : 0; da.M = M; da.cur_pos = cur_pos; da.bound = -1;
         if (iter > 0 && M > 0) {
-            double* s_cur = h->lb_s.p + (size_t)cur_pos * N;
-            double* y_cur = h->lb_y.p + (size_t)cur_pos * N;
-            LAUNCH(h, diff_kernel, nb, 256, 0, N, x, px, g, pg, s_cur, y_cur);
-            lb_reduce(h, N, y_cur, s_cur, RED_RHO, cur_pos, 0);
-        }
-        LAUNCH(h, neg_kernel, nb, 256, 0, N, g, q);
-        if (iter > 0 && M > 0) {
-            bound = (int)iter > M ? M - 1 : (int)iter - 1;
-            for (int i = bound; i >= 0; --i) {       // HLBFGS_UPDATE_First_Step
-                int st = (int)iter <= M ? cur_pos - bound + i : (cur_pos - (bound - i) + M) % M;
-                lb_reduce(h, N, q, h->lb_s.p + (size_t)st * N, RED_ALPHA, i, st);
-                LAUNCH(h, axpy_dev_kernel, nb, 256, 0, N, sc, h->lb_y.p + (size_t)st * N, q);
+            const int bound = (int)iter > M ? M - 1 : (int)iter - 1;
+            da.bound = bound;
+            for (int i = 0; i <= bound; ++i) {
+                da.st1[i] = (int)iter <= M ? cur_pos - bound + i : (cur_pos - (bound - i) + M) % M;   // HLBFGS.cpp:160-176
+                da.st2[i] = (int)iter <= M ? i : (cur_pos + 1 + i) % M;                              // :178-196
             }
-            {                                         // HLBFGS_UPDATE_Hessian: q *= ys/yy
-                double* s_cur = h->lb_s.p + (size_t)cur_pos * N;
-                double* y_cur = h->lb_y.p + (size_t)cur_pos * N;
-                lb_reduce(h, N, y_cur, s_cur, RED_YS, 0, 0);
-                lb_reduce(h, N, y_cur, y_cur, RED_FACTOR, 0, 0);
-                LAUNCH(h, scale_dev_kernel, nb, 256, 0, N, sc, q);
-            }
-            for (int i = 0; i <= bound; ++i) {        // HLBFGS_UPDATE_Second_Step
-                int st = (int)iter <= M ? i : (cur_pos + 1 + i) % M;
-                lb_reduce(h, N, h->lb_y.p + (size_t)st * N, q, RED_BETA, i, st);
-                LAUNCH(h, axpy_dev_kernel, nb, 256, 0, N, sc, h->lb_s.p + (size_t)st * N, q);
-            }
-            cur_pos = (cur_pos + 1) % M;
         }
-        CUDA_CHECK(cudaMemcpyAsync(px, x, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
-        CUDA_CHECK(cudaMemcpyAsync(pg, g, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
-        if (iter == 0) {
-            lb_reduce(h, N, g, g, RED_STP0, 0, 0);
-            LAUNCH(h, set_info_kernel, 1, 1, 0, sc, 0, 0.0, 0);
-        } else {
-            LAUNCH(h, set_info_kernel, 1, 1, 0, sc, 0, 1.0, 1);
+        da.x = x; da.g = g; da.q = q; da.px = h->lb_px.p; da.pg = h->lb_pg.p; da.wa = h->lb_wa.p;
+        da.s = h->lb_s.p; da.y = h->lb_y.p; da.sc = sc; da.partials = h->lb_part.p;
+        {
+            void* kargs[] = {(void*)&da};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lbfgs_direction_kernel, dim3(h->lb_dir_blocks), dim3(LBFGS_DIR_THREADS),
+                                                   kargs, 0, h->stream));
+            h->launches++;
         }
-        // MCSRCH: wa = x at the start of the line search (LineSearch.cpp:84)
-        CUDA_CHECK(cudaMemcpyAsync(wa, x, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
+        if (iter > 0 && M > 0) cur_pos = (cur_pos + 1) % M;
+        // MCSRCH (LineSearch.cpp:100-230): the direction kernel has moved x to the first trial point, unless the search
+        // could not start (info != -1; rare: the evaluation below is then wasted and not counted)
+        u32 nfev_ls = 0;
         for (;;) {
-            lb_reduce(h, N, g, q, RED_STORE, 0, 0);           // g.s: dginit / dg
-            LAUNCH(h, mcsrch_kernel, 1, 1, 0, sc, N);
-            CUDA_CHECK(cudaMemcpyAsync(&ls_info, &sc->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            sync_stream(h);
-            if (ls_info != -1) break;
-            LAUNCH(h, step_kernel, nb, 256, 0, N, sc, wa, q, x);
             newton_eval(h);
-            nfev_total++;
+            nfev_ls++;
+            post_eval(1);
+            CUDA_CHECK(cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+            sync_stream(h);
+            ls_info = hs.info;
+            if (ls_info != -1) break;
+            LAUNCH(h, step_kernel, nb, 256, 0, N, sc, h->lb_wa.p, q, x);
         }
-        lb_reduce(h, N, g, g, RED_GNORM, 0, 0);
-        lb_reduce(h, N, x, x, RED_XNORM, 0, 0);
+        if (ls_info == 0) nfev_ls = 0;                    // the search never started (a finished search reports 1..6)
+        nfev_total += nfev_ls;
         iter++;
-        CUDA_CHECK(cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
-        sync_stream(h);
         if (cb && cb(user, iter, hs.f, hs.gnorm)) { canceled = true; break; }
         double xnorm = hs.xnorm < 1.0 ? 1.0 : hs.xnorm;
         if (ls_info != 1) break;                          // "Linesearch has failed"
