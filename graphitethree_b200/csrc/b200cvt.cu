@@ -239,7 +239,7 @@ struct b200cvt_ctx {
     DevBuf<u32> mtab; int mtab_bits[3] = {-1, -1, -1};
     // kNN
     u32 k = 20, kstride = 20;
-    bool knn_valid = false;
+    bool knn_valid = false, planes_valid = false;   // planes_valid: the bisector table matches nbr (written by the kNN kernel)
     DevBuf<uint8_t> cellflag, has_planes;   // sharded runs only
     DevBuf<float4> facet_ball; DevBuf<u32> facet_cell, facet_list, facet_list_n;
     bool facet_cell_valid = false;
@@ -442,7 +442,7 @@ static void launch_knn(b200cvt_ctx* h, const KnnArgs& a, u32 nq) {
     else LAUNCH(h, (knn_kernel<D, 4>), blocks, KNN_WARPS * 32, 0, a);
 }
 
-static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds) {
+static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds, bool want_planes = false) {
     const u32 S = h->S;
     h->k = k; h->kstride = std::max<u32>(k, 1);
     h->nbr.ensure((size_t)S * h->kstride);
@@ -460,9 +460,14 @@ static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds) {
         h->nbr_prev.ensure((size_t)S * 20);
         a.prev_in = h->prev_valid ? h->nbr_prev.p : nullptr; a.prev_out = h->nbr_prev.p; a.prev_stride = 20;
     }
+    if (want_planes) {
+        h->planes.ensure((size_t)S * h->kstride * (h->dim == 3 ? 6 : h->dim + 2));
+        a.planes = h->planes.p;
+    }
     if (h->dim == 3) launch_knn<3>(h, a, a.qend - a.qbegin); else launch_knn<6>(h, a, a.qend - a.qbegin);
     if (k == 20 && all_seeds) h->prev_valid = true;
     h->knn_valid = true;
+    h->planes_valid = want_planes;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -639,9 +644,13 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     h->planes.ensure((size_t)S * h->kstride * PLANE_STRIDE(D));
     if (h->nranks == 1) {
         // neighbour lists + bisector tables of every seed (the facet walk may visit any seed)
-        if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true);
-        LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
-               h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, (const u32*)nullptr, h->planes.p);
+        // (the kNN kernel writes the bisector rows with the lists; lists left by b200cvt_knn get theirs from plane_table_kernel)
+        if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true, true);
+        if (!h->planes_valid) {
+            LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
+                   h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, (const u32*)nullptr, h->planes.p);
+            h->planes_valid = true;
+        }
     } else {
         // sharded: only the seeds within two grid cells of the owned Morton range get lists and bisector rows
         const u32 nown0 = h->qend() - h->qbegin();
@@ -671,10 +680,9 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         // still valid bounds (any 20 other seeds bound the 20th distance), so they stay usable once written
         if (!h->prev_valid) CUDA_CHECK(cudaMemsetAsync(h->nbr_prev.p, 0xff, sizeof(u32) * (size_t)S * 20, h->stream));
         a.prev_in = h->nbr_prev.p; a.prev_out = h->nbr_prev.p; a.prev_stride = 20;
+        a.planes = h->planes.p;
         launch_knn<D>(h, a, S);
-        h->prev_valid = true; h->knn_valid = true;
-        LAUNCH(h, plane_table_kernel<D>, (u32)h->num_sms * 16u, 256, 0,
-               h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, h->need_list.p, 0u, S, h->need_n.p, h->planes.p);
+        h->prev_valid = true; h->knn_valid = true; h->planes_valid = true;
     }
     CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
     h->stats.ensure(16);

@@ -104,6 +104,9 @@ struct KnnArgs {
     // ORIGINAL indices. The largest new distance to the old neighbours bounds the new k-th distance, so one
     // pass over the grid cells that meet that ball is enough. prev_in may be NULL; prev_out (optional) is written.
     const u32* prev_in; u32* prev_out; u32 prev_stride;
+    // optional: bisector table row of every stored neighbour, written with the list (clip_flat.cuh: PLANE_STRIDE,
+    // same values as plane_table_kernel): n = pq - pj, d = sum (pq + pj) n, |pq - pj|^2. Rows by sorted position.
+    double* planes;
     GridParams g;
 };
 
@@ -304,8 +307,30 @@ knn_kernel(KnnArgs a) {
                 u32 pos = nres + __popc(kmask & ((1u << lane) - 1u));
                 if (pos < kk) {
                     if (a.prev_out && pos < a.prev_stride) a.prev_out[(size_t)qorig * a.prev_stride + pos] = ii;
-                    a.nbr[orow * a.kstride + pos] = a.rank_of[ii];
+                    const u32 jpos = a.rank_of[ii];
+                    a.nbr[orow * a.kstride + pos] = jpos;
                     if (a.sqd) a.sqd[orow * a.kstride + pos] = __longlong_as_double((long long)dd);
+                    if (a.planes) {
+                        // generic_RVD_polygon.h:257-274; the squared distance is the list key itself
+                        constexpr int PS = (D == 3) ? 6 : D + 2;
+                        double row[PS];
+                        const SeedRec<D>* rj = xs + jpos;
+                        double d = 0.0;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            const double pj = rj->p[c];
+                            const double nc = pq[c] - pj;
+                            row[c] = nc;
+                            d += (pq[c] + pj) * nc;
+                        }
+                        row[D] = d;
+                        row[D + 1] = __longlong_as_double((long long)dd);
+#pragma unroll
+                        for (int c = D + 2; c < PS; ++c) row[c] = 0.0;
+                        double2* o = (double2*)(a.planes + (orow * a.kstride + pos) * PS);
+#pragma unroll
+                        for (int c = 0; c < PS / 2; ++c) o[c] = make_double2(row[2 * c], row[2 * c + 1]);
+                    }
                 }
             }
             nres += __popc(kmask);
