@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b200cvt_nearest": (C.c_int, [C.c_void_p, _dp, C.c_uint32, _up]),
     "b200cvt_centroids": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "b200cvt_funcgrad": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "b200cvt_rdt": (C.c_int, [C.c_void_p, _up, C.c_uint64, C.POINTER(C.c_uint64)]),
     "b200cvt_get_flags": (C.c_int, [C.c_void_p, _bp]),
     "b200cvt_get_seed_energy": (C.c_int, [C.c_void_p, _dp]),
     "b200cvt_get_stats": (C.c_int, [C.c_void_p, _qp]),
@@ -158,6 +159,15 @@ class Handle:
         f = C.c_double(f0)
         _check(lib().b200cvt_funcgrad(self._h, int(check_SR), C.byref(f), g.ctypes.data_as(_dp)))
         return f.value, g
+
+    def rdt(self):
+        """compute_RDT, simple mode (RVD.cpp:2353-2370): (n, 3) original seed indices, rows sorted."""
+        n = C.c_uint64(0)
+        _check(lib().b200cvt_rdt(self._h, None, 0, C.byref(n)))
+        tri = np.empty((int(n.value), 3), dtype=np.uint32)
+        if n.value:
+            _check(lib().b200cvt_rdt(self._h, tri.ctypes.data_as(_up), n.value, C.byref(n)))
+        return tri
 
     def flags(self):
         fl = np.empty(self.S, dtype=np.uint8)

@@ -15,6 +15,7 @@
 #include "facet_pairs.cuh"
 #include "clip_tet.cuh"
 #include "lbfgs.cuh"
+#include "rdt.cuh"
 #include "../../include/b200cvt.h"
 
 #include <cub/cub.cuh>
@@ -225,6 +226,12 @@ struct b200cvt_ctx {
     DevBuf<double> tri, triw;
     DevBuf<uint8_t> tet_inner;         // volumetric: bit lf = face opposite to corner lf is shared with another tet
     DevBuf<u32> facet_guess;
+    // surface meshes: host copies kept for the facet adjacency the RDT extraction needs (built on first use)
+    std::vector<u32> host_elems, host_perm;
+    std::vector<int32_t> host_adj;
+    DevBuf<int> facet_adj; bool facet_adj_valid = false;
+    DevBuf<u32> rdt_dev, rdt_n;
+    std::vector<u32> rdt_host; bool rdt_valid = false;
     double bb_lo[3], bb_hi[3], mesh_measure = 0.0;
     // seeds
     u32 S = 0;
@@ -693,6 +700,10 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     }
     run_pairs_t<D, 3>(h);
     CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+    if (mode == 2) {            // candidate rows only (RDT extraction)
+        CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
+        return;
+    }
 
     h->out_s.ensure(S); h->out_v.ensure((size_t)S * D);
     h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4);
@@ -834,6 +845,7 @@ static void upload_locked(b200cvt_ctx* h, const uint8_t* locked, u32 S) {
 }
 
 static void set_seeds_common(b200cvt_ctx* h, u32 S) {
+    h->rdt_valid = false;
     if (S != h->S) { h->pair_cap = 0; h->prev_valid = false; }
     h->S = S;
     h->has_seeds = true;
@@ -895,6 +907,145 @@ static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void
     }
     h->has_results = nb_iter > 0;
     h->has_energy = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// restricted Delaunay triangulation, simple mode (rdt.cuh)
+// ---------------------------------------------------------------------------------------
+// facet_corners.adjacent_facet of the device copy (sorted facet ids). Taken from the caller's adjacency when it was given
+// to b200cvt_set_mesh, else rebuilt as MeshFacets::connect() does for manifold edges: two facets that share an edge.
+static void ensure_facet_adj(b200cvt_ctx* h) {
+    if (h->facet_adj_valid) return;
+    const u32 T = h->T;
+    std::vector<int32_t> adj;
+    if (!h->host_adj.empty()) adj = h->host_adj;
+    else {
+        adj.assign((size_t)T * 3, -1);
+        struct Edge { u32 a, b, f, c; };
+        std::vector<Edge> E((size_t)T * 3);
+        for (u32 f = 0; f < T; ++f)
+            for (u32 c = 0; c < 3; ++c) {
+                u32 v0 = h->host_elems[(size_t)f * 3 + c], v1 = h->host_elems[(size_t)f * 3 + (c + 1) % 3];
+                E[(size_t)f * 3 + c] = Edge{std::min(v0, v1), std::max(v0, v1), f, c};
+            }
+        std::sort(E.begin(), E.end(), [](const Edge& x, const Edge& y) {
+            if (x.a != y.a) return x.a < y.a;
+            if (x.b != y.b) return x.b < y.b;
+            return x.f < y.f;
+        });
+        for (size_t i = 0; i < E.size();) {
+            size_t j = i + 1;
+            while (j < E.size() && E[j].a == E[i].a && E[j].b == E[i].b) ++j;
+            if (j - i == 2) {
+                adj[(size_t)E[i].f * 3 + E[i].c] = (int32_t)E[i + 1].f;
+                adj[(size_t)E[i + 1].f * 3 + E[i + 1].c] = (int32_t)E[i].f;
+            }
+            i = j;
+        }
+    }
+    std::vector<u32> inv(T);
+    for (u32 i = 0; i < T; ++i) inv[h->host_perm[i]] = i;
+    std::vector<int> sorted((size_t)T * 3);
+    for (u32 i = 0; i < T; ++i)
+        for (u32 c = 0; c < 3; ++c) {
+            const int32_t a = adj[(size_t)h->host_perm[i] * 3 + c];
+            sorted[(size_t)i * 3 + c] = (a >= 0 && (u32)a < T) ? (int)inv[(u32)a] : -1;
+        }
+    h->facet_adj.ensure(std::max<size_t>(sorted.size(), 1));
+    if (!sorted.empty())
+        CUDA_CHECK(cudaMemcpyAsync(h->facet_adj.p, sorted.data(), sizeof(int) * sorted.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->facet_adj_valid = true;
+}
+
+template <int D>
+static void launch_rdt(b200cvt_ctx* h, RdtArgs& a) {
+    if (a.nseeds == 0) return;
+    const size_t smem = (size_t)CLIP_WARPS * a.kstride * (D + 3) * sizeof(double);
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(rdt_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(h, rdt_kernel<D>, div_up(a.nseeds, CLIP_WARPS), CLIP_WARPS * 32, smem, a);
+}
+
+// RestrictedVoronoiDiagram::compute_RDT(simplices, embedding, RDTMode(0)) for the owned seeds (RVD.cpp:2353-2370):
+// check_SR = true as CentroidalVoronoiTesselation::compute_surface sets it (CVT.cpp:194). Result in h->rdt_host,
+// rows sorted lexicographically.
+template <int D>
+static void compute_rdt_t(b200cvt_ctx* h) {
+    if (h->volumetric) throw ArgError("compute_RDT of a volumetric diagram stays on the reference implementation");
+    if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
+    if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
+    ensure_facet_adj(h);
+    evaluate_t<D>(h, 2, 1);
+    const u32 S = h->S;
+    const u32 nown = h->qend() - h->qbegin();
+    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4); h->rdt_n.ensure(1);
+    size_t out_cap = std::max<size_t>(h->rdt_dev.cap / 3, (size_t)3 * nown + 1024);
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        h->rdt_dev.ensure(out_cap * 3);
+        out_cap = std::min<size_t>(h->rdt_dev.cap / 3, 0xffffffffu);
+        CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->rdt_n.p, 0, sizeof(u32), h->stream));
+        RdtArgs r;
+        memset(&r, 0, sizeof(r));
+        r.xs = h->xs.p; r.nbr = h->nbr.p; r.nbr_n = h->nbr_n.p; r.kstride = h->kstride; r.nbr_by_slot = 0;
+        r.tri = h->tri.p; r.facet_adj = h->facet_adj.p; r.T = h->T;
+        r.pair_cnt = h->pair_cnt.p; r.pair_facet = h->pair_facet.p; r.cap = h->pair_cap;
+        r.seed_list = nullptr; r.nseeds = nown; r.qbegin = h->qbegin(); r.S = S; r.flags = h->flags.p;
+        r.redo_list = h->redo_a.p; r.redo_n = h->redo_n.p;
+        r.out_tri = h->rdt_dev.p; r.out_cap = (u32)out_cap; r.out_n = h->rdt_n.p;
+        launch_rdt<D>(h, r);
+        // enlarge_neighborhood (generic_RVD.h:2183-2197), batched over the seeds that need it
+        u32 kbig = 40;
+        u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
+        int cur_slot = 0;
+        for (;;) {
+            u32 nredo = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            if (nredo == 0) break;
+            kbig = std::min<u32>(std::min<u32>(kbig, B200CVT_KMAX), S - 1);
+            h->nbr_big.ensure((size_t)nredo * kbig);
+            h->nbr_big_n.ensure(nredo);
+            KnnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
+            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
+            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+            launch_knn<D>(h, a, nredo);
+            const int nslot = cur_slot ^ 1;
+            CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
+            RdtArgs rr = r;
+            rr.nbr = h->nbr_big.p; rr.nbr_n = h->nbr_big_n.p; rr.kstride = kbig; rr.nbr_by_slot = 1;
+            rr.seed_list = cur_list; rr.nseeds = nredo;
+            rr.redo_list = nxt_list; rr.redo_n = h->redo_n.p + nslot;
+            launch_rdt<D>(h, rr);
+            std::swap(cur_list, nxt_list);
+            cur_slot = nslot;
+            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) break;
+            kbig *= 2;
+        }
+        u32 n = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&n, h->rdt_n.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (n > out_cap) { out_cap = (size_t)n + n / 8 + 1024; continue; }
+        h->rdt_host.resize((size_t)n * 3);
+        if (n > 0) CUDA_CHECK(cudaMemcpy(h->rdt_host.data(), h->rdt_dev.p, sizeof(u32) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+        struct T3 { u32 a, b, c; };
+        T3* t = reinterpret_cast<T3*>(h->rdt_host.data());
+        std::sort(t, t + n, [](const T3& x, const T3& y) {
+            if (x.a != y.a) return x.a < y.a;
+            if (x.b != y.b) return x.b < y.b;
+            return x.c < y.c;
+        });
+        h->rdt_valid = true;
+        // only the status flags (polygon overflow, neighbourhood cap) are results of this pass
+        scatter_results(h, false, false, false);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->has_results = true; h->has_energy = false;
+        return;
+    }
+    throw CapacityError("RDT triangle list keeps overflowing");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1100,6 +1251,13 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             }
             for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[order[i].second];
         }
+        h->host_elems.clear(); h->host_perm.clear(); h->host_adj.clear(); h->facet_adj_valid = false; h->rdt_valid = false;
+        if (!h->volumetric) {
+            h->host_elems.assign(elems, elems + (size_t)ne * 3);
+            h->host_perm.resize(ne);
+            for (u32 i = 0; i < ne; ++i) h->host_perm[i] = order[i].second;
+            if (adjacency) h->host_adj.assign(adjacency, adjacency + (size_t)ne * 3);
+        }
         h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = measure;
         for (int a = 0; a < 3; ++a) { h->bb_lo[a] = lo[a]; h->bb_hi[a] = hi[a]; }
         h->tri.ensure(soup.size());
@@ -1127,6 +1285,18 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         }
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         h->has_mesh = true; h->grid_valid = false; h->knn_valid = false; h->has_results = false; h->pair_cap = 0;
+    });
+}
+
+int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_out) {
+    return guarded([&] {
+        if (!h || !n_out) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (!h->rdt_valid) { if (h->dim == 3) compute_rdt_t<3>(h); else compute_rdt_t<6>(h); }
+        const uint64_t n = h->rdt_host.size() / 3;
+        *n_out = n;
+        if (tri_out && cap_triangles > 0)
+            memcpy(tri_out, h->rdt_host.data(), sizeof(u32) * 3 * (size_t)std::min<uint64_t>(n, cap_triangles));
     });
 }
 

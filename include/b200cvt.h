@@ -99,6 +99,17 @@ int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_
 
 /* Per-seed results of the last centroids/funcgrad call, original seed order:
  * flags (S), per-seed energy (S; funcgrad only), candidate (facet,seed) pair counts (S). */
+/* Replaces: RestrictedVoronoiDiagram::compute_RDT(simplices, embedding, RDTMode(0)) for surfaces
+ * (G/voronoi/RVD.cpp:2302-2372, simple mode: for_each_primal_triangle, G/voronoi/generic_RVD.h:575-619) with
+ * check_SR = true as CentroidalVoronoiTesselation::compute_surface sets it (G/voronoi/CVT.cpp:194): one triangle
+ * (s, b0, b1), s < b1 < b0 original seed indices (SymbolicVertex::bisector(0) is the larger one), per polygon vertex
+ * that lies on two bisectors. Rows sorted
+ * lexicographically (the reference's order is its traversal order); duplicates are kept as the reference keeps them.
+ * The embedding the reference returns with the triangles is the seed array itself. Call with tri_out = NULL to get the
+ * count, then with a buffer of cap_triangles rows. Partitioned handles return the triangles of their own seeds.
+ * Needs the facet adjacency: the one given to b200cvt_set_mesh, else it is rebuilt from shared edges. */
+int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_out);
+
 int b200cvt_get_flags(b200cvt_handle h, uint8_t* flags_out);
 int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out);
 int b200cvt_get_stats(b200cvt_handle h, uint64_t* stats_out /* 16 entries, see b200cvt.cu */);

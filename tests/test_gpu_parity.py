@@ -466,3 +466,53 @@ def test_volume_properties_large(built):
     f2, _ = h.funcgrad(True)
     assert f2 < f
     h.close()
+
+
+# ---------------------------------------------------------------------------------------
+# restricted Delaunay triangulation, simple mode: b200cvt_rdt
+# ---------------------------------------------------------------------------------------
+def rows(tri):
+    t = np.asarray(tri, dtype=np.int64).reshape(-1, 3)
+    return t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_rdt_against_reference_golden(built, path):
+    # the reference's compute_RDT(RDTMode(0)) at its own Lloyd result: identical triangle lists (duplicates included)
+    G = load(path)
+    h = handle_for(G["V"], G["F"], G.get("weights"))
+    h.set_seeds(G["x_lloyd"])
+    tri = h.rdt()
+    assert (h.flags() & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    ref = rows(G["rdt_tri"])
+    assert (ref[:, 0] < ref[:, 2]).all() and (ref[:, 2] < ref[:, 1]).all()     # (s, bisector(0), bisector(1)): s < b1 < b0
+    got = rows(tri)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    # the call is cached until the seeds change, and leaves the evaluation path usable
+    assert np.array_equal(h.rdt(), tri)
+    h.set_seeds(G["x_lloyd"])
+    mg, m = h.centroids(True)
+    assert abs(m.sum() - port.surface_eval(G["V"], G["F"], G["x_lloyd"], 0, True, weights=G.get("weights")).m.sum()) <= 1e-9 * m.sum()
+    h.close()
+
+
+def test_rdt_closed_surface_properties_c1(built):
+    # C1 size: after Lloyd the simple-mode RDT of a sphere is a closed genus-0 triangulation of the seeds
+    V, F = shapes.icosphere(45)
+    X = shapes.sample_surface(V, F, 10000, 1)
+    h = handle_for(V, F)
+    x = h.lloyd(X, 10)
+    h.set_seeds(x)
+    tri = np.unique(np.sort(rows(h.rdt()), axis=1), axis=0)
+    assert tri.shape[0] == 2 * 10000 - 4                                         # Euler characteristic 2
+    e = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [0, 2]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()                                                      # every edge shared by two triangles
+    assert np.unique(tri).size == 10000                                          # every seed is a vertex
+    # every RDT edge joins kNN neighbours (the Delaunay graph is a subgraph of the 20-NN graph after Lloyd)
+    h.set_seeds(x)
+    idx, cnt20, _, _ = h.knn(20)
+    nbr = [set(idx[i, :cnt20[i]].tolist()) for i in range(10000)]
+    ue = np.unique(e, axis=0)
+    assert all(int(b) in nbr[int(a)] for a, b in ue[:: max(1, ue.shape[0] // 2000)])
+    h.close()
