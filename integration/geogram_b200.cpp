@@ -162,9 +162,12 @@ namespace GEO {
     b200cvt_handle RestrictedVoronoiDiagramB200::handle() {
         const index_t nv = mesh_->vertices.nb(), nf = mesh_->facets.nb(), stride = mesh_->vertices.dimension();
         std::vector<uint32_t> tri(size_t(nf) * 3);
+        std::vector<int32_t> adj(size_t(nf) * 3);
         for(index_t f = 0; f < nf; ++f) {
             for(index_t lv = 0; lv < 3; ++lv) {
                 tri[size_t(f) * 3 + lv] = mesh_->facets.vertex(f, lv);
+                const index_t a = mesh_->facets.adjacent(f, lv);
+                adj[size_t(f) * 3 + lv] = (a == NO_INDEX) ? -1 : int32_t(a);
             }
         }
         std::vector<double> weights;
@@ -176,12 +179,13 @@ namespace GEO {
         }
         unsigned long long hsh = hash_bytes(0x243F6A8885A308D3ull + nv, mesh_->vertices.point_ptr(0), sizeof(double) * size_t(nv) * stride);
         hsh = hash_bytes(hsh, tri.data(), sizeof(uint32_t) * tri.size());
+        hsh = hash_bytes(hsh, adj.data(), sizeof(int32_t) * adj.size());
         if(has_weights_) {
             hsh = hash_bytes(hsh, weights.data(), sizeof(double) * weights.size());
         }
         if(!mesh_uploaded_ || hsh != mesh_hash_) {
             check(
-                b200cvt_set_mesh(h_, mesh_->vertices.point_ptr(0), nv, stride, tri.data(), nullptr, nf,
+                b200cvt_set_mesh(h_, mesh_->vertices.point_ptr(0), nv, stride, tri.data(), adj.data(), nf,
                                  has_weights_ ? weights.data() : nullptr),
                 "b200cvt_set_mesh"
             );
@@ -281,7 +285,21 @@ namespace GEO {
     void RestrictedVoronoiDiagramB200::compute_RDT(
         vector<index_t>& simplices, vector<double>& embedding, RDTMode mode, const vector<bool>& seed_is_locked, MeshFacetsAABB* AABB
     ) {
-        ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
+        /* simple mode (RVD.cpp:2353-2370) with check_SR = true, as compute_surface asks for it (CVT.cpp:194): on the device.
+         * Multinerve / RVC-centroid modes walk connected components of the cells on the host: reference implementation. */
+        if(!gpu_eligible() || mode != RDTMode(0) || !check_SR_) {
+            ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
+            return;
+        }
+        upload_seeds();
+        uint64_t n = 0;
+        check(b200cvt_rdt(h_, nullptr, 0, &n), "b200cvt_rdt");
+        std::vector<uint32_t> tri(size_t(n) * 3);
+        check(b200cvt_rdt(h_, tri.data(), n, &n), "b200cvt_rdt");
+        simplices.assign(tri.begin(), tri.end());
+        const index_t nb = delaunay_->nb_vertices();
+        embedding.assign(delaunay_->vertex_ptr(0), delaunay_->vertex_ptr(0) + size_t(nb) * dimension_);
+        ++nb_gpu_calls_;
     }
 
     void RestrictedVoronoiDiagramB200::compute_RVD(Mesh& M, coord_index_t dim, bool cell_borders_only, bool integration_simplices) {
