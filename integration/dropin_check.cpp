@@ -48,6 +48,8 @@ namespace {
         return ok;
     }
 
+    bool g_volumetric = false;   /* the element table holds tetrahedra; CVT in volumetric mode */
+
     void load_mesh(const std::vector<unsigned char>& buf, Mesh& M) {
         const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf.data());
         uint32_t nv = hdr[0], nf = hdr[1], dim = hdr[2];
@@ -60,6 +62,17 @@ namespace {
             for(uint32_t c = 0; c < dim; ++c) {
                 M.vertices.point_ptr(v)[c] = V[size_t(v) * dim + c];
             }
+        }
+        if(g_volumetric) {
+            M.cells.create_tets(nf);
+            for(uint32_t t = 0; t < nf; ++t) {
+                for(uint32_t lv = 0; lv < 4; ++lv) {
+                    M.cells.set_vertex(t, lv, T[size_t(t) * 4 + lv]);
+                }
+            }
+            M.cells.connect();
+            M.cells.compute_borders();
+            return;
         }
         M.facets.create_triangles(nf);
         for(uint32_t f = 0; f < nf; ++f) {
@@ -96,6 +109,7 @@ namespace {
     template <class CVT_T>
     void run(Mesh& M, index_t S, index_t dim, const double* seeds, index_t nl, index_t nn, index_t m, Run& out) {
         CVT_T cvt(&M, coord_index_t(dim), "NN");
+        cvt.set_volumetric(g_volumetric);
         cvt.set_points(S, seeds);
         double t0 = Stopwatch::now();
         cvt.Lloyd_iterations(nl);
@@ -107,6 +121,12 @@ namespace {
             out.t_newton = Stopwatch::now() - t0;
         }
         out.x_final.assign(cvt.embedding(0), cvt.embedding(0) + size_t(S) * dim);
+        if constexpr (std::is_same<CVT_T, CentroidalVoronoiTesselationB200>::value) {
+            out.on_gpu = cvt.last_call_on_gpu();
+        }
+        if(g_volumetric) {
+            return;        /* compute_volume / the tetrahedral RDT stay on the reference implementation */
+        }
         cvt.RVD()->delete_threads();
         cvt.set_use_RVC_centroids(false);   /* vertices of the remesh = the seeds, so that the triangle sets are comparable */
         cvt.compute_surface(&out.surface, false);
@@ -128,7 +148,7 @@ namespace {
 
 int main(int argc, char** argv) {
     if(argc < 6) {
-        fprintf(stderr, "usage: %s mesh.bin seeds.bin nb_Lloyd nb_Newton m [nb_pre_Lloyd]\n", argv[0]);
+        fprintf(stderr, "usage: %s mesh.bin seeds.bin nb_Lloyd nb_Newton m [nb_pre_Lloyd] [volumetric]\n", argv[0]);
         return 2;
     }
     GEO::initialize(GEO::GEOGRAM_INSTALL_NONE);
@@ -156,11 +176,13 @@ int main(int argc, char** argv) {
      * iteration of the C1-like case, 5e-15 from the second on). Those are the "flagged configurations" of the parity
      * statement; one stock iteration removes them. */
     const index_t npre = (argc > 6) ? index_t(atoi(argv[6])) : 0;
+    g_volumetric = (argc > 7) && atoi(argv[7]) != 0;
     std::vector<double> start(seeds, seeds + size_t(S) * dim);
     if(npre > 0) {
         Mesh M;
         load_mesh(mb, M);
         CentroidalVoronoiTesselation pre(&M, coord_index_t(dim), "NN");
+        pre.set_volumetric(g_volumetric);
         pre.set_points(S, seeds);
         pre.Lloyd_iterations(npre);
         start.assign(pre.embedding(0), pre.embedding(0) + size_t(S) * dim);
@@ -216,7 +238,7 @@ int main(int argc, char** argv) {
             ++only_b200;
         }
     }
-    double diag = bbox_diagonal(ref.surface);
+    double diag = (ref.surface.vertices.nb() > 0) ? bbox_diagonal(ref.surface) : 0.0;
     double h_ab = 0.0, h_ba = 0.0;
     if(ref.surface.facets.nb() > 0 && b200.surface.facets.nb() > 0) {
         double sampling = 0.01 * diag;
@@ -224,14 +246,14 @@ int main(int argc, char** argv) {
         h_ba = mesh_one_sided_Hausdorff_distance(b200.surface, ref.surface, sampling);
     }
     printf(
-        "{\"seeds\": %u, \"dim\": %u, \"pre_lloyd\": %u, \"lloyd\": %u, \"newton\": %u, \"on_gpu\": %s, "
+        "{\"volumetric\": %s, \"seeds\": %u, \"dim\": %u, \"pre_lloyd\": %u, \"lloyd\": %u, \"newton\": %u, \"on_gpu\": %s, "
         "\"max_abs_dx_lloyd\": %.3e, \"max_abs_dx_final\": %.3e, "
         "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
         "\"ref_vertices\": %u, \"b200_vertices\": %u, "
         "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"bbox_diagonal\": %.6e, "
         "\"nn_rows\": %u, \"nn_mismatch\": %u, "
         "\"t_ref_lloyd\": %.4f, \"t_ref_newton\": %.4f, \"t_b200_lloyd\": %.4f, \"t_b200_newton\": %.4f, \"ref_threads\": %u}\n",
-        S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
+        g_volumetric ? "true" : "false", S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
         max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
         ta.size(), tb.size(), only_ref, only_b200,
         ref.surface.vertices.nb(), b200.surface.vertices.nb(),

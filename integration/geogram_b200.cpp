@@ -133,7 +133,8 @@ namespace GEO {
         RestrictedVoronoiDiagram(
             delaunay, mesh, (mesh->vertices.nb() > 0) ? mesh->vertices.point_ptr(0) : nullptr, mesh->vertices.dimension()
         ),
-        h_(nullptr), check_SR_(false), mesh_hash_(0), mesh_uploaded_(false), nb_gpu_calls_(0) {
+        h_(nullptr), h_vol_(nullptr), check_SR_(false), mesh_hash_(0), vol_hash_(0), mesh_uploaded_(false), vol_uploaded_(false),
+        nb_gpu_calls_(0) {
         ref_ = RestrictedVoronoiDiagram::create(delaunay, mesh);   /* also forces set_stores_neighbors(true), RVD.cpp:2552 */
         has_weights_ = mesh->vertices.attributes().is_defined("weight");
         if(has_weights_) {
@@ -148,18 +149,56 @@ namespace GEO {
         if(h_ != nullptr) {
             b200cvt_destroy(h_);
         }
+        if(h_vol_ != nullptr) {
+            b200cvt_destroy(h_vol_);
+        }
     }
 
     bool RestrictedVoronoiDiagramB200::gpu_eligible() const {
         /* the range is NO_INDEX/NO_INDEX until set_facets_range is called (RVD.cpp:2623-2624) = the whole mesh */
         const bool whole_mesh = (facets_begin_ == NO_INDEX && facets_end_ == NO_INDEX) ||
             (facets_begin_ == 0 && facets_end_ == mesh_->facets.nb());
-        return h_ != nullptr && !volumetric_ && !ref_->exact_predicates() && mesh_->facets.nb() > 0 &&
-            mesh_->facets.are_simplices() && whole_mesh &&
-            delaunay_ != nullptr && delaunay_->nb_vertices() > 0;
+        if(h_ == nullptr || ref_->exact_predicates() || delaunay_ == nullptr || delaunay_->nb_vertices() == 0) {
+            return false;
+        }
+        if(volumetric_) {
+            /* tets only (the reference walks any cell type through its own tet decomposition), dimension 3 */
+            const bool whole_cells = (tets_begin_ == NO_INDEX && tets_end_ == NO_INDEX) ||
+                (tets_begin_ == 0 && tets_end_ == mesh_->cells.nb());
+            return dimension_ == 3 && mesh_->cells.nb() > 0 && mesh_->cells.are_simplices() && whole_cells;
+        }
+        return mesh_->facets.nb() > 0 && mesh_->facets.are_simplices() && whole_mesh;
     }
 
     b200cvt_handle RestrictedVoronoiDiagramB200::handle() {
+        if(volumetric_) {
+            const index_t nv = mesh_->vertices.nb(), nt = mesh_->cells.nb(), stride = mesh_->vertices.dimension();
+            if(h_vol_ == nullptr) {
+                check(b200cvt_create(-1, 3, 1, &h_vol_), "b200cvt_create");
+            }
+            std::vector<uint32_t> tet(size_t(nt) * 4);
+            std::vector<int32_t> adj(size_t(nt) * 4);
+            for(index_t t = 0; t < nt; ++t) {
+                for(index_t lv = 0; lv < 4; ++lv) {
+                    tet[size_t(t) * 4 + lv] = mesh_->cells.vertex(t, lv);
+                    const index_t a = mesh_->cells.adjacent(t, lv);
+                    adj[size_t(t) * 4 + lv] = (a == NO_INDEX) ? -1 : int32_t(a);
+                }
+            }
+            unsigned long long hsh = hash_bytes(0x13198A2E03707344ull + nv, mesh_->vertices.point_ptr(0), sizeof(double) * size_t(nv) * stride);
+            hsh = hash_bytes(hsh, tet.data(), sizeof(uint32_t) * tet.size());
+            hsh = hash_bytes(hsh, adj.data(), sizeof(int32_t) * adj.size());
+            if(!vol_uploaded_ || hsh != vol_hash_) {
+                /* the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783) */
+                check(
+                    b200cvt_set_mesh(h_vol_, mesh_->vertices.point_ptr(0), nv, stride, tet.data(), adj.data(), nt, nullptr),
+                    "b200cvt_set_mesh"
+                );
+                vol_hash_ = hsh;
+                vol_uploaded_ = true;
+            }
+            return h_vol_;
+        }
         const index_t nv = mesh_->vertices.nb(), nf = mesh_->facets.nb(), stride = mesh_->vertices.dimension();
         std::vector<uint32_t> tri(size_t(nf) * 3);
         std::vector<int32_t> adj(size_t(nf) * 3);
@@ -200,7 +239,7 @@ namespace GEO {
     }
 
     void RestrictedVoronoiDiagramB200::compute_centroids_on_surface(double* mg, double* m) {
-        if(!gpu_eligible()) {
+        if(volumetric_ || !gpu_eligible()) {
             ref_->compute_centroids_on_surface(mg, m);
             return;
         }
@@ -210,7 +249,7 @@ namespace GEO {
     }
 
     void RestrictedVoronoiDiagramB200::compute_CVT_func_grad_on_surface(double& f, double* g) {
-        if(!gpu_eligible()) {
+        if(volumetric_ || !gpu_eligible()) {
             ref_->compute_CVT_func_grad_on_surface(f, g);
             return;
         }
@@ -267,11 +306,23 @@ namespace GEO {
     }
 
     void RestrictedVoronoiDiagramB200::compute_centroids_in_volume(double* mg, double* m) {
-        ref_->compute_centroids_in_volume(mg, m);
+        if(!volumetric_ || !gpu_eligible()) {
+            ref_->compute_centroids_in_volume(mg, m);
+            return;
+        }
+        upload_seeds();
+        check(b200cvt_centroids(handle(), check_SR_ ? 1 : 0, mg, m), "b200cvt_centroids");
+        ++nb_gpu_calls_;
     }
 
     void RestrictedVoronoiDiagramB200::compute_CVT_func_grad_in_volume(double& f, double* g) {
-        ref_->compute_CVT_func_grad_in_volume(f, g);
+        if(!volumetric_ || !gpu_eligible()) {
+            ref_->compute_CVT_func_grad_in_volume(f, g);
+            return;
+        }
+        upload_seeds();
+        check(b200cvt_funcgrad(handle(), check_SR_ ? 1 : 0, &f, g), "b200cvt_funcgrad");
+        ++nb_gpu_calls_;
     }
 
     void RestrictedVoronoiDiagramB200::compute_integration_simplex_func_grad(double& f, double* g, IntegrationSimplex* F) {
@@ -287,7 +338,7 @@ namespace GEO {
     ) {
         /* simple mode (RVD.cpp:2353-2370) with check_SR = true, as compute_surface asks for it (CVT.cpp:194): on the device.
          * Multinerve / RVC-centroid modes walk connected components of the cells on the host: reference implementation. */
-        if(!gpu_eligible() || mode != RDTMode(0) || !check_SR_) {
+        if(volumetric_ || !gpu_eligible() || mode != RDTMode(0) || !check_SR_) {
             ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
             return;
         }

@@ -68,8 +68,9 @@ namespace GEO {
     public:
         RestrictedVoronoiDiagramB200(Delaunay* delaunay, Mesh* mesh);
 
-        /** true if the GPU path takes the next compute_* call (dimension 3 or 6, triangulated surface, whole facet
-         *  range, fast predicates, surfacic mode); otherwise the call is delegated to the reference. */
+        /** true if the GPU path takes the next compute_* call: fast predicates, and either surfacic mode (dimension 3 or 6,
+         *  triangulated surface, whole facet range) or volumetric mode (dimension 3, tetrahedral cells, whole tet range);
+         *  otherwise the call is delegated to the reference. */
         bool gpu_eligible() const;
         /** the C-ABI handle with the current mesh uploaded (re-uploaded when the mesh changed) */
         b200cvt_handle handle();
@@ -111,10 +112,11 @@ namespace GEO {
     private:
         void upload_seeds();
         RestrictedVoronoiDiagram_var ref_;   /* the unmodified reference implementation, for everything off the hot path */
-        b200cvt_handle h_;
+        b200cvt_handle h_;                   /* surfacic handle */
+        b200cvt_handle h_vol_;               /* volumetric handle (created on first use) */
         bool check_SR_;
-        unsigned long long mesh_hash_;
-        bool mesh_uploaded_;
+        unsigned long long mesh_hash_, vol_hash_;
+        bool mesh_uploaded_, vol_uploaded_;
         index_t nb_gpu_calls_;
     };
 

@@ -32,14 +32,15 @@ def write_inputs(tmp_path, V, F, X):
     return mp, sp
 
 
-def run_check(tmp_path, V, F, X, nl, nn, m=7, pre=1):
+def run_check(tmp_path, V, F, X, nl, nn, m=7, pre=1, volumetric=False):
     """pre = stock Lloyd iterations that make the common start: on a raw random sampling the reference's own first
     iteration depends on its thread count (cells that need more than 20 neighbours, check_SR = false; measured 7e-3
     between 1, 3 and 8 threads, 5e-15 afterwards) — the flagged configurations of the parity statement."""
     if not os.path.exists(EXE):
         pytest.fail("integration/_build/dropin_check is missing: run __graft_entry__.build() where /root/reference exists")
     mp, sp = write_inputs(tmp_path, V, F, X)
-    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m), str(pre)], capture_output=True, text=True, timeout=900)
+    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m), str(pre), "1" if volumetric else "0"],
+                         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
     print(r)
@@ -70,3 +71,14 @@ def test_dropin_lloyd_newton_trefoil(tmp_path):
     assert r["only_ref"] == 0 and r["only_b200"] == 0
     tol = 1e-6 * r["bbox_diagonal"]
     assert r["hausdorff_ref_to_b200"] <= tol and r["hausdorff_b200_to_ref"] <= tol
+
+
+def test_dropin_volumetric_lloyd_newton(tmp_path):
+    # CentroidalVoronoiTesselation::set_volumetric(true) on a tetrahedralised cube: the adapter's compute_centroids_in_volume /
+    # compute_CVT_func_grad_in_volume and the device-resident loops against the stock classes
+    V, T = shapes.kuhn_cube(10)                      # 6 000 tets
+    X = 0.02 + 0.96 * np.random.default_rng(4).random((600, 3))
+    r = run_check(tmp_path, V, T, X, 4, 5, pre=2, volumetric=True)
+    assert r["volumetric"] and r["on_gpu"]
+    assert r["max_abs_dx_lloyd"] <= 1e-9
+    assert r["max_abs_dx_final"] <= 1e-7
