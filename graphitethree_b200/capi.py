@@ -184,9 +184,11 @@ class Handle:
         _check(lib().b200cvt_get_stats(self._h, st.ctypes.data_as(_qp)))
         d = dict(planes=int(st[0]), cuts=int(st[1]), triangles=int(st[2]), nonempty_pairs=int(st[3]),
                  redo_seeds=int(st[4]), candidate_pairs=int(st[5]), pair_cap=int(st[6]), grid_cells=int(st[7]))
-        for i, ph in enumerate(("advance", "cut", "integrate")):
-            r, l = int(st[8 + 2 * i]), int(st[9 + 2 * i])
-            d["phase_" + ph] = dict(rounds=r, lanes_per_round=(l / r if r else 0.0))
+        d["clip_planes"] = int(st[8])
+        d["subdivision"] = dict(pieces=int(st[9]), pieces_uncertified=int(st[10]), hops=int(st[11]), seeds_collected=int(st[12]))
+        d["facets_uncertified"] = int(st[14])                     # home list ended inside the distance bound
+        d["facets_subdivided"] = int(st[15] & 0xffffffff)         # ... of which covered by small pieces
+        d["facets_subdivision_gave_up"] = int(st[15] >> 32)       # ... budgets exceeded: whole-facet grid scan
         return d
 
     def lloyd(self, x, nb_iter, locked=None, callback=None):

@@ -260,7 +260,7 @@ struct b200cvt_ctx {
     // pairs
     u32 pair_cap = 0;
     DevBuf<u32> pair_cnt, pair_facet, pair_mask, max_cnt;
-    DevBuf<uint2> tasks;
+    DevBuf<uint2> tasks, big_list;
     // flat pair list (seed-major, facets ascending) + per-pair contributions
     DevBuf<u32> pair_off, flat_seed, flat_facet, slow_list;
     DevBuf<double> contrib, facet_area, planes;
@@ -492,7 +492,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
     const u32 nown = h->qend() - h->qbegin();
     h->pair_cnt.ensure((size_t)S + 1);
     h->pair_off.ensure((size_t)nown + 2);
-    h->max_cnt.ensure(2);
+    h->max_cnt.ensure(4);
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->pair_cnt.p, h->pair_off.p, (int)nown + 1, h->stream);
     h->cub_tmp.ensure(scan_bytes);
@@ -500,7 +500,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
         h->pair_facet.ensure((size_t)S * h->pair_cap);
         h->pair_mask.ensure((size_t)S * h->pair_cap);
         CUDA_CHECK(cudaMemsetAsync(h->pair_cnt.p, 0, sizeof(u32) * ((size_t)S + 1), h->stream));
-        CUDA_CHECK(cudaMemsetAsync(h->max_cnt.p, 0, 2 * sizeof(u32), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->max_cnt.p, 0, 4 * sizeof(u32), h->stream));
         FacetPairArgs a;
         memset(&a, 0, sizeof(a));
         a.tri = h->tri.p; a.T = h->T; a.xs = h->xs.p; a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.kstride = h->kstride;
@@ -511,6 +511,10 @@ static void run_pairs_t(b200cvt_ctx* h) {
         a.max_cnt = h->max_cnt.p; a.stats = h->want_stats ? h->stats.p : nullptr; a.g = h->g;
         h->tasks.ensure(std::max<size_t>((size_t)h->T * 2, 1024));
         a.tasks = h->tasks.p; a.task_cap = (u32)std::min<size_t>(h->tasks.cap, 0xffffffffu); a.task_n = h->max_cnt.p + 1;
+        if (NC == 3) {
+            h->big_list.ensure(std::max<size_t>((size_t)h->T / 8, 4096));
+            a.big_list = h->big_list.p; a.big_cap = (u32)std::min<size_t>(h->big_list.cap, 0xffffffffu); a.big_n = h->max_cnt.p + 2;
+        }
         if (h->T > 0 && h->nranks > 1) {
             // the facets that can meet the cell of an owned seed
             h->facet_cell.ensure(h->T); h->facet_list.ensure(h->T); h->facet_list_n.ensure(1);
@@ -528,6 +532,11 @@ static void run_pairs_t(b200cvt_ctx* h) {
         }
         if (h->T > 0) {
             LAUNCH(h, (facet_home_kernel<D, NC>), div_up(h->T, 128), 128, 0, a);
+            if (NC == 3) {
+                const size_t smem_big = (size_t)BIG_WARPS * BIG_STACK * sizeof(BigPiece<D>);
+                CUDA_CHECK(cudaFuncSetAttribute(facet_big_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+                LAUNCH(h, facet_big_kernel<D>, (u32)h->num_sms * 4u, BIG_WARPS * 32, smem_big, a);
+            }
             LAUNCH(h, (facet_task_kernel<D, NC>), (u32)h->num_sms * 8u, 128, 0, a);
         }
         // flat offsets of the owned seeds (pair_cnt[qend] is 0: only owned seeds receive pairs)

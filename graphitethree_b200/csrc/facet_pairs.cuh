@@ -52,6 +52,7 @@ struct FacetPairArgs {
     u32 cap;
     u32* max_cnt;             // device scalar: max row length seen (overflow detection)
     uint2* tasks; u32 task_cap; u32* task_n;   // candidate (seed, facet) tasks of kernel A for kernel B
+    uint2* big_list; u32 big_cap; u32* big_n;  // (facet, home seed) of the facets left to facet_big_kernel
     unsigned long long* stats; // optional: [14] facets that took the grid fallback
     GridParams g;
 };
@@ -61,7 +62,8 @@ struct FacetPairArgs {
 // not strictly inside (candidate neighbours); *hop = first bisector with the facet centroid outside
 // (the neighbour is closer to the centroid than s), -1 if none.
 // The side values only feed conservative decisions (a rounding margin is applied), so FMA is used.
-template <int D, int NC, bool HOME>
+// MODE 0: mask only; 1 (home): + candidates, stops at the first hop; 2 (walk): + candidates, no hop
+template <int D, int NC, int MODE>
 __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2, const double* pi, const double* prow, u32 nn,
                                               bool* empty, u32* cand, int* hop) {
     constexpr int PS = PLANE_STRIDE(D);
@@ -71,7 +73,7 @@ __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2
     const double R2lim = 4.1 * R2;
     u32 mask = 0, cm = 0;
     bool emp = false;
-    if (HOME) *hop = -1;
+    if (MODE == 1) *hop = -1;
     // one bisector row = PS doubles, fetched as 16-byte vectors; the next row is requested before this one is used
     double2 rowbuf[PS / 2], nextbuf[PS / 2];
     if (nn > 0) {
@@ -110,14 +112,14 @@ __device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2
             all_in = all_in && (tk > margin);
             all_out = all_out && (tk < -margin);
         }
-        if (HOME && tsum < 0.0) { *hop = (int)jj; break; }
+        if (MODE == 1 && tsum < 0.0) { *hop = (int)jj; break; }
         if (all_in) continue;   // clearly inside: cannot touch any clipped polygon / cell
         cm |= 1u << jj;
         if (all_out) emp = true;   // clearly outside: removes the element
         else mask |= 1u << jj;
     }
     *empty = emp;
-    if (HOME) *cand = cm;
+    if (MODE >= 1) *cand = cm;
     return mask;
 }
 
@@ -164,10 +166,245 @@ __device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const doubl
                     if (!in) continue;
                     const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
                     bool empty = false;
-                    const u32 mask = classify_facet<D, NC, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                    const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
                     if (!empty) emit_pair<D>(a, s, f, mask);
                 }
             }
+}
+
+// Candidates of a FACET whose home list does not reach the distance bound because the facet is much larger than the seed
+// spacing (crease facets of an anisotropic 6D surface span tens of cells; their corner balls hold 10^4 seeds). The facet
+// is covered by pieces: a piece whose home list reaches its distance bound is handled by the one-level rule of
+// facet_home_kernel (home seed of the piece by hopping, then every listed neighbour with a piece corner not strictly
+// inside its bisector); any other piece is bisected along its longest edge, down to half a seed spacing, where the union
+// of the piece's corner balls is scanned on the grid (a few cells). A cell that meets the facet meets a piece. Purely
+// geometric, hence complete whatever the neighbour lists are. facet_home_kernel only lists such facets; here one WARP
+// takes one facet: the pieces live on a per-warp stack in shared memory, every round each lane pops one piece and either
+// settles it or pushes its two halves; the seeds found go into a per-warp hash set; the lanes then classify the set
+// against the whole facet with each seed's own bisectors and emit every pair once.
+#define BIG_WARPS 2
+#define BIG_HASH 1024            // slots per warp
+#define BIG_HASH_MAX 768         // distinct seeds per facet before giving up
+#define BIG_STACK 160            // pieces per warp
+#define BIG_MAX_ROUNDS 256
+
+template <int D> struct BigPiece { double w[3][D]; u32 home; u32 pad; };
+
+template <int D>
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
+    constexpr int PS = PLANE_STRIDE(D);
+    extern __shared__ double s_big[];
+    __shared__ u32 s_tab[BIG_WARPS][BIG_HASH];
+    __shared__ u32 s_cnt[BIG_WARPS][2];      // [0] distinct seeds [1] stack height
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+    u32* tab = s_tab[w];
+    BigPiece<D>* stack = (BigPiece<D>*)s_big + (size_t)w * BIG_STACK;
+    const u32 nbig = min(*a.big_n, a.big_cap);
+    const double tau = a.g.h * (1.0 / 6.0);       // half a seed spacing (the grid cell is ~3 spacings wide)
+    const double tau2 = tau * tau;
+    for (u32 e = blockIdx.x * BIG_WARPS + w; e < nbig; e += gridDim.x * BIG_WARPS) {
+        const uint2 ent = a.big_list[e];
+        const u32 f = ent.x, s0 = ent.y;
+        for (int i = lane; i < BIG_HASH; i += 32) tab[i] = B200_NONE;
+        double v[3][D];
+        const double* t = a.tri + (size_t)f * 3 * D;
+        double vmax2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double q2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { v[i][c] = t[i * D + c]; q2 += v[i][c] * v[i][c]; }
+            vmax2 = fmax(vmax2, q2);
+        }
+        if (lane == 0) { s_cnt[w][0] = 0; s_cnt[w][1] = 0; }
+        __syncwarp();
+        auto collect = [&](u32 sd) -> bool {
+            u32 slot = (sd * 2654435761u) >> 22;
+            for (int probe = 0; probe < BIG_HASH; ++probe) {
+                const u32 old = atomicCAS(&tab[slot], B200_NONE, sd);
+                if (old == sd) return true;
+                if (old == B200_NONE) return atomicAdd(&s_cnt[w][0], 1u) < BIG_HASH_MAX;
+                slot = (slot + 1) & (BIG_HASH - 1);
+            }
+            return false;
+        };
+        bool ok = true;
+        for (int round = 0; round < BIG_MAX_ROUNDS; ++round) {
+            double pw[3][D];
+            u32 home = s0;
+            bool active;
+            if (round == 0) {
+                // first round: 32 pieces = five levels of longest-edge bisection, lane bit b picks the half at level b
+                active = true;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) pw[i][c] = v[i][c];
+                for (int level = 0; level < 5; ++level) {
+                    double e2[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) e2[i] = dist2<D>(pw[i], pw[(i + 1) % 3]);
+                    int le = 0;
+                    if (e2[1] > e2[le]) le = 1;
+                    if (e2[2] > e2[le]) le = 2;
+                    const int i0 = le, i1 = (le + 1) % 3;
+                    const int repl = ((lane >> level) & 1) ? i0 : i1;      // the corner replaced by the midpoint
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const double mid = 0.5 * (pw[i0][c] + pw[i1][c]);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) if (i == repl) pw[i][c] = mid;
+                    }
+                }
+            } else {
+                const u32 height = s_cnt[w][1];
+                if (height == 0) break;
+                const u32 take = min(height, 32u);
+                active = (u32)lane < take;
+                if (active) {
+                    const BigPiece<D>& pc = stack[height - 1 - lane];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int c = 0; c < D; ++c) pw[i][c] = pc.w[i][c];
+                    home = pc.home;
+                }
+                __syncwarp();
+                if (lane == 0) s_cnt[w][1] = height - take;
+                __syncwarp();
+            }
+            if (!__all_sync(B200_FULL, ok)) break;
+            if (active) {
+                double wmax2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    double q2 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) q2 += pw[i][c] * pw[i][c];
+                    wmax2 = fmax(wmax2, q2);
+                }
+                // home seed of the piece, starting from its parent's
+                bool certified = false, empty0 = false;
+                u32 cand = 0;
+                for (int it = 0; it < 64; ++it) {
+                    if (a.has_planes && !a.has_planes[home]) break;
+                    double p0[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) p0[c] = xs[home].p[c];
+                    const u32 nn0 = min(min(a.nbr_n[home], a.kstride), 31u);
+                    int hop = -1;
+                    const u32 m0 = classify_facet<D, 3, 1>(pw, wmax2, p0, a.planes + (size_t)home * a.kstride * PS, nn0, &empty0, &cand, &hop);
+                    if (hop >= 0) { home = a.nbr[(size_t)home * a.kstride + hop]; cand = 0; continue; }
+                    certified = (m0 & PMASK_SR_OK) || (nn0 + 1 >= a.S);
+                    break;
+                }
+                bool split = false;
+                if (!certified) {
+                    double e2[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) e2[i] = dist2<D>(pw[i], pw[(i + 1) % 3]);
+                    int le = 0;
+                    if (e2[1] > e2[le]) le = 1;
+                    if (e2[2] > e2[le]) le = 2;
+                    if (e2[le] > tau2) {
+                        split = true;
+                        const u32 pos = atomicAdd(&s_cnt[w][1], 2u);
+                        if (pos + 2 > BIG_STACK) ok = false;
+                        else {
+                            // (mid, w[le+1], w[le+2]) and (w[le], mid, w[le+2])
+                            const int i0 = le, i1 = (le + 1) % 3, i2 = (le + 2) % 3;
+                            BigPiece<D>& c0 = stack[pos];
+                            BigPiece<D>& c1 = stack[pos + 1];
+#pragma unroll
+                            for (int c = 0; c < D; ++c) {
+                                const double mid = 0.5 * (pw[i0][c] + pw[i1][c]);
+                                c0.w[0][c] = mid; c0.w[1][c] = pw[i1][c]; c0.w[2][c] = pw[i2][c];
+                                c1.w[0][c] = pw[i0][c]; c1.w[1][c] = mid; c1.w[2][c] = pw[i2][c];
+                            }
+                            c0.home = home; c1.home = home;
+                        }
+                    }
+                }
+                if (!split) {
+                    if (a.stats) { atomicAdd(&a.stats[9], 1ull); if (!certified) atomicAdd(&a.stats[10], 1ull); }
+                    if (certified) {
+                        ok = ok && collect(home);
+                        while (cand && ok) {
+                            const int jj = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            ok = collect(a.nbr[(size_t)home * a.kstride + jj]);
+                        }
+                    } else {
+                        // exact nearest seed of the piece centroid, then the union of the corner balls B(w_i, |w_i - home|)
+                        double gc[D];
+#pragma unroll
+                        for (int c = 0; c < D; ++c) gc[c] = (pw[0][c] + pw[1][c] + pw[2][c]) * (1.0 / 3.0);
+                        home = grid_nearest<D>(xs, a.cell_range, a.g, gc, nullptr);
+                        double r2[3], lo3[3], hi3[3];
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) { lo3[ax] = 1e300; hi3[ax] = -1e300; }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            r2[i] = dist2<D>(pw[i], xs[home].p) * (1.0 + 1e-12);
+                            const double rr = sqrt(r2[i]) * (1.0 + 1e-12);
+#pragma unroll
+                            for (int ax = 0; ax < 3; ++ax) { lo3[ax] = fmin(lo3[ax], pw[i][ax] - rr); hi3[ax] = fmax(hi3[ax], pw[i][ax] + rr); }
+                        }
+                        int lo[3], hi[3];
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) { lo[ax] = grid_coord(a.g, lo3[ax], ax); hi[ax] = grid_coord(a.g, hi3[ax], ax); }
+                        for (int cz = lo[2]; cz <= hi[2] && ok; ++cz)
+                            for (int cy = lo[1]; cy <= hi[1] && ok; ++cy)
+                                for (int cx = lo[0]; cx <= hi[0] && ok; ++cx) {
+                                    const uint2 rg = a.cell_range[morton_encode(a.g, cx, cy, cz)];
+                                    for (u32 sd = rg.x; sd < rg.y && ok; ++sd) {
+                                        double ps[D];
+#pragma unroll
+                                        for (int c = 0; c < D; ++c) ps[c] = xs[sd].p[c];
+                                        bool in = false;
+#pragma unroll
+                                        for (int i = 0; i < 3; ++i) in = in || dist2<D>(pw[i], ps) <= r2[i];
+                                        if (in) ok = collect(sd);
+                                    }
+                                }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const bool all_ok = __all_sync(B200_FULL, ok) && s_cnt[w][1] == 0;
+        __syncwarp();
+        if (a.stats && lane == 0) atomicAdd(&a.stats[15], all_ok ? 1ull : (1ull << 32));
+        if (all_ok) {
+            // classification of (facet, seed) for every collected seed, with the seed's own bisectors: the set is first
+            // compacted into the (now empty) stack area so that every lane has a seed
+            u32* dense = (u32*)stack;
+            u32 nd = 0;
+            for (int i0 = 0; i0 < BIG_HASH; i0 += 32) {
+                const u32 sd = tab[i0 + lane];
+                const bool keep = sd != B200_NONE && sd >= a.qbegin && sd < a.qend && !(a.has_planes && !a.has_planes[sd]);
+                const u32 m = __ballot_sync(B200_FULL, keep);
+                if (keep) dense[nd + __popc(m & ((1u << lane) - 1u))] = sd;
+                nd += __popc(m);
+            }
+            __syncwarp();
+            for (u32 i = lane; i < nd; i += 32) {
+                const u32 sd = dense[i];
+                double ps[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) ps[c] = xs[sd].p[c];
+                const u32 nns = min(min(a.nbr_n[sd], a.kstride), 31u);
+                bool empty = false;
+                const u32 mask = classify_facet<D, 3, 0>(v, vmax2, ps, a.planes + (size_t)sd * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                if (!empty) emit_pair<D>(a, sd, f, mask);
+            }
+        } else if (lane == 0) {
+            grid_candidates<D, 3>(a, v, vmax2, s0, f);      // budgets exceeded: corner balls of the whole facet
+        }
+        __syncwarp();
+    }
 }
 
 // kernel A: one thread per facet — home seed, classification of (facet, home), candidate tasks
@@ -216,7 +453,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             for (int c = 0; c < D; ++c) p0[c] = xs[s0].p[c];
             const u32 nn0 = min(min(a.nbr_n[s0], a.kstride), 31u);
             int hop = -1;
-            mask0 = classify_facet<D, NC, true>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
+            mask0 = classify_facet<D, NC, 1>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
             if (hop >= 0) { s0 = a.nbr[(size_t)s0 * a.kstride + hop]; cand = 0; continue; }
             // the scan reached the distance bound (or the list holds every other seed): s0 is the nearest seed of
             // the centroid and every candidate is in the list
@@ -248,7 +485,19 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             for (int i = 0; i < NC; ++i)
 #pragma unroll
                 for (int c = 0; c < D; ++c) vv[i][c] = v[i][c];
-            grid_candidates<D, NC>(a, vv, vmax2, s0, f);
+            // facets much larger than the seed spacing go to facet_big_kernel (the corner balls of the whole facet would
+            // hold thousands of seeds); everything else, and tets, scan the grid here
+            bool done = false;
+            if (NC == 3 && a.big_list) {
+                double dm2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) dm2 = fmax(dm2, dist2<D>(vv[i], vv[(i + 1) % 3]));
+                if (dm2 > a.g.h * a.g.h) {
+                    const u32 pos = atomicAdd(a.big_n, 1u);
+                    if (pos < a.big_cap) { a.big_list[pos] = make_uint2(f, s0); done = true; }
+                }
+            }
+            if (!done) grid_candidates<D, NC>(a, vv, vmax2, s0, f);
         }
     }
     // candidate tasks (seed, facet), appended with one atomic per warp
@@ -299,7 +548,7 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
         for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
         const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
         bool empty = false;
-        const u32 mask = classify_facet<D, NC, false>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+        const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
         if (!empty) emit_pair<D>(a, s, f, mask);
     }
 }
