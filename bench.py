@@ -27,6 +27,16 @@ import time
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout. Libraries loaded later write banners to file descriptor 1 (NCCL prints its
+# version there from C): everything but the final line is sent to stderr, the line itself goes to the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -157,7 +167,7 @@ def run_reference(args, rank, world):
     line.update({"value": value, "ms_per_step": 1e3 * tt / max(args.steps, 1),
                  "cpu_baseline": {"value": value, "unit": "seed-iterations/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "seed-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -393,7 +403,7 @@ def main():
                                             "sample": "2 Lloyd iterations on the full input, %.1f s" % t}
             except Exception as ex_:
                 line["cpu_baseline"] = {"error": str(ex_)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     h.close()
     if world > 1:
         dist.barrier()

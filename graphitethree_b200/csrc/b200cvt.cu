@@ -264,6 +264,7 @@ struct b200cvt_ctx {
     // flat pair list (seed-major, facets ascending) + per-pair contributions
     DevBuf<u32> pair_off, flat_seed, flat_facet, slow_list;
     DevBuf<double> contrib, facet_area, planes;
+    DevBuf<float> planes32;
     DevBuf<uint8_t> pstat;
     DevBuf<u32> flat_mask, iota;
     DevBuf<unsigned char> sort_tmp;
@@ -469,7 +470,8 @@ static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds, b
     }
     if (want_planes) {
         h->planes.ensure((size_t)S * h->kstride * (h->dim == 3 ? 6 : h->dim + 2));
-        a.planes = h->planes.p;
+        h->planes32.ensure((size_t)S * h->kstride * (h->dim == 3 ? 4 : 8));
+        a.planes = h->planes.p; a.planes32 = h->planes32.p;
     }
     if (h->dim == 3) launch_knn<3>(h, a, a.qend - a.qbegin); else launch_knn<6>(h, a, a.qend - a.qbegin);
     if (k == 20 && all_seeds) h->prev_valid = true;
@@ -504,7 +506,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
         FacetPairArgs a;
         memset(&a, 0, sizeof(a));
         a.tri = h->tri.p; a.T = h->T; a.xs = h->xs.p; a.nbr = h->nbr.p; a.nbr_n = h->nbr_n.p; a.kstride = h->kstride;
-        a.planes = h->planes.p; a.has_planes = h->nranks > 1 ? h->has_planes.p : nullptr;
+        a.planes32 = h->planes32.p; a.has_planes = h->nranks > 1 ? h->has_planes.p : nullptr;
         a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
         a.facet_guess = h->facet_guess.p; a.S = S; a.qbegin = h->qbegin(); a.qend = h->qend();
         a.pair_cnt = h->pair_cnt.p; a.pair_facet = h->pair_facet.p; a.pair_mask = h->pair_mask.p; a.cap = h->pair_cap;
@@ -658,13 +660,14 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     if (!h->grid_valid) build_grid(h);
     CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
     h->planes.ensure((size_t)S * h->kstride * PLANE_STRIDE(D));
+    h->planes32.ensure((size_t)S * h->kstride * PLANE32_STRIDE(D));
     if (h->nranks == 1) {
         // neighbour lists + bisector tables of every seed (the facet walk may visit any seed)
         // (the kNN kernel writes the bisector rows with the lists; lists left by b200cvt_knn get theirs from plane_table_kernel)
         if (!h->knn_valid || h->k != 20) run_knn_main(h, 20, false, true, true);
         if (!h->planes_valid) {
             LAUNCH(h, plane_table_kernel<D>, std::min<u32>(div_up((u64)S * h->kstride, 256), (u32)h->num_sms * 16u), 256, 0,
-                   h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, (const u32*)nullptr, h->planes.p);
+                   h->xs.p, h->nbr.p, h->nbr_n.p, h->kstride, (const u32*)nullptr, 0u, S, (const u32*)nullptr, h->planes.p, h->planes32.p);
             h->planes_valid = true;
         }
     } else {
@@ -696,7 +699,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         // still valid bounds (any 20 other seeds bound the 20th distance), so they stay usable once written
         if (!h->prev_valid) CUDA_CHECK(cudaMemsetAsync(h->nbr_prev.p, 0xff, sizeof(u32) * (size_t)S * 20, h->stream));
         a.prev_in = h->nbr_prev.p; a.prev_out = h->nbr_prev.p; a.prev_stride = 20;
-        a.planes = h->planes.p;
+        a.planes = h->planes.p; a.planes32 = h->planes32.p;
         launch_knn<D>(h, a, S);
         h->prev_valid = true; h->knn_valid = true; h->planes_valid = true;
     }
@@ -1155,7 +1158,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
     h->locked.release(); h->cnt_orig.release(); h->stats.release();
     h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release();
-    h->planes.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->sort_tmp.release();
+    h->planes.release(); h->planes32.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->sort_tmp.release();
     h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
     h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

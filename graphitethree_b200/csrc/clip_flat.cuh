@@ -197,7 +197,7 @@ __global__ void facet_area_kernel(const double* tri, u32 T, double* area) {
 template <int D>
 __global__ void __launch_bounds__(256)
 plane_table_kernel(const void* xs_, const u32* nbr, const u32* nbr_n, u32 kstride, const u32* seed_list, u32 qbegin, u32 nseeds,
-                   const u32* nseeds_dev, double* planes) {
+                   const u32* nseeds_dev, double* planes, float* planes32) {
     constexpr int PS = PLANE_STRIDE(D);
     const SeedRec<D>* xs = (const SeedRec<D>*)xs_;
     if (nseeds_dev) nseeds = *nseeds_dev;
@@ -219,7 +219,15 @@ plane_table_kernel(const void* xs_, const u32* nbr, const u32* nbr_n, u32 kstrid
             d += (pi[c] + pj[c]) * nc;
         }
         o[D] = d;
-        o[D + 1] = dist2<D>(pi, pj);
+        const double dij = dist2<D>(pi, pj);
+        o[D + 1] = dij;
+        if (planes32) {
+            constexpr int PS32 = (D == 3) ? 4 : 8;
+            float* o32 = planes32 + ((size_t)s * kstride + jj) * PS32;
+#pragma unroll
+            for (int c = 0; c < D; ++c) o32[c] = (float)(pi[c] - pj[c]);
+            o32[D] = (float)dij;
+        }
     }
 }
 
@@ -278,9 +286,10 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
             R2 = fmax(R2, dist2<D>(pi, v));
         }
     }
-    // no masked bisector: the cell contains the facet, the radius test was decided on the unclipped facet
+    // no masked bisector: the cell contains the facet. The classification (FP32, conservative) may have certified the radius
+    // test on the unclipped facet; if it did not, the test is redone exactly below with the last neighbour
     bool sr_ok = (mask == 0) && (mask_in & 0x80000000u), slow = false, cut_any = false;
-    int last_jj = (mask == 0) ? (int)nn - 1 : -1;
+    int last_jj = -1;
     // clip_by_cell_SR (generic_RVD.h:2155-2177) over the masked bisectors, increasing distance
     while (mask) {
         const int jj = __ffs(mask) - 1;

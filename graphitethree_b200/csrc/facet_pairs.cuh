@@ -38,7 +38,7 @@ struct FacetPairArgs {
     u32 T;
     const void* xs;
     const u32* nbr; const u32* nbr_n; u32 kstride;
-    const double* planes;     // [S][kstride][PLANE_STRIDE]
+    const float* planes32;    // [S][kstride][PLANE32_STRIDE] FP32 filter copy of the bisector table (n, |n|^2)
     const uint8_t* has_planes; // optional [S]: 1 if the seed's rows of nbr/planes are valid (sharded runs)
     const u32* facet_list; const u32* facet_list_n;   // optional: the facets to process (sharded runs), count on the device
     const uint2* cell_range;
@@ -61,58 +61,76 @@ struct FacetPairArgs {
 // (| PMASK_SR_OK); *empty = some bisector has all corners outside; *cand = bisectors with a corner
 // not strictly inside (candidate neighbours); *hop = first bisector with the facet centroid outside
 // (the neighbour is closer to the centroid than s), -1 if none.
-// The side values only feed conservative decisions (a rounding margin is applied), so FMA is used.
 // MODE 0: mask only; 1 (home): + candidates, stops at the first hop; 2 (walk): + candidates, no hop
+//
+// The side values only feed conservative decisions, so the scan runs in FP32 on seed-local coordinates: with
+// q = c - p_s (FP64 difference, rounded once) the reference's side value 2 c.n - d (generic_RVD_polygon.h:257-297) is
+// 2 q.n + |n|^2, n = p_s - p_j, and the filter table (PLANE32_STRIDE floats per bisector: n, |n|^2) holds n and |n|^2
+// rounded to float. Rounding errors: <= 1e-6 (|q||n| + |n|^2) for the FP32 evaluation, plus the reference's own FP64
+// rounding on global coordinates, <= 4e-15 (|c|^2 + |p_s|^2); both are covered by the margin. A corner is "inside" /
+// "outside" only beyond the margin, the radius test passes only beyond a 1e-5 relative inflation, so every decision
+// taken here also holds for the reference's FP64 values; the exact tests are redone by the clip kernels.
+#define PLANE32_STRIDE(D) ((D) == 3 ? 4 : 8)
+
 template <int D, int NC, int MODE>
-__device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2, const double* pi, const double* prow, u32 nn,
+__device__ __forceinline__ u32 classify_facet(const double (*v)[D], double vmax2, const double* pi, const float* prow, u32 nn,
                                               bool* empty, u32* cand, int* hop) {
-    constexpr int PS = PLANE_STRIDE(D);
-    double R2 = 0.0;
+    constexpr int PS = PLANE32_STRIDE(D);
+    float q[NC][D];
+    double R2d = 0.0, pi2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) R2 = fmax(R2, dist2<D>(pi, v[i]));
-    const double R2lim = 4.1 * R2;
+    for (int c = 0; c < D; ++c) pi2 += pi[c] * pi[c];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        double r = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double dq = v[i][c] - pi[c];
+            q[i][c] = (float)dq;
+            r += dq * dq;
+        }
+        R2d = fmax(R2d, r);
+    }
+    const float R2 = __double2float_ru(R2d);
+    const float R2lim = 4.1f * R2 * 1.00001f;
+    const float mextra = __double2float_ru(4e-15 * (vmax2 + pi2));
     u32 mask = 0, cm = 0;
     bool emp = false;
     if (MODE == 1) *hop = -1;
-    // one bisector row = PS doubles, fetched as 16-byte vectors; the next row is requested before this one is used
-    double2 rowbuf[PS / 2], nextbuf[PS / 2];
+    // one bisector row = PS floats, fetched as 16-byte vectors; the next row is requested before this one is used
+    float4 rowbuf[PS / 4], nextbuf[PS / 4];
     if (nn > 0) {
-        const double2* r2 = (const double2*)prow;
+        const float4* r4 = (const float4*)prow;
 #pragma unroll
-        for (int q = 0; q < PS / 2; ++q) nextbuf[q] = __ldg(r2 + q);
+        for (int k = 0; k < PS / 4; ++k) nextbuf[k] = __ldg(r4 + k);
     }
     for (u32 jj = 0; jj < nn; ++jj) {
 #pragma unroll
-        for (int q = 0; q < PS / 2; ++q) rowbuf[q] = nextbuf[q];
+        for (int k = 0; k < PS / 4; ++k) rowbuf[k] = nextbuf[k];
         if (jj + 1 < nn) {
-            const double2* r2 = (const double2*)(prow + (size_t)(jj + 1) * PS);
+            const float4* r4 = (const float4*)(prow + (size_t)(jj + 1) * PS);
 #pragma unroll
-            for (int q = 0; q < PS / 2; ++q) nextbuf[q] = __ldg(r2 + q);
+            for (int k = 0; k < PS / 4; ++k) nextbuf[k] = __ldg(r4 + k);
         }
-        const double* pl = (const double*)rowbuf;
-        const double dij = pl[D + 1];
+        const float* pl = (const float*)rowbuf;
+        const float dij = pl[D];
         // radius test on the unclipped facet (generic_RVD.h:2155-2174): clipping only shrinks R2, so every
         // bisector the reference tests is visited
         if (dij > R2lim) { mask |= PMASK_SR_OK; break; }
-        double nj[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) nj[c] = pl[c];
-        const double d = pl[D];
-        // rounding margin of a side value 2 q.n - d for any point q of the facet: |q.n| <= (|q|^2 + |n|^2) / 2
-        const double margin = 1e-12 * (fabs(d) + vmax2 + dij);
-        double tsum = 0.0;
+        const float margin = 2e-6f * (R2 + dij) + mextra;
+        float tsum = 0.0f;
         bool all_in = true, all_out = true;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            double l = 0.0;
+            float l = 0.0f;
 #pragma unroll
-            for (int c = 0; c < D; ++c) l = fma(v[i][c], nj[c], l);
-            const double tk = fma(2.0, l, -d);
+            for (int c = 0; c < D; ++c) l = fmaf(q[i][c], pl[c], l);
+            const float tk = fmaf(2.0f, l, dij);
             tsum += tk;
             all_in = all_in && (tk > margin);
             all_out = all_out && (tk < -margin);
         }
-        if (MODE == 1 && tsum < 0.0) { *hop = (int)jj; break; }
+        if (MODE == 1 && tsum < 0.0f) { *hop = (int)jj; break; }
         if (all_in) continue;   // clearly inside: cannot touch any clipped polygon / cell
         cm |= 1u << jj;
         if (all_out) emp = true;   // clearly outside: removes the element
@@ -136,7 +154,7 @@ __device__ __forceinline__ void emit_pair(const FacetPairArgs& a, u32 s, u32 f, 
 // every owned seed inside the union of the balls B(c_i, |c_i - s0|), from the uniform grid
 template <int D, int NC>
 __device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const double (*v)[D], double vmax2, u32 s0, u32 f) {
-    constexpr int PS = PLANE_STRIDE(D);
+    constexpr int PS = PLANE32_STRIDE(D);
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
     double r2[NC], lo3[3], hi3[3];
 #pragma unroll
@@ -166,7 +184,7 @@ __device__ __noinline__ void grid_candidates(const FacetPairArgs& a, const doubl
                     if (!in) continue;
                     const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
                     bool empty = false;
-                    const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                    const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes32 + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
                     if (!empty) emit_pair<D>(a, s, f, mask);
                 }
             }
@@ -193,7 +211,7 @@ template <int D> struct BigPiece { double w[3][D]; u32 home; u32 pad; };
 template <int D>
 __global__ void __launch_bounds__(BIG_WARPS * 32)
 facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
-    constexpr int PS = PLANE_STRIDE(D);
+    constexpr int PS = PLANE32_STRIDE(D);
     extern __shared__ double s_big[];
     __shared__ u32 s_tab[BIG_WARPS][BIG_HASH];
     __shared__ u32 s_cnt[BIG_WARPS][2];      // [0] distinct seeds [1] stack height
@@ -295,7 +313,7 @@ facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
                     for (int c = 0; c < D; ++c) p0[c] = xs[home].p[c];
                     const u32 nn0 = min(min(a.nbr_n[home], a.kstride), 31u);
                     int hop = -1;
-                    const u32 m0 = classify_facet<D, 3, 1>(pw, wmax2, p0, a.planes + (size_t)home * a.kstride * PS, nn0, &empty0, &cand, &hop);
+                    const u32 m0 = classify_facet<D, 3, 1>(pw, wmax2, p0, a.planes32 + (size_t)home * a.kstride * PS, nn0, &empty0, &cand, &hop);
                     if (hop >= 0) { home = a.nbr[(size_t)home * a.kstride + hop]; cand = 0; continue; }
                     certified = (m0 & PMASK_SR_OK) || (nn0 + 1 >= a.S);
                     break;
@@ -397,7 +415,7 @@ facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
                 for (int c = 0; c < D; ++c) ps[c] = xs[sd].p[c];
                 const u32 nns = min(min(a.nbr_n[sd], a.kstride), 31u);
                 bool empty = false;
-                const u32 mask = classify_facet<D, 3, 0>(v, vmax2, ps, a.planes + (size_t)sd * a.kstride * PS, nns, &empty, nullptr, nullptr);
+                const u32 mask = classify_facet<D, 3, 0>(v, vmax2, ps, a.planes32 + (size_t)sd * a.kstride * PS, nns, &empty, nullptr, nullptr);
                 if (!empty) emit_pair<D>(a, sd, f, mask);
             }
         } else if (lane == 0) {
@@ -411,7 +429,7 @@ facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
 template <int D, int NC>
 __global__ void __launch_bounds__(128, FACET_MINBLK)
 facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
-    constexpr int PS = PLANE_STRIDE(D);
+    constexpr int PS = PLANE32_STRIDE(D);
     const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
@@ -453,7 +471,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             for (int c = 0; c < D; ++c) p0[c] = xs[s0].p[c];
             const u32 nn0 = min(min(a.nbr_n[s0], a.kstride), 31u);
             int hop = -1;
-            mask0 = classify_facet<D, NC, 1>(v, vmax2, p0, a.planes + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
+            mask0 = classify_facet<D, NC, 1>(v, vmax2, p0, a.planes32 + (size_t)s0 * a.kstride * PS, nn0, &empty0, &cand, &hop);
             if (hop >= 0) { s0 = a.nbr[(size_t)s0 * a.kstride + hop]; cand = 0; continue; }
             // the scan reached the distance bound (or the list holds every other seed): s0 is the nearest seed of
             // the centroid and every candidate is in the list
@@ -526,7 +544,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
 template <int D, int NC>
 __global__ void __launch_bounds__(128, FACET_MINBLK)
 facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
-    constexpr int PS = PLANE_STRIDE(D);
+    constexpr int PS = PLANE32_STRIDE(D);
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
     const u32 ntask = min(*a.task_n, a.task_cap);
     for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < ntask; e += gridDim.x * blockDim.x) {
@@ -548,7 +566,7 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
         for (int c = 0; c < D; ++c) ps[c] = xs[s].p[c];
         const u32 nns = min(min(a.nbr_n[s], a.kstride), 31u);
         bool empty = false;
-        const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
+        const u32 mask = classify_facet<D, NC, 0>(v, vmax2, ps, a.planes32 + (size_t)s * a.kstride * PS, nns, &empty, nullptr, nullptr);
         if (!empty) emit_pair<D>(a, s, f, mask);
     }
 }

@@ -107,6 +107,7 @@ struct KnnArgs {
     // optional: bisector table row of every stored neighbour, written with the list (clip_flat.cuh: PLANE_STRIDE,
     // same values as plane_table_kernel): n = pq - pj, d = sum (pq + pj) n, |pq - pj|^2. Rows by sorted position.
     double* planes;
+    float* planes32;         // with planes: FP32 filter copy (facet_pairs.cuh: PLANE32_STRIDE floats: n, |n|^2)
     GridParams g;
 };
 
@@ -330,6 +331,18 @@ knn_kernel(KnnArgs a) {
                         double2* o = (double2*)(a.planes + (orow * a.kstride + pos) * PS);
 #pragma unroll
                         for (int c = 0; c < PS / 2; ++c) o[c] = make_double2(row[2 * c], row[2 * c + 1]);
+                        if (a.planes32) {
+                            constexpr int PS32 = (D == 3) ? 4 : 8;
+                            float r32[PS32];
+#pragma unroll
+                            for (int c = 0; c < D; ++c) r32[c] = (float)row[c];
+                            r32[D] = (float)row[D + 1];
+#pragma unroll
+                            for (int c = D + 1; c < PS32; ++c) r32[c] = 0.0f;
+                            float4* o32 = (float4*)(a.planes32 + (orow * a.kstride + pos) * PS32);
+#pragma unroll
+                            for (int c = 0; c < PS32 / 4; ++c) o32[c] = make_float4(r32[4 * c], r32[4 * c + 1], r32[4 * c + 2], r32[4 * c + 3]);
+                        }
                     }
                 }
             }

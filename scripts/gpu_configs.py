@@ -1,6 +1,6 @@
 """BASELINE.json configs C3 (trefoil tube 20 M triangles / 5 M seeds, Lloyd, here on ONE B200) and C4 (6D anisotropic
 CAD-like surface 2 M triangles / 500 k seeds): seed-iterations/s, phase times and size-independent properties.
-usage: gpu_configs.py [c3] [c4] [--small]"""
+usage: gpu_configs.py [c3] [c4] [--small] [--ref]"""
 import os, sys, time, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,6 +38,16 @@ def run(name, V, F, S, newton=0):
     out["g_identity_rel"] = float(np.abs(g - 2.0 * (m[:, None] * x - mg)).max() / np.abs(g).max())
     out["flags_overflow_or_kmax"] = int((fl & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum())
     h.close()
+    if "--ref" in sys.argv:
+        from oracle import ref
+        if ref.available():
+            r = ref.RefCVT(V, F, multithread=True)
+            r.set_points(x)
+            r.lloyd(1)                         # thread partition of the mesh
+            t = r.lloyd(2)
+            out["reference_seed_iterations_per_s_lloyd"] = S * 2 / t
+            out["reference_threads"] = ref.RefCVT.nb_threads()
+            r.close()
     print(json.dumps(out), flush=True)
 
 
