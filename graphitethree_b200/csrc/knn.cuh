@@ -56,13 +56,16 @@ template <int NPL>
 struct WarpTopK {
     u64 d[NPL];
     u32 id[NPL];
+    bool fresh;
     __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int r = 0; r < NPL; ++r) { d[r] = ~0ull; id[r] = B200_NONE; }
+        fresh = true;
     }
     // merges 32 new keys (one per lane, any order) into the sorted list
     __device__ __forceinline__ void merge(u64 bd, u32 bi, int lane) {
         warp_bitonic_sort(bd, bi, lane);
+        if (fresh) { d[0] = bd; id[0] = bi; fresh = false; return; }      // empty list: the sorted batch is the list
 #pragma unroll
         for (int r = 0; r < NPL; ++r) {
             u64 rd = __shfl_sync(B200_FULL, bd, 31 - lane);
@@ -138,9 +141,15 @@ knn_kernel(KnnArgs a) {
         u32 kq = kk + 1; if (kq > a.S) kq = a.S;
         u32 kreq = kq + 1; if (kreq > a.S) kreq = a.S;
         if (kreq > 32u * NPL) kreq = 32u * NPL;
+        // grid coordinates are evaluated once per warp, one (axis, offset) per lane, and broadcast
         int c0[3];
+        {
+            const int ax = lane % 3;
+            const double pv = ax == 0 ? pq[0] : (ax == 1 ? pq[1] : pq[2]);
+            const int gcv = grid_coord(a.g, pv, ax);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) c0[ax] = grid_coord(a.g, pq[ax], ax);
+            for (int x = 0; x < 3; ++x) c0[x] = __shfl_sync(B200_FULL, gcv, x);
+        }
 
         WarpTopK<NPL> top;
         // threshold from the previous lists
@@ -175,8 +184,11 @@ knn_kernel(KnnArgs a) {
             int blo[3], bhi[3];
             if (have_thr) {
                 const double rad = sqrt(__longlong_as_double((long long)thr0_d)) * (1.0 + 1e-9) + 1e-300;
+                const int ax = lane % 3;
+                const double pv = ax == 0 ? pq[0] : (ax == 1 ? pq[1] : pq[2]);
+                const int gcv = grid_coord(a.g, (lane < 3) ? pv - rad : pv + rad, ax);     // lanes 0-2: low corner, 3-5: high corner
 #pragma unroll
-                for (int ax = 0; ax < 3; ++ax) { blo[ax] = grid_coord(a.g, pq[ax] - rad, ax); bhi[ax] = grid_coord(a.g, pq[ax] + rad, ax); }
+                for (int x = 0; x < 3; ++x) { blo[x] = __shfl_sync(B200_FULL, gcv, x); bhi[x] = __shfl_sync(B200_FULL, gcv, 3 + x); }
             } else {
 #pragma unroll
                 for (int ax = 0; ax < 3; ++ax) { blo[ax] = c0[ax] - r; bhi[ax] = c0[ax] + r; }
