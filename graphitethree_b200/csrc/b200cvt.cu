@@ -3,11 +3,12 @@
 //
 // Per evaluation (one Lloyd iteration or one Newton function evaluation), on one GPU:
 //   1. seed_keys + radix sort + gather      : Morton-sort the seeds into the uniform grid
-//   2. knn_kernel                           : k nearest seeds of every owned seed (FP64 exact)
-//   3. pairs_kernel                         : candidate (facet, seed) pairs, rows per seed
-//   4. clip_kernel                          : one warp per seed clips + integrates, FP64
-//   5. update / scatter / reductions        : x <- mg/m (Lloyd) or f, g (Newton)
-// Everything stays in device memory between iterations.
+//   2. knn_kernel                           : 20 nearest seeds of every seed (FP64 exact) + their bisector rows
+//   3. facet_home / facet_big / facet_task  : candidate (facet, seed) pairs with classification masks, rows per seed
+//   4. compact_pairs + clip_win + reduce_pairs : flat pair list, thread-per-pair clip + integrate (FP64), per-seed sums
+//      (clip_kernel: warp per seed, for enlarged neighbourhoods / overflowing polygons; clip_tet_kernel: volumetric mode)
+//   5. update / scatter / L-BFGS kernels    : x <- mg/m (Lloyd) or f, g, direction and line search (Newton)
+// Everything stays in device memory between iterations. DESIGN.md §4 describes every kernel.
 #include "common.cuh"
 #include "knn.cuh"
 #include "clip.cuh"

@@ -1,4 +1,6 @@
-// clip.cuh — candidate (facet, seed) pairs + fused clip/integrate kernel for the surface RVD.
+// clip.cuh — warp-per-seed clip/integrate kernel for the surface RVD: the general path (any neighbour-list length,
+// polygons of up to CLIP_MAXV vertices) behind the fast thread-per-pair path of clip_flat.cuh. It re-evaluates the seeds
+// whose neighbourhood had to be enlarged (check_SR) or whose polygon overflowed the fast path.
 //
 // Replaces the facet-driven double flood-fill of
 //   GEOGen::RestrictedVoronoiDiagram::compute_surfacic_with_seeds_priority
@@ -10,12 +12,7 @@
 // against the seed's bisector planes (staged in shared memory), integrates its polygon and
 // the warp reduces mass / centroid / energy / gradient in FP64.
 //
-// Candidate pairs. For a facet f with corners c_i and ANY seed s0, a seed s whose Voronoi
-// cell meets f satisfies |c_i - s| <= |c_i - s0| for some corner i (the half-space
-// {x : |x-s| <= |x-s0|} meets the triangle iff it contains a corner). The pair kernel takes
-// s0 = nearest seed of the facet centroid and appends f to the list of every seed inside
-// the union of the three balls B(c_i, |c_i - s0|). Every true (facet, seed) pair is found
-// exactly once; false candidates are clipped away to nothing by the seed's own bisectors.
+// Candidate (facet, seed) rows come from facet_pairs.cuh.
 //
 // Arithmetic: every expression follows the reference's operation order and this translation
 // unit is compiled with -fmad=false (the reference is built with -ffp-contract=off), so that
@@ -28,104 +25,6 @@
 #define CLIP_WARPS 4
 #define CLIP_MAXV 24
 #define B200CVT_KMAX_DEV 124u
-
-// ---------------------------------------------------------------------------------------
-// candidate pairs: one thread per facet
-// ---------------------------------------------------------------------------------------
-struct PairArgs {
-    const double* tri;        // [T][3][D] facet corner coordinates
-    u32 fbegin, fend;
-    const void* xs;
-    const uint2* cell_range;
-    const u32* rank_of;
-    u32* facet_guess;         // [T] original index of the last nearest seed (B200_NONE: none)
-    u32 qbegin, qend;         // owned sorted range
-    u32* pair_cnt;            // [S] sorted order
-    u32* pair_facet;          // [S][cap]
-    u32 cap;
-    u32* max_cnt;             // device scalar: max list length seen (overflow detection)
-    GridParams g;
-};
-
-template <int D>
-__global__ void __launch_bounds__(128)
-pairs_kernel(PairArgs a) {
-    u32 f = a.fbegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.fend) return;
-    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
-    double c[3][D];
-    const double* t = a.tri + (size_t)f * 3 * D;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < D; ++k) c[i][k] = t[i * D + k];
-    double gc[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) gc[k] = (c[0][k] + c[1][k] + c[2][k]) * (1.0 / 3.0);
-
-    // stage 1: a first seed near the centroid (last iteration's answer, or a ring search)
-    u32 s0 = B200_NONE; double d0 = 1e300;
-    u32 guess = a.facet_guess[f];
-    if (guess != B200_NONE) {
-        s0 = a.rank_of[guess];
-        d0 = dist2<D>(gc, xs[s0].p);
-    } else {
-        s0 = grid_nearest<D>(xs, a.cell_range, a.g, gc, &d0);
-    }
-    // stage 2: exact nearest inside the ball B(gc, sqrt(d0))
-    {
-        double rho = sqrt(d0) * (1.0 + 1e-12);
-        int lo[3], hi[3];
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) { lo[ax] = grid_coord(a.g, gc[ax] - rho, ax); hi[ax] = grid_coord(a.g, gc[ax] + rho, ax); }
-        u32 best_orig = (u32)xs[s0].orig;
-        for (int cz = lo[2]; cz <= hi[2]; ++cz)
-            for (int cy = lo[1]; cy <= hi[1]; ++cy)
-                for (int cx = lo[0]; cx <= hi[0]; ++cx) {
-                    uint2 rg = a.cell_range[morton_encode(a.g, cx, cy, cz)];
-                    for (u32 s = rg.x; s < rg.y; ++s) {
-                        double d = dist2<D>(gc, xs[s].p);
-                        u32 o = (u32)xs[s].orig;
-                        if (d < d0 || (d == d0 && o < best_orig)) { d0 = d; s0 = s; best_orig = o; }
-                    }
-                }
-        a.facet_guess[f] = best_orig;
-    }
-    // stage 3: every seed inside the union of the balls B(c_i, |c_i - s0|)
-    double r2[3], lo3[3], hi3[3];
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) { lo3[ax] = 1e300; hi3[ax] = -1e300; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        r2[i] = dist2<D>(c[i], xs[s0].p) * (1.0 + 1e-12);
-        double rr = sqrt(r2[i]) * (1.0 + 1e-12);
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) { lo3[ax] = fmin(lo3[ax], c[i][ax] - rr); hi3[ax] = fmax(hi3[ax], c[i][ax] + rr); }
-    }
-    int lo[3], hi[3];
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) { lo[ax] = grid_coord(a.g, lo3[ax], ax); hi[ax] = grid_coord(a.g, hi3[ax], ax); }
-    u32 npairs = 0;
-    for (int cz = lo[2]; cz <= hi[2]; ++cz)
-        for (int cy = lo[1]; cy <= hi[1]; ++cy)
-            for (int cx = lo[0]; cx <= hi[0]; ++cx) {
-                uint2 rg = a.cell_range[morton_encode(a.g, cx, cy, cz)];
-                u32 sb = max(rg.x, a.qbegin), se = min(rg.y, a.qend);
-                for (u32 s = sb; s < se; ++s) {
-                    double ps[D];
-#pragma unroll
-                    for (int k = 0; k < D; ++k) ps[k] = xs[s].p[k];
-                    bool in = dist2<D>(c[0], ps) <= r2[0] || dist2<D>(c[1], ps) <= r2[1] || dist2<D>(c[2], ps) <= r2[2];
-                    if (in) {
-                        u32 slot = atomicAdd(&a.pair_cnt[s], 1u);
-                        if (slot < a.cap) a.pair_facet[(size_t)s * a.cap + slot] = f;
-                        else atomicMax(a.max_cnt, slot + 1);
-                        ++npairs;
-                    }
-                }
-            }
-    (void)npairs;
-}
 
 // ---------------------------------------------------------------------------------------
 // clip + integrate: one warp per seed, one lane per candidate facet

@@ -6,24 +6,21 @@
 // bit-identical to the reference's — but a different mapping:
 //
 //   compact_pairs_kernel  : one warp per seed sorts its candidate row by facet id and writes it
-//                           into the flat pair arrays (seed-major, facets ascending)
-//   classify_pairs_kernel : thread t walks the neighbour list of pair t's seed until the radius
-//                           test passes on the UNCLIPPED facet and records, in a bit mask, the
-//                           bisectors that do not leave all three facet corners strictly on the
-//                           seed's side. No such bisector: the cell contains the facet, the pair is
-//                           integrated at once from the precomputed facet area. All corners
-//                           strictly outside one bisector: the pair is empty. Registers only.
-//   (radix sort of the pair indices by min(popcount(mask), 7): warps of pairs with equal work)
-//   clip_cut_kernel       : thread per pair with >= 1 masked bisector: applies exactly the
-//                           reference's loop restricted to the masked bisectors (the others cannot
-//                           change the polygon), radius test with the CURRENT polygon before each.
+//                           into the flat pair arrays (seed-major, facets ascending). The rows carry, for every
+//                           pair, the bit mask of the bisectors that may cut the UNCLIPPED facet (facet_pairs.cuh:
+//                           conservative FP32 scan); no bit = the cell contains the facet = the pair is integrated
+//                           at once from the precomputed facet area.
+//   clip_win_kernel       : a block takes a window of 512 consecutive pairs, counting-sorts it by the number of
+//                           masked bisectors in shared memory (warps of pairs with equal work), then every thread
+//                           applies exactly the reference's loop restricted to the masked bisectors (the others
+//                           cannot change the polygon), radius test with the CURRENT polygon before each.
 //                           The polygon lives in shared memory, lane-interleaved
 //                           ([vertex][coord][lane]: lanes indexing different vertices never
 //                           conflict), and is clipped IN PLACE: both intersection points of a cut
-//                           are built first (all lanes together), then the vertices are moved in
+//                           are built first, then the vertices are moved in
 //                           the reference's emission order (the write index is never more than one
 //                           slot ahead of the read index; the next vertex is held in registers).
-//   reduce_pairs_kernel   : one thread per seed sums its pairs' contributions in facet order —
+//   reduce_pairs_kernel   : one warp per seed sums its pairs' contributions in facet order with a fixed tree —
 //                           deterministic, independent of the partition and of atomics order.
 //
 // Pairs the fast path cannot finish (more than CLIPF_MAXV vertices, more than two crossings of one

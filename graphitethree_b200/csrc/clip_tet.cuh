@@ -188,7 +188,10 @@ struct TetClipArgs {
     unsigned long long* stats;
 };
 
-__global__ void __launch_bounds__(TETC_WARPS * 32)
+#ifndef TETC_MINBLK
+#define TETC_MINBLK 1
+#endif
+__global__ void __launch_bounds__(TETC_WARPS * 32, TETC_MINBLK)
 clip_tet_kernel(TetClipArgs a) {
     extern __shared__ double s_dyn[];
     const int lane = threadIdx.x & 31;

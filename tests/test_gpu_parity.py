@@ -516,3 +516,30 @@ def test_rdt_closed_surface_properties_c1(built):
     ue = np.unique(e, axis=0)
     assert all(int(b) in nbr[int(a)] for a, b in ue[:: max(1, ue.shape[0] // 2000)])
     h.close()
+
+
+def test_anisotropic_6d_crease_facets_parity(built):
+    # C4-like: CAD-like surface with sharp creases lifted to 6D (normals x 0.04 x bbox diagonal). Facets next to a crease are
+    # much longer in 6D than the seed spacing and span many cells: their candidates come from facet_big_kernel (adaptive
+    # bisection). Exact cells (check_SR = true) against the oracle, no exemption.
+    V3, F = shapes.cad_like(12)
+    V = shapes.lift_anisotropic(V3, F, 0.04)
+    X = shapes.sample_surface(V, F, 6000, 2)
+    h = handle_for(V, F)
+    x = h.lloyd(X, 3)
+    h.stats()
+    h.set_seeds(x)
+    f, g = h.funcgrad(True)
+    st = h.stats()
+    assert st["facets_subdivided"] > 0 and st["facets_subdivision_gave_up"] == 0
+    assert (h.flags() & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    e = port.surface_eval(V, F, x, 1, True, kcap=256)
+    assert abs(f - e.f) <= RTOL * abs(e.f)
+    assert_close(g, e.g, what="gradient")
+    assert_close(h.seed_energy(), e.f_seed, what="per-seed energy")
+    h.set_seeds(x)
+    mg, m = h.centroids(True)
+    e0 = port.surface_eval(V, F, x, 0, True, kcap=256)
+    assert_close(m, e0.m, what="mass")
+    assert_close(mg, e0.mg, what="mass*centroid")
+    h.close()
