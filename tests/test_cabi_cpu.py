@@ -119,3 +119,22 @@ def test_sharded_lloyd_exchange_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
+
+
+def test_bench_reference_arm_contract():
+    # `bench.py --impl reference`: ONE JSON line on stdout (library banners go to stderr), the contract's keys, timed on
+    # the host cores with the reference built from its own sources (or the oracle port when it is absent)
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--small", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "CVT seed-iterations/sec" and d["unit"] == "seed-iterations/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
