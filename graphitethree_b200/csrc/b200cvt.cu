@@ -17,6 +17,7 @@
 #include "clip_tet.cuh"
 #include "lbfgs.cuh"
 #include "rdt.cuh"
+#include "mesh_prep.cuh"
 #include "../../include/b200cvt.h"
 
 #include <cub/cub.cuh>
@@ -1178,57 +1179,65 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         const int per = h->volumetric ? 4 : 3;
         // the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783)
         if (h->volumetric) weights = nullptr;
-        // pass 1: validate, bounding box, total area / volume
+        // On the device (mesh_prep.cuh): pass 1 validates the indices and reduces the bounding box and the total area /
+        // volume; pass 2 sorts the elements in Morton order of their centroids (10 bits per axis, stable: ties keep the
+        // caller's order), so that the elements one warp walks share home seeds and bisector rows — the reference reorders
+        // the caller's mesh for the same reason (mesh_partition Hilbert sort, RVD.cpp:2390-2395), here only the device copy
+        // is permuted; pass 3 gathers the corner coordinates (and weights) in that order.
+        h->has_mesh = false;       // a call that fails leaves the handle without a mesh, not with half of the new one
+        DevBuf<double> d_vert, d_w;
+        DevBuf<u32> d_elems, d_keys, d_keys2, d_vals, d_order;
+        DevBuf<MeshPartial> d_part;
+        DevBuf<unsigned char> d_tmp;
+        struct Scratch {
+            DevBuf<double>& a; DevBuf<double>& b; DevBuf<u32>& c; DevBuf<u32>& d; DevBuf<u32>& e; DevBuf<u32>& f; DevBuf<u32>& g;
+            DevBuf<MeshPartial>& p; DevBuf<unsigned char>& t;
+            ~Scratch() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); p.release(); t.release(); }
+        } scratch_guard{d_vert, d_w, d_elems, d_keys, d_keys2, d_vals, d_order, d_part, d_tmp};
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         double measure = 0.0;
-        for (u32 f = 0; f < ne; ++f) {
-            const double* p[4];
-            for (int lv = 0; lv < per; ++lv) {
-                u32 v = elems[(size_t)f * per + lv];
-                if (v >= nv) throw ArgError("element references a vertex out of range");
-                p[lv] = vertices + (size_t)v * stride;
-                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[lv][a]); hi[a] = std::max(hi[a], p[lv][a]); }
+        std::vector<u32> perm(ne);
+        h->tri.ensure((size_t)ne * per * D);
+        if (weights) h->triw.ensure((size_t)ne * 3);
+        if (ne > 0) {
+            d_vert.ensure((size_t)nv * stride); d_elems.ensure((size_t)ne * per);
+            CUDA_CHECK(cudaMemcpyAsync(d_vert.p, vertices, sizeof(double) * (size_t)nv * stride, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(d_elems.p, elems, sizeof(u32) * (size_t)ne * per, cudaMemcpyHostToDevice, h->stream));
+            if (weights) {
+                d_w.ensure(nv);
+                CUDA_CHECK(cudaMemcpyAsync(d_w.p, weights, sizeof(double) * nv, cudaMemcpyHostToDevice, h->stream));
             }
-            double e1[3], e2[3];
-            for (int a = 0; a < 3; ++a) { e1[a] = p[1][a] - p[0][a]; e2[a] = p[2][a] - p[0][a]; }
-            double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-            if (per == 3) measure += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
-            else measure += std::fabs(cx * (p[3][0] - p[0][0]) + cy * (p[3][1] - p[0][1]) + cz * (p[3][2] - p[0][2])) / 6.0;
-        }
-        // pass 2: elements in Morton order of their centroids (10 bits per axis), so that the elements one warp walks
-        // share home seeds and bisector rows. The reference reorders the caller's mesh for the same reason
-        // (mesh_partition Hilbert sort, RVD.cpp:2390-2395); here only the device copy is permuted.
-        std::vector<std::pair<u32, u32>> order(ne);
-        {
+            const u32 nblk = std::min<u32>(div_up(ne, MESHPREP_THREADS), MESHPREP_BLOCKS);
+            d_part.ensure(nblk);
+            if (per == 3) LAUNCH(h, mesh_bounds_kernel<3>, nblk, MESHPREP_THREADS, 0, d_vert.p, nv, stride, d_elems.p, ne, d_part.p);
+            else LAUNCH(h, mesh_bounds_kernel<4>, nblk, MESHPREP_THREADS, 0, d_vert.p, nv, stride, d_elems.p, ne, d_part.p);
+            std::vector<MeshPartial> part(nblk);
+            CUDA_CHECK(cudaMemcpyAsync(part.data(), d_part.p, sizeof(MeshPartial) * nblk, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            bool bad = false;
+            for (u32 i = 0; i < nblk; ++i) {
+                bad = bad || part[i].bad;
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], part[i].lo[a]); hi[a] = std::max(hi[a], part[i].hi[a]); }
+                measure += part[i].measure;
+            }
+            if (bad) throw ArgError("element references a vertex out of range");
             double maxext = 0.0;
             for (int a = 0; a < 3; ++a) maxext = std::max(maxext, hi[a] - lo[a]);
             const double sc = maxext > 0.0 ? 1023.999 / maxext : 0.0;
-            for (u32 f = 0; f < ne; ++f) {
-                u32 q[3];
-                for (int a = 0; a < 3; ++a) {
-                    double c = 0.0;
-                    for (int lv = 0; lv < per; ++lv) c += vertices[(size_t)elems[(size_t)f * per + lv] * stride + a];
-                    double t = (c * (1.0 / per) - lo[a]) * sc;
-                    q[a] = (u32)std::min(1023.0, std::max(0.0, t));
-                }
-                u32 code = 0;
-                for (int b = 0; b < 10; ++b)
-                    code |= (((q[0] >> b) & 1u) << (3 * b)) | (((q[1] >> b) & 1u) << (3 * b + 1)) | (((q[2] >> b) & 1u) << (3 * b + 2));
-                order[f] = std::make_pair(code, f);
-            }
-            std::sort(order.begin(), order.end());
-        }
-        std::vector<double> soup((size_t)ne * per * D);
-        std::vector<double> sw;
-        if (weights) sw.resize((size_t)ne * 3);
-        for (u32 i = 0; i < ne; ++i) {
-            const u32 f = order[i].second;
-            for (int lv = 0; lv < per; ++lv) {
-                const u32 v = elems[(size_t)f * per + lv];
-                const double* p = vertices + (size_t)v * stride;
-                for (int c = 0; c < D; ++c) soup[((size_t)i * per + lv) * D + c] = p[c];
-                if (weights) sw[(size_t)i * 3 + lv] = weights[v];
-            }
+            d_keys.ensure(ne); d_keys2.ensure(ne); d_vals.ensure(ne); d_order.ensure(ne);
+            if (per == 3) LAUNCH(h, mesh_codes_kernel<3>, div_up(ne, 256), 256, 0, d_vert.p, stride, d_elems.p, ne, lo[0], lo[1], lo[2], sc, d_keys.p, d_vals.p);
+            else LAUNCH(h, mesh_codes_kernel<4>, div_up(ne, 256), 256, 0, d_vert.p, stride, d_elems.p, ne, lo[0], lo[1], lo[2], sc, d_keys.p, d_vals.p);
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.p, d_keys2.p, d_vals.p, d_order.p, (int)ne, 0, 30, h->stream);
+            d_tmp.ensure(tmp_bytes);
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.p, d_keys2.p, d_vals.p, d_order.p, (int)ne, 0, 30, h->stream));
+            h->launches += 4;
+            double* sw = weights ? h->triw.p : nullptr;
+            if (per == 4) LAUNCH(h, (mesh_soup_kernel<3, 4>), div_up(ne, 256), 256, 0, d_vert.p, stride, d_elems.p, d_order.p, ne, (const double*)nullptr, h->tri.p, (double*)nullptr);
+            else if (D == 3) LAUNCH(h, (mesh_soup_kernel<3, 3>), div_up(ne, 256), 256, 0, d_vert.p, stride, d_elems.p, d_order.p, ne, d_w.p, h->tri.p, sw);
+            else LAUNCH(h, (mesh_soup_kernel<6, 3>), div_up(ne, 256), 256, 0, d_vert.p, stride, d_elems.p, d_order.p, ne, d_w.p, h->tri.p, sw);
+            CUDA_CHECK(cudaMemcpyAsync(perm.data(), d_order.p, sizeof(u32) * ne, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
         }
         // volumetric: which faces of a tet are shared with another tet (cells.tet_adjacent != NO_CELL); face lf is opposite
         // to corner lf. Taken from the caller's adjacency when given, else from matching sorted face triples.
@@ -1262,23 +1271,16 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
                         by_elem[F[i + 1].t] |= (uint8_t)(1u << F[i + 1].lf);
                     }
             }
-            for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[order[i].second];
+            for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[perm[i]];
         }
         h->host_elems.clear(); h->host_perm.clear(); h->host_adj.clear(); h->facet_adj_valid = false; h->rdt_valid = false;
         if (!h->volumetric) {
             h->host_elems.assign(elems, elems + (size_t)ne * 3);
-            h->host_perm.resize(ne);
-            for (u32 i = 0; i < ne; ++i) h->host_perm[i] = order[i].second;
+            h->host_perm = perm;
             if (adjacency) h->host_adj.assign(adjacency, adjacency + (size_t)ne * 3);
         }
         h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = measure;
         for (int a = 0; a < 3; ++a) { h->bb_lo[a] = lo[a]; h->bb_hi[a] = hi[a]; }
-        h->tri.ensure(soup.size());
-        CUDA_CHECK(cudaMemcpyAsync(h->tri.p, soup.data(), sizeof(double) * soup.size(), cudaMemcpyHostToDevice, h->stream));
-        if (weights) {
-            h->triw.ensure(sw.size());
-            CUDA_CHECK(cudaMemcpyAsync(h->triw.p, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice, h->stream));
-        }
         if (h->volumetric) {
             h->tet_inner.ensure(std::max<size_t>(ne, 1));
             if (ne > 0) CUDA_CHECK(cudaMemcpyAsync(h->tet_inner.p, inner.data(), ne, cudaMemcpyHostToDevice, h->stream));
