@@ -6,7 +6,7 @@
  * CHECK the CUDA path; nothing under graphitethree_b200/ may call, link or load it.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg use it.
  *
- * Parity status: PINNED against the reference itself — tests/test_oracle_vs_reference.py
+ * Parity status: PINNED against the reference itself — tests/test_oracle_cpu.py
  * compares every function below with oracle/_ref (the unmodified reference compiled by
  * oracle/Makefile.ref) when that build is present, and tests/golden/ holds vectors
  * generated from the reference by tests/golden/make_golden.py.
@@ -295,7 +295,37 @@ typedef struct {
     double w;
     int32_t adj_facet;   /* facet across the edge STARTING at this vertex */
     int32_t adj_seed;    /* seed across the edge ENDING at this vertex    */
+    int32_t sym[3];      /* SymbolicVertex (generic_RVD_vertex.h:376-640): sorted set, -(facet+1) / seed+1; symbolic mode only */
+    int nsym;            /* 4 = the small_set overflowed */
 } orc_vertex;
+
+/* symbolic mode (RestrictedVoronoiDiagram::set_symbolic): on while the RDT is extracted */
+static int orc_symbolic = 0;
+static struct { u32* tri; u64 cap; u64 n; } orc_rdt_sink = {0, 0, 0};
+
+/* small_set<signed_index_t,3>::insert (generic_RVD_vertex.h:169-203): sorted, no duplicates */
+static void sym_insert(orc_vertex* v, int32_t x) {
+    int pos = 0;
+    while (pos < v->nsym && pos < 3 && v->sym[pos] < x) ++pos;
+    if (pos < v->nsym && pos < 3 && v->sym[pos] == x) return;
+    if (v->nsym >= 3) { v->nsym = 4; return; }
+    for (int i = v->nsym; i > pos; --i) v->sym[i] = v->sym[i - 1];
+    v->sym[pos] = x;
+    v->nsym++;
+}
+
+/* SymbolicVertex::intersect_symbolic (generic_RVD_vertex.h:582-640): sets_intersect(v1, v2) + bisector E; 1 = ok */
+static int sym_intersect(orc_vertex* I, const orc_vertex* v1, const orc_vertex* v2, u32 E) {
+    int i = 0, j = 0, n1 = v1->nsym < 3 ? v1->nsym : 3, n2 = v2->nsym < 3 ? v2->nsym : 3;
+    I->nsym = 0;
+    while (i < n1 && j < n2) {
+        if (v1->sym[i] < v2->sym[j]) ++i;
+        else if (v2->sym[j] < v1->sym[i]) ++j;
+        else { I->sym[I->nsym++] = v1->sym[i]; ++i; ++j; }
+    }
+    sym_insert(I, (int32_t)E + 1);
+    return I->nsym == 3;
+}
 
 typedef struct {
     int n;
@@ -339,6 +369,14 @@ static int clip_by_plane(const orc_polygon* in, orc_polygon* out, const double* 
             I->w = l1 * prev->w + l2 * vk->w;
             if (status > 0) { I->adj_facet = prev->adj_facet; I->adj_seed = (int32_t)j; }
             else { I->adj_facet = -1; I->adj_seed = vk->adj_seed; }
+            /* symbolic mode (:305-314): on a failed symbolic intersection the previous vertex is copied into the result
+             * (the intersection point is then dropped with it); the edge fields set above are kept as the reference
+             * sets them after the copy */
+            if (orc_symbolic && !sym_intersect(I, prev, vk, j)) {
+                int32_t af = I->adj_facet, as = I->adj_seed;
+                *I = *prev;
+                I->adj_facet = af; I->adj_seed = as;
+            }
         }
         if (status > 0) {
             if (out->n >= ORC_MAXPOLY) return 1;
@@ -542,6 +580,19 @@ static void surfacic_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 pai
                 P[0].v[lv].w = R->weights ? R->weights[vid] : 1.0;
                 P[0].v[lv].adj_facet = R->adj[3 * cf + lv];
                 P[0].v[lv].adj_seed = -1;
+                P[0].v[lv].nsym = 0;
+            }
+            if (orc_symbolic) {
+                /* generic_RVD_polygon.cpp:69-100: corner i2 = {facet, facet across (i1,i2), facet across (i2,i2+1)};
+                 * border edges get the "virtual" facets nb_facets + corner */
+                for (int i1 = 0; i1 < 3; ++i1) {
+                    int i2 = (i1 + 1) % 3;
+                    orc_vertex* v2 = &P[0].v[i2];
+                    int32_t a1 = P[0].v[i1].adj_facet, a2 = v2->adj_facet;
+                    sym_insert(v2, -(int32_t)cf - 1);
+                    sym_insert(v2, -(a1 >= 0 ? a1 : (int32_t)(R->nt + i1)) - 1);
+                    sym_insert(v2, -(a2 >= 0 ? a2 : (int32_t)(R->nt + i2)) - 1);
+                }
             }
             seed_stamp[cs] = cf;
             sstack[0] = cs; ss_n = 1;
@@ -556,6 +607,26 @@ static void surfacic_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 pai
                     npairs++;
                 }
                 integrate_polygon(R, A, seed, Q);
+                if (orc_symbolic && orc_rdt_sink.tri) {
+                    /* PrimalTriangleAction (generic_RVD.h:575-619): a vertex on two bisectors = triangle (seed, bisector(0),
+                     * bisector(1)), bisector(0) being the LAST entry of the sorted set (generic_RVD_vertex.h:481-484) */
+                    for (int v = 0; v < Q->n; ++v) {
+                        const orc_vertex* ve = &Q->v[v];
+                        int nbis = 0;
+                        for (int q = 0; q < ve->nsym && q < 3; ++q) nbis += ve->sym[q] > 0;
+                        if (nbis == 2) {
+                            int top = (ve->nsym < 3 ? ve->nsym : 3) - 1;
+                            u32 iv2 = (u32)(ve->sym[top] - 1), iv3 = (u32)(ve->sym[top - 1] - 1);
+                            if (seed < iv2 && seed < iv3) {
+                                if (orc_rdt_sink.n < orc_rdt_sink.cap) {
+                                    u32* o = orc_rdt_sink.tri + 3 * orc_rdt_sink.n;
+                                    o[0] = seed; o[1] = iv2; o[2] = iv3;
+                                }
+                                orc_rdt_sink.n++;
+                            }
+                        }
+                    }
+                }
                 for (int v = 0; v < Q->n; ++v) {
                     int32_t nf = Q->v[v].adj_facet;
                     if (nf >= 0 && (u32)nf != cf && !facet_marked[nf]) {
@@ -1047,6 +1118,30 @@ int orc_surface_eval(int dim, u32 nv, const double* V, u32 nt, const u32* T, con
     if (counters) memcpy(counters, &R.cn, sizeof(orc_counters));
     rvd_free(&R, ksize);
     if (!flags) free(fl);
+    return 0;
+}
+
+/* RestrictedVoronoiDiagram::compute_RDT(simplices, embedding, RDTMode(0)) for surfaces — G/voronoi/RVD.cpp:2353-2370:
+ * for_each_primal_triangle(GetPrimalTriangles) over the symbolic polygons, check_SR = true as compute_surface sets it
+ * (CVT.cpp:194). tri_out: (seed, bisector(0), bisector(1)) rows in traversal order; *n_out may exceed cap. */
+int orc_rdt(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int32_t* adj, u32 S, const double* x,
+            u32 k, u32 kcap, u32* tri_out, u64 cap, u64* n_out) {
+    if (dim > ORC_MAXDIM || orc_volumetric_mode) return 1;
+    orc_rvd R;
+    uint8_t* fl = (uint8_t*)calloc(S ? S : 1, 1);
+    rvd_init(&R, dim, nv, V, nt, T, adj, NULL, S, x, k, kcap, NULL, 1, fl);
+    double* m = (double*)calloc(S ? S : 1, sizeof(double));
+    double* mg = (double*)calloc((size_t)(S ? S : 1) * dim, sizeof(double));
+    orc_accum A;
+    A.mode = 0; A.m = m; A.mg = mg; A.g = NULL; A.f_seed = NULL; A.f = 0.0;
+    orc_symbolic = 1;
+    orc_rdt_sink.tri = tri_out; orc_rdt_sink.cap = cap; orc_rdt_sink.n = 0;
+    surfacic_traversal(&R, &A, NULL, 0, NULL);
+    orc_symbolic = 0;
+    if (n_out) *n_out = orc_rdt_sink.n;
+    orc_rdt_sink.tri = NULL; orc_rdt_sink.cap = 0;
+    rvd_free(&R, NULL);
+    free(m); free(mg); free(fl);
     return 0;
 }
 

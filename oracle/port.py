@@ -140,6 +140,23 @@ def surface_eval(V, T, x, mode, check_SR, k=20, kcap=None, ksize=None, weights=N
     return r
 
 
+def rdt(V, T, x, k=20, kcap=256, adj=None):
+    """compute_RDT, simple mode (RVD.cpp:2353-2370), check_SR = true: (n, 3) rows (seed, bisector(0), bisector(1))."""
+    V, x = _f64(V), _f64(x)
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    if adj is None:
+        adj = _adjacency(T)
+    S, dim = x.shape
+    cap = 8 * S + 64
+    tri = np.zeros((cap, 3), dtype=np.uint32)
+    n = C.c_uint64(0)
+    rc = _lib().orc_rdt(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up), _p(adj, _ip),
+                        C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(min(kcap, max(S - 1, 1))), _p(tri, _up),
+                        C.c_uint64(cap), C.byref(n))
+    assert rc == 0 and n.value <= cap
+    return tri[:n.value].copy()
+
+
 def lloyd(V, T, x, nb_iter, k=20, locked=None, weights=None, adj=None):
     V = _f64(V)
     x = np.array(x, dtype=np.float64, order="C", copy=True)

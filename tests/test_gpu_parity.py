@@ -543,3 +543,19 @@ def test_anisotropic_6d_crease_facets_parity(built):
     assert_close(m, e0.m, what="mass")
     assert_close(mg, e0.mg, what="mass*centroid")
     h.close()
+
+
+def test_rdt_against_oracle_trefoil(built):
+    # larger than the golden cases, genus 1: the device RDT against the oracle's restatement (pinned to the reference by
+    # tests/test_oracle_cpu.py), on a raw sampling (enlarged neighbourhoods) and after Lloyd
+    V, F = shapes.trefoil_tube(300, 30)
+    X = shapes.sample_surface(V, F, 3000, 5)
+    h = handle_for(V, F)
+    for x in (X, h.lloyd(X, 5)):
+        h.set_seeds(x)
+        got = rows(h.rdt())
+        want = rows(port.rdt(V, F, x))
+        assert got.shape == want.shape and np.array_equal(got, want)
+    t = np.unique(np.sort(got, axis=1), axis=0)
+    assert t.shape[0] == 2 * 3000                       # torus: Euler characteristic 0
+    h.close()

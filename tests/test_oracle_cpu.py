@@ -180,3 +180,31 @@ def test_tet_adjacency_kuhn_cube():
         ok = adj[:, lf] >= 0
         back = adj[adj[ok, lf]]
         assert ((back == t[ok, None]).sum(1) == 1).all()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_rdt_matches_reference_golden(path):
+    # compute_RDT, simple mode, at the reference's own Lloyd result: same triangles in the same (traversal) order
+    G = load(path)
+    tri = port.rdt(G["V"], G["F"], G["x_lloyd"])
+    assert np.array_equal(tri, G["rdt_tri"])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_rdt_matches_live_reference():
+    # a raw random sampling (cells that need enlarged neighbourhoods) and a relaxed one, C1-like size
+    V, F = shapes.icosphere(20)
+    X = shapes.sample_surface(V, F, 2000, 11)
+    xl, _ = port.lloyd(V, F, X, 3)
+    for x in (X, xl):
+        r = ref.RefCVT(V, F, multithread=False)
+        try:
+            r.set_points(x)
+            r.update_delaunay()
+            tri, _ = r.rdt(0)
+        finally:
+            r.close()
+        assert np.array_equal(port.rdt(V, F, x), tri)
+    # closed genus-0 surface after Lloyd: 2 S - 4 distinct triangles
+    t = np.unique(np.sort(port.rdt(V, F, xl).astype(np.int64), axis=1), axis=0)
+    assert t.shape[0] == 2 * 2000 - 4
