@@ -359,7 +359,7 @@ def main():
                                 "share_of_step": cum["clip_kernel"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"]),
                                 "note": "FP64 geometry: the kernel is bound by FP64/issue rate, not HBM; see roofline_flops"}
             states = [X, x_final]
-            if args.small or not args.no_cpu_baseline:
+            if world == 1 and (args.small or not args.no_cpu_baseline):      # oracle event counts: N = 1 only
                 f_lloyd = algorithmic_flops_per_seed_iteration(V, F, states, False)
                 f_newton = algorithmic_flops_per_seed_iteration(V, F, [x_final], True)
             else:
@@ -379,8 +379,8 @@ def main():
             line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
         except Exception as ex_:   # the bench value stands even if the roofline leg fails
             line["roofline"] = {"error": str(ex_)}
-        # CPU baseline on the host cores, bounded sample of the same workload
-        if not args.no_cpu_baseline:
+        # CPU baseline on the host cores, bounded sample of the same workload: rank 0 at N = 1 only
+        if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref
                 if ref.available():
