@@ -138,3 +138,22 @@ def test_bench_reference_arm_contract():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    # include/b200cvt.h must be usable from C (the reference-side FFI is extern "C"): compile a C99 client that takes the
+    # address of every declared entry point with -Wall -Werror and link it against the library
+    header = open(capi.HEADER_PATH).read()
+    names = sorted(set(re.findall(r"\b(b200cvt_[a-z_0-9]+)\s*\(", header)) - {"b200cvt_progress_cb", "b200cvt_exchange_cb"})
+    src = tmp_path / "client.c"
+    src.write_text('#include "b200cvt.h"\n#include <stdio.h>\nint main(void) {\n    const void* f[] = {\n'
+                   + "".join("        (const void*)%s,\n" % n for n in names)
+                   + '    };\n    printf("%zu\\n", sizeof(f) / sizeof(f[0]));\n    return b200cvt_last_error() == 0;\n}\n')
+    exe = tmp_path / "client"
+    root = os.path.dirname(capi.HEADER_PATH)
+    libdir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", root, str(src), "-o", str(exe),
+                        "-L", libdir, "-lb200cvt", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and int(r.stdout.strip()) == len(names)

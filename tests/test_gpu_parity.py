@@ -263,7 +263,22 @@ def test_error_behaviour(built):
     with pytest.raises(capi.B200CVTError) as ei:
         h.set_mesh(V, bad)
     assert ei.value.code == 1
+    # a failed set_mesh leaves the handle without a mesh; RDT has the same preconditions as an evaluation
+    with pytest.raises(capi.B200CVTError) as ei:
+        h.rdt()
+    assert ei.value.code == 3
+    h.set_mesh(V, F)
+    tri = h.rdt()                                   # 100 random seeds on a coarse sphere: still a valid call
+    assert tri.shape[1] == 3 and (tri[:, 0] < tri[:, 2]).all() and (tri[:, 2] < tri[:, 1]).all()
     h.close()
+    hv = capi.Handle(3, volumetric=True)
+    Vt, T = shapes.kuhn_cube(3)
+    hv.set_mesh(Vt, T)
+    hv.set_seeds(X)
+    with pytest.raises(capi.B200CVTError) as ei:
+        hv.rdt()                                    # tetrahedral RDT stays on the reference implementation
+    assert ei.value.code == 1
+    hv.close()
 
 
 def test_full_size_properties_c2(built):
