@@ -160,30 +160,39 @@ __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u3
 // (facet filter); seeds within two cells get neighbour lists and bisector rows.
 // One thread per owned seed that is the first of its cell.
 __global__ void mark_cells_kernel(const u32* sorted_keys, u32 qbegin, u32 qend, GridParams g, uint8_t* cellflag) {
+    // A warp takes 32 consecutive owned seeds; every first seed of a grid cell (~1 in 9) has the cells within three cells
+    // of its own marked by the WHOLE warp, 11 of the 343 neighbours per lane (one thread per cell ran 3 lanes wide).
+    const int lane = threadIdx.x & 31;
     const u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= qend) return;
-    const u32 key = sorted_keys[s];
-    if (s > qbegin && sorted_keys[s - 1] == key) return;
-    // decode the Morton cell id
-    int c[3] = {0, 0, 0};
-    int in = 0;
-    for (int b = 0; b < 11; ++b)
-        for (int ax = 0; ax < 3; ++ax)
-            if (b < g.bits[ax]) { c[ax] |= (int)((key >> in) & 1u) << b; ++in; }
-    for (int dz = -3; dz <= 3; ++dz) {
-        const int cz = c[2] + dz; if (cz < 0 || cz >= g.res[2]) continue;
-        for (int dy = -3; dy <= 3; ++dy) {
-            const int cy = c[1] + dy; if (cy < 0 || cy >= g.res[1]) continue;
-            for (int dx = -3; dx <= 3; ++dx) {
-                const int cx = c[0] + dx; if (cx < 0 || cx >= g.res[0]) continue;
-                const int m = max(max(abs(dx), abs(dy)), abs(dz));
-                const u32 cid = morton_encode(g, cx, cy, cz);
-                // three byte planes (within one / two / three cells): every writer stores the same value 1, so
-                // concurrent writes are harmless
-                if (m <= 1) cellflag[cid] = 1;
-                if (m <= 2) cellflag[(size_t)g.ncells + cid] = 1;
-                cellflag[2 * (size_t)g.ncells + cid] = 1;
-            }
+    u32 key = 0;
+    bool first = false;
+    if (s < qend) {
+        key = sorted_keys[s];
+        first = (s == qbegin) || (sorted_keys[s - 1] != key);
+    }
+    u32 todo = __ballot_sync(B200_FULL, first);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 k = __shfl_sync(B200_FULL, key, src);
+        // decode the Morton cell id
+        int c[3] = {0, 0, 0};
+        int in = 0;
+        for (int b = 0; b < 11; ++b)
+            for (int ax = 0; ax < 3; ++ax)
+                if (b < g.bits[ax]) { c[ax] |= (int)((k >> in) & 1u) << b; ++in; }
+        for (int e = lane; e < 343; e += 32) {
+            const int dz = e / 49 - 3, dy = (e / 7) % 7 - 3, dx = e % 7 - 3;
+            const int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
+            if (cx < 0 || cx >= g.res[0] || cy < 0 || cy >= g.res[1] || cz < 0 || cz >= g.res[2]) continue;
+            const int m = max(max(abs(dx), abs(dy)), abs(dz));
+            const u32 cid = morton_encode(g, cx, cy, cz);
+            // three byte planes (within one / two / three cells): every writer stores the same value 1, so concurrent
+            // writes are harmless; a cell that already reads as marked is not written again
+            uint8_t* f1 = cellflag + cid; uint8_t* f2 = f1 + g.ncells; uint8_t* f3 = f2 + g.ncells;
+            if (m <= 1 && !*f1) *f1 = 1;
+            if (m <= 2 && !*f2) *f2 = 1;
+            if (!*f3) *f3 = 1;
         }
     }
 }

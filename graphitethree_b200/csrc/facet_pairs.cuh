@@ -464,8 +464,31 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
         }
         bool certified = false, empty0 = false;
         u32 mask0 = 0;
+        bool skip = false;
         for (int it = 0; relevant && it < 32; ++it) {
-            if (a.has_planes && !a.has_planes[s0]) break;
+            if (a.has_planes && !a.has_planes[s0]) {
+                // sharded run: s0 lies more than two grid cells away from every owned seed. A seed whose cell meets the
+                // facet is within 2 rho + delta of the centroid g (rho = facet radius about g, delta = |g - s0|), hence
+                // within 2 rho + 2 delta of s0: if that is at most two cells, no owned seed can meet this facet
+                double gc[D], rho2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double sc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) sc += v[i][c];
+                    gc[c] = sc * (1.0 / NC);
+                }
+#pragma unroll
+                for (int i = 0; i < NC; ++i) rho2 = fmax(rho2, dist2<D>(gc, v[i]));
+                const double delta = sqrt(dist2<D>(gc, xs[s0].p));
+                // (D > 3: the grid only sees the first three coordinates, the bound does not carry over: no skip)
+                if (D == 3 && (2.0 * sqrt(rho2) + 2.0 * delta) * (1.0 + 1e-9) <= 2.0 * a.g.h) {
+                    skip = true;
+                    a.facet_guess[f] = (u32)xs[s0].orig;      // a seed near the centroid: lets the facet filter drop this facet next time
+                    if (a.stats) atomicAdd(&a.stats[13], 1ull);
+                }
+                break;
+            }
             double p0[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) p0[c] = xs[s0].p[c];
@@ -478,7 +501,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             certified = (mask0 & PMASK_SR_OK) || (nn0 + 1 >= a.S);
             break;
         }
-        if (!relevant) {
+        if (!relevant || skip) {
             cand = 0;
         } else if (certified) {
             a.facet_guess[f] = (u32)xs[s0].orig;
