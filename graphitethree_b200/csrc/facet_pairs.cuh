@@ -662,27 +662,30 @@ facet_filter_kernel(FacetFilterArgs a) {
     const int lane = threadIdx.x & 31;
     bool rel = false;
     if (f < a.T) {
+        // the kernel is bound by load latency: everything that does not depend on a decision is requested up front
         const u32 cid = a.facet_cell[f];
         const float4 b = a.ball[f];
+        const u32 guess = a.facet_guess[f];
         const uint8_t* f1 = a.cellflag; const uint8_t* f2 = f1 + a.g.ncells; const uint8_t* f3 = f2 + a.g.ncells;
-        const double h = a.g.h;
+        const uint8_t l1 = f1[cid], l2 = f2[cid], l3 = f3[cid];
         const uint2 rg = a.cell_range[cid];
+        const u32 gpos = (guess != B200_NONE) ? a.rank_of[guess] : 0u;
+        const double h = a.g.h;
         // (D > 3: the grid only sees the first three coordinates and the float ball only stores those, so neither
         // bound on delta holds in the facet's own space: every facet stays relevant)
         if (D > 3) rel = true;
-        else if (!f3[cid] && (double)b.w <= 0.6 * h && rg.y > rg.x) rel = false;
+        else if (!l3 && (double)b.w <= 0.6 * h && rg.y > rg.x) rel = false;
         else {
-            const u32 guess = a.facet_guess[f];
             rel = true;
             if (guess != B200_NONE) {
                 const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
-                const SeedRec<D>* r = xs + a.rank_of[guess];
+                const SeedRec<D>* r = xs + gpos;
                 const double qx = r->p[0] - (double)b.x, qy = r->p[1] - (double)b.y, qz = r->p[2] - (double)b.z;
                 const double d2 = qx * qx + qy * qy + qz * qz;
                 const double R = (2.0 * (double)b.w + sqrt(d2)) * (1.0 + 1e-6);
-                if (R <= h) rel = f1[cid] != 0;
-                else if (R <= 2.0 * h) rel = f2[cid] != 0;
-                else if (R <= 3.0 * h) rel = f3[cid] != 0;
+                if (R <= h) rel = l1 != 0;
+                else if (R <= 2.0 * h) rel = l2 != 0;
+                else if (R <= 3.0 * h) rel = l3 != 0;
             }
         }
     }
