@@ -441,7 +441,9 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
 // them) in shared memory, so that the lanes of a warp run the same number of plane iterations; each thread then
 // clips CLIPW_ROUNDS pairs, one from each quarter of the sorted window (equal work per warp).
 #define CLIPW_THREADS 128
-#define CLIPW_ROUNDS 4
+#ifndef CLIPW_ROUNDS
+#define CLIPW_ROUNDS 4          // measured at C2: 4 rounds 0.429 ms, 6 rounds 0.423 ms, 8 rounds 0.461 ms (shared memory)
+#endif
 #define CLIPW_W (CLIPW_THREADS * CLIPW_ROUNDS)
 #define CLIPW_NW (CLIPW_THREADS / 32)
 #define CLIPW_NCNT (8 * CLIPW_ROUNDS * CLIPW_NW)
@@ -455,17 +457,17 @@ clip_win_kernel(ClipFlatArgs a) {
     double* P = s_dyn + (size_t)w * (CLIPF_MAXV * VW * 32) + lane;
     unsigned short* order = (unsigned short*)(s_dyn + (size_t)CLIPW_NW * CLIPF_MAXV * VW * 32);   // [CLIPW_W]
     u32* ccnt = (u32*)(order + CLIPW_W);                                                          // [class][round][warp]
-    static_assert(CLIPW_NCNT == 32 * 4, "the counter scan below takes 4 counters per lane of one warp");
-    static_assert(CLIPW_NCNT <= CLIPW_THREADS, "one thread clears one counter");
+    constexpr int CPL = CLIPW_NCNT / 32;      // counters per lane in the scan below
+    static_assert(CLIPW_NCNT % 32 == 0 && CLIPW_ROUNDS <= 8, "counter scan by one warp; class/rank packing");
     const u32 npairs = *a.npairs_dev;
     const u32 lt = (1u << lane) - 1u;
     ClipStats st;
     for (u32 base = blockIdx.x * CLIPW_W; base < npairs; base += gridDim.x * CLIPW_W) {
         const u32 cnt = min((u32)CLIPW_W, npairs - base);
-        if (tid < CLIPW_NCNT) ccnt[tid] = 0;
+        for (int i = tid; i < CLIPW_NCNT; i += CLIPW_THREADS) ccnt[i] = 0;
         __syncthreads();
         // class and rank inside (class, round, warp) of every pair of the window
-        u32 pcls = 0, prank = 0;
+        u32 pcls = 0; u64 prank = 0;
 #pragma unroll
         for (int r = 0; r < CLIPW_ROUNDS; ++r) {
             const u32 idx = r * CLIPW_THREADS + tid;
@@ -474,14 +476,14 @@ clip_win_kernel(ClipFlatArgs a) {
             const u32 m = __match_any_sync(B200_FULL, cls);
             const u32 rank = __popc(m & lt);
             if (cls < 8 && rank == 0) ccnt[(cls * CLIPW_ROUNDS + r) * CLIPW_NW + w] = __popc(m);
-            pcls |= cls << (4 * r); prank |= rank << (8 * r);
+            pcls |= cls << (4 * r); prank |= (u64)rank << (8 * r);
         }
         __syncthreads();
         if (w == 0) {
             // exclusive scan of the counters in (class, round, warp) order = stable counting sort
-            u32 v[4], sum = 0;
+            u32 v[CPL], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { v[i] = ccnt[lane * 4 + i]; sum += v[i]; }
+            for (int i = 0; i < CPL; ++i) { v[i] = ccnt[lane * CPL + i]; sum += v[i]; }
             u32 incl = sum;
 #pragma unroll
             for (int m = 1; m < 32; m <<= 1) {
@@ -490,12 +492,12 @@ clip_win_kernel(ClipFlatArgs a) {
             }
             u32 run = incl - sum;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ccnt[lane * 4 + i] = run; run += v[i]; }
+            for (int i = 0; i < CPL; ++i) { ccnt[lane * CPL + i] = run; run += v[i]; }
         }
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < CLIPW_ROUNDS; ++r) {
-            const u32 cls = (pcls >> (4 * r)) & 15u, rank = (prank >> (8 * r)) & 255u;
+            const u32 cls = (pcls >> (4 * r)) & 15u, rank = (u32)(prank >> (8 * r)) & 255u;
             if (cls < 8) order[ccnt[(cls * CLIPW_ROUNDS + r) * CLIPW_NW + w] + rank] = (unsigned short)(r * CLIPW_THREADS + tid);
         }
         __syncthreads();
