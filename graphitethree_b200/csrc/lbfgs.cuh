@@ -225,7 +225,12 @@ __device__ inline void mcsrch_dev(LbfgsScalars* sc, u32 n) {
 // ---------------------------------------------------------------------------------------
 // fused direction kernel
 // ---------------------------------------------------------------------------------------
+#ifndef LBFGS_DIR_THREADS
 #define LBFGS_DIR_THREADS 512
+#endif
+#ifndef LBFGS_DIR_BLOCKS_PER_SM
+#define LBFGS_DIR_BLOCKS_PER_SM 2
+#endif
 
 struct LbfgsDirArgs {
     u32 N;

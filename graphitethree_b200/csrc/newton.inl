@@ -50,7 +50,7 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         if (!coop) throw std::runtime_error("device does not support cooperative launches");
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_direction_kernel, LBFGS_DIR_THREADS, 0));
         if (per_sm < 1) throw std::runtime_error("lbfgs_direction_kernel does not fit on an SM");
-        h->lb_dir_blocks = (u32)h->num_sms * (u32)std::min(per_sm, 2);
+        h->lb_dir_blocks = (u32)h->num_sms * (u32)std::min(per_sm, LBFGS_DIR_BLOCKS_PER_SM);
     }
     h->lb_part.ensure(std::max<size_t>(6 * (size_t)h->lb_dir_blocks, 4 * (size_t)LBFGS_POST_BLOCKS)); h->lb_sc.ensure(1);
     CUDA_CHECK(cudaMemsetAsync(h->lb_sc.p, 0, sizeof(LbfgsScalars), h->stream));

@@ -18,7 +18,8 @@ c = h.cumulative(reset=True)
 n = c["evals"]
 print("%(name)s lloyd  " + " ".join("%%s=%%.3f" %% (k, c[k] / n) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")), "sum=%%.3f" %% ((c["sort"] + c["knn"] + c["pairs"] + c["clip"]) / n))
 import time
-t0 = time.time(); xn, info = h.newton(x, 10, 7); t1 = time.time()
+h.newton(x, 10, 7)                       # warm-up: allocations, cooperative-launch set-up
+t0 = time.time(); xn, info = h.newton(x, 20, 7); t1 = time.time()
 c = h.cumulative(reset=True); n = c["evals"]
 print("%(name)s newton " + " ".join("%%s=%%.3f" %% (k, c[k] / n) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")), "evals=%%d wall_ms_per_eval=%%.3f" %% (n, (t1 - t0) * 1e3 / n))
 h.close()
