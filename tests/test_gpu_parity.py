@@ -574,3 +574,52 @@ def test_rdt_against_oracle_trefoil(built):
     t = np.unique(np.sort(got, axis=1), axis=0)
     assert t.shape[0] == 2 * 3000                       # torus: Euler characteristic 0
     h.close()
+
+
+def test_sharded_volumetric_two_partitions_one_gpu(built):
+    """Volumetric mode through the partition + exchange path: two handles on one GPU stand in for two ranks."""
+    import torch
+    V, T = shapes.kuhn_cube(12)
+    X = 0.02 + 0.96 * np.random.default_rng(9).random((1001, 3))
+    S, dim, world = X.shape[0], 3, 2
+    chunk = sharding.chunk_doubles(dim, S, world)
+    shared = torch.zeros(chunk * world, dtype=torch.float64, device="cuda")
+    barrier = threading.Barrier(world)
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            h = volume_handle(V, T)
+            h.set_partition(rank, world)
+            sl = torch.zeros(chunk, dtype=torch.float64, device="cuda")
+            al = torch.zeros(chunk * world, dtype=torch.float64, device="cuda")
+
+            def exchange():
+                shared[rank * chunk:(rank + 1) * chunk].copy_(sl)
+                torch.cuda.synchronize()
+                barrier.wait()
+                al.copy_(shared)
+                torch.cuda.synchronize()
+                barrier.wait()
+                return 0
+            h.set_exchange(sl.data_ptr(), al.data_ptr(), chunk, exchange)
+            xd = torch.from_numpy(X).cuda()
+            h.set_seeds_device(xd.data_ptr(), S)
+            h.lloyd_device(3)
+            info = h.newton_device(2, 7)
+            results[rank] = (h.get_seeds(), info)
+            h.close()
+        except Exception as ex:   # pragma: no cover
+            errors.append(ex)
+            barrier.abort()
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    h = volume_handle(V, T)
+    x1 = h.lloyd(X, 3)
+    x1, info = h.newton(x1, 2, 7)
+    h.close()
+    assert np.array_equal(results[0][0], results[1][0])          # both ranks hold the same seeds
+    assert np.abs(results[0][0] - x1).max() <= 1e-12             # and the unsharded run's
+    assert results[0][1] == info
