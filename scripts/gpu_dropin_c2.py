@@ -1,5 +1,5 @@
 """The drop-in checker (integration/_build/dropin_check: stock CentroidalVoronoiTesselation vs the B200 adapter classes through
-the reference's own C++ API) at C2 size: 2 M triangles, 200 k seeds, 10 Lloyd + 30 Newton. Prints the checker's JSON line."""
+the reference's own C++ API) at C2 size: 2 M triangles, 200 k seeds, 10 Lloyd + 30 Newton, from the sampling after two stock Lloyd iterations (no truncated cell is left there: the oracle flags 194 seeds after one iteration, none after two). Prints the checker's JSON line."""
 import os, sys, subprocess, tempfile, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,5 +15,5 @@ with open(mp, "wb") as f:
 with open(sp, "wb") as f:
     f.write(np.array([X.shape[0], X.shape[1]], dtype=np.uint32).tobytes()); f.write(np.ascontiguousarray(X, dtype=np.float64).tobytes())
 exe = os.path.join(ROOT, "integration", "_build", "dropin_check")
-out = subprocess.run([exe, mp, sp, "10", "30", "7", "1", "0"], capture_output=True, text=True, timeout=1500)
+out = subprocess.run([exe, mp, sp, "10", "30", "7", "2", "0"], capture_output=True, text=True, timeout=1500)
 print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-2000:])
