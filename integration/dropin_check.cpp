@@ -20,6 +20,7 @@
 #include <geogram/basic/stopwatch.h>
 #include <geogram/mesh/mesh_distance.h>
 #include <geogram/mesh/mesh_geometry.h>
+#include <geogram/mesh/mesh_repair.h>
 
 #include <algorithm>
 #include <array>
@@ -239,9 +240,33 @@ int main(int argc, char** argv) {
         }
     }
     double diag = (ref.surface.vertices.nb() > 0) ? bbox_diagonal(ref.surface) : 0.0;
-    double h_ab = 0.0, h_ba = 0.0;
+    double h_ab = 0.0, h_ba = 0.0, h_ctrl = 0.0;
     if(ref.surface.facets.nb() > 0 && b200.surface.facets.nb() > 0) {
         double sampling = 0.01 * diag;
+        /* control: the REFERENCE's own triangles in lexicographic order instead of traversal order, through the same
+         * post-process as compute_surface (CVT.cpp:218-229: assign_triangle_mesh + mesh_repair). A non-zero distance to the
+         * reference's surface shows how much of h_ab / h_ba is the order sensitivity of that post-process. */
+        {
+            std::vector<Tri> sorted;
+            for(index_t f = 0; f + 2 < ref.rdt.size(); f += 3) {
+                sorted.push_back(Tri{{ref.rdt[f], ref.rdt[f + 1], ref.rdt[f + 2]}});
+            }
+            std::sort(sorted.begin(), sorted.end());
+            vector<index_t> tris;
+            for(const Tri& t : sorted) {
+                tris.push_back(t[0]); tris.push_back(t[1]); tris.push_back(t[2]);
+            }
+            vector<double> v3(size_t(S) * 3);
+            for(index_t i = 0; i < S; ++i) {
+                for(index_t c = 0; c < 3; ++c) {
+                    v3[index_t(i * 3 + c)] = ref.x_final[size_t(i) * dim + c];
+                }
+            }
+            Mesh ctrl;
+            ctrl.facets.assign_triangle_mesh(3, v3, tris, true);
+            mesh_repair(ctrl, MESH_REPAIR_DEFAULT, 1e-6 * bbox_diagonal(ctrl));
+            h_ctrl = mesh_one_sided_Hausdorff_distance(ref.surface, ctrl, sampling);
+        }
         h_ab = mesh_one_sided_Hausdorff_distance(ref.surface, b200.surface, sampling);
         h_ba = mesh_one_sided_Hausdorff_distance(b200.surface, ref.surface, sampling);
     }
@@ -250,14 +275,14 @@ int main(int argc, char** argv) {
         "\"max_abs_dx_lloyd\": %.3e, \"max_abs_dx_final\": %.3e, "
         "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
         "\"ref_vertices\": %u, \"b200_vertices\": %u, "
-        "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"bbox_diagonal\": %.6e, "
+        "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"hausdorff_ref_to_ref_sorted\": %.3e, \"bbox_diagonal\": %.6e, "
         "\"nn_rows\": %u, \"nn_mismatch\": %u, "
         "\"t_ref_lloyd\": %.4f, \"t_ref_newton\": %.4f, \"t_b200_lloyd\": %.4f, \"t_b200_newton\": %.4f, \"ref_threads\": %u}\n",
         g_volumetric ? "true" : "false", S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
         max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
         ta.size(), tb.size(), only_ref, only_b200,
         ref.surface.vertices.nb(), b200.surface.vertices.nb(),
-        h_ab, h_ba, diag, nn_rows, nn_mismatch,
+        h_ab, h_ba, h_ctrl, diag, nn_rows, nn_mismatch,
         ref.t_lloyd, ref.t_newton, b200.t_lloyd, b200.t_newton, unsigned(Process::maximum_concurrent_threads())
     );
     return 0;
