@@ -372,10 +372,18 @@ def main():
                                       "frac_fp32": tf / fp32, "frac_fp64": tf / fp64, "achieved_whole_clip_phase": tf_phase,
                                       "peak_source": "FMA microbenchmark on this GPU (b200cvt_measure_peaks), non-tensor",
                                       "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton}}
-            knn_bytes = S * (dim * 8 + 20 * 4 + 4) * n_eval          # read seed, write k indices + count (every rank: all seeds)
+            # kNN kernel: read seed, write k indices + count, plus the bisector rows it now writes with the lists
+            # (k rows of 6 doubles and 4 floats) — every rank: the seeds of its range and halo
+            knn_bytes = S * (dim * 8 + 20 * 4 + 4 + 20 * (6 * 8 + 4 * 4 if dim == 3 else 8 * 8 + 8 * 4)) * n_eval
             knn_gbs = knn_bytes / (cum["knn"] * 1e-3 / args.steps) / 1e9
+            knn_traffic = None
+            try:
+                knn_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("knn_kernel")
+            except Exception:
+                pass
             line["roofline_knn"] = {"bound": "hbm", "achieved": knn_gbs, "peak": hbm, "unit": "GB/s", "frac": knn_gbs / hbm,
-                                    "peak_source": peak_src, "copy_gbs_here": copy, "traffic": None}
+                                    "peak_source": peak_src, "copy_gbs_here": copy, "traffic": knn_traffic,
+                                    "note": "issue-bound (64-bit key compare-exchanges), not HBM; time = the kNN phase of bench.py's timers"}
             line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
         except Exception as ex_:   # the bench value stands even if the roofline leg fails
             line["roofline"] = {"error": str(ex_)}
