@@ -353,6 +353,9 @@ static void sync_stream(b200cvt_ctx* h) {
 // ---------------------------------------------------------------------------------------
 // grid construction
 // ---------------------------------------------------------------------------------------
+#ifndef FACET_TASK_BLOCKS_PER_SM
+#define FACET_TASK_BLOCKS_PER_SM 8u
+#endif
 #ifndef GRID_CELL_SURF
 #define GRID_CELL_SURF 3.0
 #endif
@@ -550,7 +553,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
                 CUDA_CHECK(cudaFuncSetAttribute(facet_big_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
                 LAUNCH(h, facet_big_kernel<D>, (u32)h->num_sms * 4u, BIG_WARPS * 32, smem_big, a);
             }
-            LAUNCH(h, (facet_task_kernel<D, NC>), (u32)h->num_sms * 8u, 128, 0, a);
+            LAUNCH(h, (facet_task_kernel<D, NC>), (u32)h->num_sms * FACET_TASK_BLOCKS_PER_SM, 128, 0, a);
         }
         // flat offsets of the owned seeds (pair_cnt[qend] is 0: only owned seeds receive pairs)
         size_t tb = h->cub_tmp.cap;
