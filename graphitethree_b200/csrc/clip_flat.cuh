@@ -448,8 +448,11 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
 #define CLIPW_NW (CLIPW_THREADS / 32)
 #define CLIPW_NCNT (8 * CLIPW_ROUNDS * CLIPW_NW)
 
+#ifndef CLIPW_MINBLK
+#define CLIPW_MINBLK 6
+#endif
 template <int D, bool WEIGHTED>
-__global__ void __launch_bounds__(CLIPW_THREADS, (D == 3 && !WEIGHTED) ? 6 : 1)
+__global__ void __launch_bounds__(CLIPW_THREADS, (D == 3 && !WEIGHTED) ? CLIPW_MINBLK : 1)
 clip_win_kernel(ClipFlatArgs a) {
     constexpr int VW = D + (WEIGHTED ? 1 : 0);
     extern __shared__ double s_dyn[];
