@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 static thread_local std::string g_last_error;
@@ -215,6 +216,10 @@ __global__ void fill_u32_kernel(u32* p, size_t n, u32 v) {
 // ---------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
     T* p = nullptr; size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }          // every member buffer of the handle is released by `delete h`
     void ensure(size_t n) {
         if (n <= cap) return;
         if (p) cudaFree(p);
@@ -866,7 +871,9 @@ static void upload_locked(b200cvt_ctx* h, const uint8_t* locked, u32 S) {
         h->locked.ensure(S);
         CUDA_CHECK(cudaMemcpyAsync(h->locked.p, locked, S, cudaMemcpyHostToDevice, h->stream));
     } else if (h->locked.p) {
-        CUDA_CHECK(cudaMemsetAsync(h->locked.p, 0, std::min<size_t>(h->locked.cap, S), h->stream));
+        // a handle reused with more seeds: the kernels read locked[o] for every o < S
+        h->locked.ensure(S);
+        CUDA_CHECK(cudaMemsetAsync(h->locked.p, 0, h->locked.cap, h->stream));
     }
 }
 
@@ -897,6 +904,7 @@ static void pack_slice(b200cvt_ctx* h, const double* out_s, const double* out_v)
 // Lloyd_iterations (geogram/voronoi/CVT.cpp:133-167) on the device-resident seeds
 static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void* user) {
     const u32 S = h->S;
+    if (nb_iter > 0) h->rdt_valid = false;      // the seeds move: a cached triangulation is stale
     for (u32 it = 0; it < nb_iter; ++it) {
         evaluate(h, 0, 0);
         u32 n = h->slice_len();
@@ -1151,12 +1159,12 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
         if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
         if (device >= ndev) throw ArgError("device ordinal out of range");
         CUDA_CHECK(cudaSetDevice(device));
-        b200cvt_ctx* h = new b200cvt_ctx;
+        std::unique_ptr<b200cvt_ctx> h(new b200cvt_ctx);
         h->device = device; h->dim = dim; h->volumetric = volumetric;
         CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
-        *out = h;
+        *out = h.release();
     });
 }
 
@@ -1164,21 +1172,10 @@ void b200cvt_destroy(b200cvt_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->tri.release(); h->triw.release(); h->tet_inner.release(); h->facet_guess.release(); h->x.release();
-    h->keys.release(); h->vals.release(); h->keys2.release(); h->vals2.release(); h->cub_tmp.release();
-    h->xs.release(); h->rank_of.release(); h->cell_range.release(); h->nbr.release(); h->nbr_n.release();
-    h->sqd.release(); h->flags.release(); h->redo_a.release(); h->redo_b.release(); h->redo_n.release();
-    h->nbr_big.release(); h->nbr_big_n.release(); h->pair_cnt.release(); h->pair_facet.release(); h->max_cnt.release();
-    h->out_s.release(); h->out_v.release(); h->s_orig.release(); h->v_orig.release(); h->flags_orig.release();
-    h->locked.release(); h->cnt_orig.release(); h->stats.release();
-    h->pair_off.release(); h->flat_seed.release(); h->flat_facet.release(); h->slow_list.release(); h->contrib.release(); h->pstat.release(); h->facet_area.release();
-    h->planes.release(); h->planes32.release(); h->flat_mask.release(); h->pair_mask.release(); h->tasks.release(); h->mtab.release(); h->nbr_prev.release(); h->cellflag.release(); h->has_planes.release(); h->need_list.release(); h->need_n.release(); h->facet_ball.release(); h->facet_cell.release(); h->facet_list.release(); h->facet_list_n.release(); h->iota.release(); h->sort_tmp.release();
-    h->lb_g.release(); h->lb_q.release(); h->lb_px.release(); h->lb_pg.release(); h->lb_wa.release();
-    h->lb_s.release(); h->lb_y.release(); h->lb_part.release(); h->lb_sc.release();
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
-    delete h;
+    delete h;                         // DevBuf members release their device memory
 }
 
 int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint32_t stride, const uint32_t* elems,
@@ -1487,7 +1484,7 @@ int b200cvt_set_partition(b200cvt_handle h, uint32_t rank, uint32_t nranks) {
         if (!h) throw ArgError("null handle");
         if (nranks == 0 || rank >= nranks) throw ArgError("bad partition");
         h->rank = rank; h->nranks = nranks;
-        h->knn_valid = false; h->has_results = false;
+        h->knn_valid = false; h->has_results = false; h->rdt_valid = false;
     });
 }
 
