@@ -15,7 +15,10 @@ metric = seed-iterations/s = S * (Lloyd iterations + Newton function evaluations
   N > 1 : one process per GPU (torchrun), seeds sharded by Morton range, mesh replicated, one NCCL
           all-gather per evaluation through torch.distributed (scaling "weak")
   --impl reference : the unmodified reference (oracle/_ref, built from /root/reference by
-          oracle/Makefile.ref) on the host cores, a bounded sample of the same job per step
+          oracle/Makefile.ref) on the host cores, THE SAME JOB per step (10 Lloyd + Newton_iterations(30, 7) from the
+          same initial seeds); the number of steps actually run is bounded by a time budget and stated in the line
+  "c3"  : second timed leg, BASELINE.json configs[2] as stated: trefoil tube, 20 M triangles, 5 M seeds, Lloyd
+          iterations, seeds sharded by Morton range over the N GPUs (strong scaling), Lloyd iterations/s
 """
 import argparse
 import json
@@ -60,6 +63,16 @@ def workload(n_gpus, small=False):
 def workload_name(n_gpus, T, S):
     return ("noise-displaced sphere %d triangles, %d seeds, %d Lloyd + %d Newton (HLBFGS m=%d) iterations per step"
             % (T, S, LLOYD_ITERS, NEWTON_ITERS, NEWTON_M))
+
+
+def workload_config(T, S):
+    """The workload, identical in both arms (the arm-specific facts go under "run")."""
+    return {"workload": workload_name(0, T, S), "seeds": int(S), "triangles": int(T), "lloyd_iterations": LLOYD_ITERS,
+            "newton_iterations": NEWTON_ITERS, "newton_m": NEWTON_M,
+            "l2": "inputs larger than L2 (facet table %d MB, seeds re-sorted every evaluation)" % (T * 72 // 2 ** 20)}
+
+
+REF_BUDGET_S = 150.0     # wall-clock budget of the timed steps of the reference arm
 
 
 class ClockSampler:
@@ -125,7 +138,7 @@ def algorithmic_flops_per_seed_iteration(V, F, states, func_grad):
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation on the host cores (all threads), bounded sample per step."""
+    """The reference's own CPU implementation on the host cores (all threads): the same job as the B200 arm per step."""
     if rank != 0:
         return
     from oracle import ref
@@ -133,9 +146,7 @@ def run_reference(args, rank, world):
     S = X.shape[0]
     line = {"impl": "reference", "metric": "CVT seed-iterations/sec", "unit": "seed-iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.gpus, F.shape[0], S), "l2": "inputs larger than L2"}}
-    sample_lloyd, sample_newton = 2, 2
+            "dtype": "f64", "data": "synthetic", "config": workload_config(F.shape[0], S)}
     if ref.available():
         kind = "reference"
         r = ref.RefCVT(V, F, multithread=True)
@@ -144,30 +155,94 @@ def run_reference(args, rank, world):
         def step():
             r.set_points(X)
             c0 = r.counters()["funcgrad"]
-            t = r.lloyd(sample_lloyd) + r.newton(sample_newton, NEWTON_M)
-            return t, sample_lloyd + (r.counters()["funcgrad"] - c0)
+            t = r.lloyd(LLOYD_ITERS) + r.newton(NEWTON_ITERS, NEWTON_M)
+            return t, LLOYD_ITERS + (r.counters()["funcgrad"] - c0)
     else:
         from oracle import port
         kind, cores = "port", 1
 
         def step():
             t0 = time.time()
-            x, _ = port.lloyd(V, F, X, sample_lloyd)
-            x, info = port.newton(V, F, x, sample_newton, NEWTON_M)
-            return time.time() - t0, sample_lloyd + info["nfev"]
-    for _ in range(args.warmup):
-        step()
-    tt, ev = 0.0, 0
-    for _ in range(args.steps):
+            x, _ = port.lloyd(V, F, X, LLOYD_ITERS)
+            x, info = port.newton(V, F, x, NEWTON_ITERS, NEWTON_M)
+            return time.time() - t0, LLOYD_ITERS + info["nfev"]
+    # one untimed job at most (thread pool, Hilbert partition of the mesh); a CPU has no clocks to warm
+    n_warm = min(args.warmup, 1)
+    t_first = 0.0
+    for _ in range(n_warm):
+        t_first, _ = step()
+    tt, ev, done = 0.0, 0, 0
+    while done < args.steps:
         t, e = step()
-        tt += t; ev += e
+        tt += t; ev += e; done += 1
+        if tt + t > REF_BUDGET_S:        # the next step would overrun the budget
+            break
     value = S * ev / tt
-    sample = "%d Lloyd + Newton_iterations(%d) per step (%d evaluations/step) on the full %d-seed / %d-triangle input" % (
-        sample_lloyd, sample_newton, ev // max(args.steps, 1), S, F.shape[0])
-    line.update({"value": value, "ms_per_step": 1e3 * tt / max(args.steps, 1),
+    sample = ("the full job (%d Lloyd + Newton_iterations(%d, m=%d) = %d evaluations) on the full %d-seed / %d-triangle input; "
+              "%d of the %d requested steps run inside a %.0f s budget, %d untimed warm-up job(s)" % (
+                  LLOYD_ITERS, NEWTON_ITERS, NEWTON_M, ev // max(done, 1), S, F.shape[0], done, args.steps, REF_BUDGET_S, n_warm))
+    line.update({"value": value, "ms_per_step": 1e3 * tt / max(done, 1), "steps_timed": done,
+                 "run": {"evaluations_per_step": ev // max(done, 1), "parallelism": "%d host threads" % cores, "wall_s": tt},
                  "cpu_baseline": {"value": value, "unit": "seed-iterations/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "seed-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     emit(line)
+
+
+def c3_leg(args, rank, local_rank, world, torch, dist, capi, sharding):
+    """BASELINE.json configs[2] as stated: procedural trefoil-knot tube, 20 M triangles, 5 M seeds, Lloyd iterations, seeds
+    sharded by Morton range over the N GPUs (STRONG scaling: total size fixed). Device time, max over ranks."""
+    from graphitethree_b200 import shapes
+    small = args.small
+    V, F = shapes.trefoil_tube(1000 if small else 10000, 100 if small else 1000)
+    S = 50000 if small else 5000000
+    X = shapes.sample_surface(V, F, S, 1)
+    stream = torch.cuda.Stream()
+    h = capi.Handle(3, device=local_rank)
+    h.set_stream(stream.cuda_stream)
+    t0 = time.time()
+    h.set_mesh(V, F)
+    t_mesh = time.time() - t0
+    h.set_partition(rank, world)
+    ex = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            ex = sharding.TorchExchange(3, S, rank, world, torch.device("cuda", local_rank), sync=False)
+
+            def exchange():
+                with torch.cuda.stream(stream):
+                    return ex()
+        h.set_exchange(ex.slice.data_ptr(), ex.all.data_ptr(), ex.chunk, exchange)
+    xd = torch.from_numpy(X).cuda()
+    warm, iters = 4, 20
+    with torch.cuda.stream(stream):
+        h.set_seeds_device(xd.data_ptr(), S)
+        h.lloyd_device(warm)                   # relaxation + warm-up (buffers, neighbour-list coherence)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    h.cumulative(reset=True)
+    l0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        h.lloyd_device(iters)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    c = h.cumulative()
+    launches = h.launch_count() - l0
+    x = h.get_seeds()
+    t = float(ms.item()) * 1e-3
+    out = {"workload": "trefoil-knot tube %d triangles, %d seeds, Lloyd iterations, Morton-range x%d (strong scaling)" % (F.shape[0], S, world),
+           "n_gpus": world, "triangles": int(F.shape[0]), "seeds": S, "lloyd_iterations_timed": iters, "warmup_iterations": warm,
+           "ms_per_iteration": 1e3 * t / iters, "lloyd_iterations_per_s": iters / t, "seed_iterations_per_s": S * iters / t,
+           "target_lloyd_iterations_per_s_at_8_gpus": 50.0, "set_mesh_s": round(t_mesh, 2), "gpu_launches": int(launches),
+           "rank0_phase_ms_per_iteration": {k: round(c[k] / max(c["evals"], 1), 3) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")},
+           "seeds_finite": bool(np.isfinite(x).all()), "scaling": "strong"}
+    h.close()
+    return out
 
 
 def main():
@@ -178,6 +253,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the second timed leg (C3: 20 M triangles / 5 M seeds, Lloyd)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -235,12 +311,6 @@ def main():
         info = h.newton_device(NEWTON_ITERS, NEWTON_M)
         evals["n"] = LLOYD_ITERS + info["nfev"]
         evals["newton"] = info
-
-    def step_e2e():
-        x_pin_np[...] = X
-        h.lloyd(x_pin_np, 0)          # no-op placeholder keeps the call sequence explicit
-        xl = lib_lloyd(x_pin_np)
-        lib_newton(xl)
 
     # host-pointer calls on the pinned buffer, in place (what a geogram adapter does with points_.data())
     import ctypes as C
@@ -321,16 +391,21 @@ def main():
         e2e = {"value": S * evals["n"] * args.steps / float(te.item()), "unit": "seed-iterations/s",
                "h2d_bytes_per_step": S * dim * 8, "d2h_bytes_per_step": S * dim * 8}
 
+    c3 = None
+    if not args.no_c3:
+        try:
+            c3 = c3_leg(args, rank, local_rank, world, torch, dist, capi, sharding)
+        except Exception as ex_:      # the headline line stands even if the second leg fails
+            c3 = {"error": str(ex_)}
     if rank == 0:
         own = (S + world - 1) // world
         line = {"metric": "CVT seed-iterations/sec", "value": value, "unit": "seed-iterations/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.gpus, F.shape[0], S), "seeds": S, "triangles": int(F.shape[0]),
-                           "evaluations_per_step": n_eval, "newton": evals["newton"], "parallelism": "morton-range x%d" % world,
-                           "l2": "inputs larger than L2 (facet table %d MB, re-sorted seeds every evaluation)" % (F.shape[0] * 72 // 2 ** 20),
-                           "wall_s": wall},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+                "config": workload_config(F.shape[0], S),
+                "run": {"evaluations_per_step": n_eval, "newton": evals["newton"], "parallelism": "morton-range x%d" % world,
+                        "wall_s": wall},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "c3": c3}
         # roofline of the dominant kernel (clip_win_kernel), SURVEY.md §8(d). Durations are CUDA events recorded by the
         # library on its stream around that kernel alone, accumulated over the timed region.
         try:
@@ -347,14 +422,15 @@ def main():
             bytes_unit = 8 * dim + 4 * 20 + (T / S) * (24 + 24 * dim) + 8 * (dim + 1)
             n_launch = max(cum["evals"], 1)
             clip_ms = cum["clip_kernel"] / n_launch
-            traffic = None
+            traffic, traffic_src = None, None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clip_win_kernel")
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic, traffic_src = tj.get("clip_win_kernel"), tj.get("_note")
             except Exception:
                 pass
             ach = bytes_unit * own / (clip_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                                "kernel": "clip_win_kernel", "peak_source": peak_src, "kernel_ms_per_launch": clip_ms,
+                                "traffic_source": traffic_src, "kernel": "clip_win_kernel", "peak_source": peak_src, "kernel_ms_per_launch": clip_ms,
                                 "algorithmic_bytes_per_seed_iteration": bytes_unit, "units_per_launch": own,
                                 "share_of_step": cum["clip_kernel"] / (cum["sort"] + cum["knn"] + cum["pairs"] + cum["clip"]),
                                 "note": "FP64 geometry: the kernel is bound by FP64/issue rate, not HBM; see roofline_flops"}
@@ -374,7 +450,9 @@ def main():
                                       "algorithmic_flops_per_seed_iteration": {"lloyd": f_lloyd, "func_grad": f_newton}}
             # kNN kernel: read seed, write k indices + count, plus the bisector rows it now writes with the lists
             # (k rows of 6 doubles and 4 floats) — every rank: the seeds of its range and halo
-            knn_bytes = S * (dim * 8 + 20 * 4 + 4 + 20 * (6 * 8 + 4 * 4 if dim == 3 else 8 * 8 + 8 * 4)) * n_eval
+            # units = the kNN queries one launch serves: all seeds at N = 1, the owned range + its two-cell halo at N > 1
+            knn_queries = S if world == 1 else (h.stats().get("knn_queries") or own)
+            knn_bytes = knn_queries * (dim * 8 + 20 * 4 + 4 + 20 * (6 * 8 + 4 * 4 if dim == 3 else 8 * 8 + 8 * 4)) * n_eval
             knn_gbs = knn_bytes / (cum["knn"] * 1e-3 / args.steps) / 1e9
             knn_traffic = None
             try:
@@ -383,6 +461,7 @@ def main():
                 pass
             line["roofline_knn"] = {"bound": "hbm", "achieved": knn_gbs, "peak": hbm, "unit": "GB/s", "frac": knn_gbs / hbm,
                                     "peak_source": peak_src, "copy_gbs_here": copy, "traffic": knn_traffic,
+                                    "units_per_launch": int(knn_queries),
                                     "note": "issue-bound (64-bit key compare-exchanges), not HBM; time = the kNN phase of bench.py's timers"}
             line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
         except Exception as ex_:   # the bench value stands even if the roofline leg fails

@@ -185,7 +185,8 @@ class Handle:
         d = dict(planes=int(st[0]), cuts=int(st[1]), triangles=int(st[2]), nonempty_pairs=int(st[3]),
                  redo_seeds=int(st[4]), candidate_pairs=int(st[5]), pair_cap=int(st[6]), grid_cells=int(st[7]))
         d["clip_planes"] = int(st[8])
-        d["subdivision"] = dict(pieces=int(st[9]), pieces_uncertified=int(st[10]), hops=int(st[11]), seeds_collected=int(st[12]))
+        d["knn_queries"] = int(st[11])                            # seeds served by the last kNN launch (owned + halo when sharded)
+        d["subdivision"] = dict(pieces=int(st[9]), pieces_uncertified=int(st[10]), seeds_collected=int(st[12]))
         d["facets_skipped_far_from_owned_seeds"] = int(st[13])    # sharded runs
         d["facets_uncertified"] = int(st[14])                     # home list ended inside the distance bound
         d["facets_subdivided"] = int(st[15] & 0xffffffff)         # ... of which covered by small pieces

@@ -248,7 +248,7 @@ struct b200cvt_ctx {
     DevBuf<int> facet_adj; bool facet_adj_valid = false;
     DevBuf<u32> rdt_dev, rdt_n;
     std::vector<u32> rdt_host; bool rdt_valid = false;
-    double bb_lo[3], bb_hi[3], mesh_measure = 0.0;
+    double bb_lo[3], bb_hi[3], mesh_measure = 0.0, mesh_vmax2 = 0.0;
     // seeds
     u32 S = 0;
     bool has_seeds = false, grid_valid = false;
@@ -760,10 +760,12 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         fa.flat_seed = h->flat_seed.p; fa.flat_facet = h->flat_facet.p; fa.npairs_dev = h->pair_off.p + nown;
         fa.mode = mode; fa.contrib = h->contrib.p; fa.cstride = cstride; fa.pstat = h->pstat.p;
         fa.flat_mask = h->flat_mask.p;
+        fa.planes32 = h->planes32.p; fa.vmax2 = h->mesh_vmax2;
+
         fa.stats = h->want_stats ? h->stats.p : nullptr;
         const int VW = D + (h->weighted ? 1 : 0);
-        const size_t smem = (size_t)CLIPW_NW * CLIPF_MAXV * VW * 32 * sizeof(double) + CLIPW_W * sizeof(unsigned short) +
-                            CLIPW_NCNT * sizeof(u32);
+        const size_t smem = (size_t)CLIPW_NW * CLIPF_CAP * 32 * (VW * sizeof(double) + CLIPF_QW(D) * sizeof(float4)) +
+                            CLIPW_W * sizeof(unsigned short) + CLIPW_NCNT * sizeof(u32);
         // windows of the seed-major pair list, a few per resident block
         const u32 per_sm = std::max<u32>(1, std::min<u32>(8, (u32)((227 * 1024) / (smem + 1024))));
         const u32 blocks = std::min<u32>(div_up(np, CLIPW_W), (u32)h->num_sms * per_sm);
@@ -1302,6 +1304,17 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             else if (D == 3) LAUNCH(h, (facet_ball_kernel<3, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
             else LAUNCH(h, (facet_ball_kernel<6, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
         }
+        h->mesh_vmax2 = 0.0;
+        if (ne > 0) {
+            DevBuf<unsigned long long> d_mx;
+            d_mx.ensure(1);
+            CUDA_CHECK(cudaMemsetAsync(d_mx.p, 0, sizeof(unsigned long long), h->stream));
+            LAUNCH(h, soup_vmax2_kernel, 1024, 256, 0, h->tri.p, (size_t)ne * per, D, d_mx.p);
+            unsigned long long bits = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&bits, d_mx.p, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            memcpy(&h->mesh_vmax2, &bits, sizeof(double));
+        }
         h->facet_area.ensure(ne);
         if (ne > 0 && !h->volumetric) {
             if (D == 3) LAUNCH(h, facet_area_kernel<3>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
@@ -1457,7 +1470,7 @@ int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out) {
 
 // stats: [0] planes tested [1] planes that cut [2] integration triangles [3] non-empty pairs
 //        [4] seeds re-clipped with an enlarged neighbourhood [5] candidate pairs [6] pair row capacity [7] grid cells
-//        [8..13] clip state machine: (rounds, lanes served) of the advance / cut / integrate phases  [14..15] reserved
+//        [8] bisectors tested by the clip kernel  [9..10], [13..15] facet walk (facet_pairs.cuh)  [11] kNN queries of the last evaluation
 int b200cvt_get_stats(b200cvt_handle h, uint64_t* out) {
     return guarded([&] {
         if (!h || !out) throw ArgError("null argument");
@@ -1475,6 +1488,10 @@ int b200cvt_get_stats(b200cvt_handle h, uint64_t* out) {
             for (u32 v : c) total += v;
         }
         out[5] = total; out[6] = h->pair_cap; out[7] = h->g.ncells;
+        // [11] seeds served by the kNN launch of the last evaluation (sharded runs: owned range + two-cell halo)
+        u32 nq = h->S;
+        if (h->nranks > 1 && h->need_n.p && h->knn_valid) CUDA_CHECK(cudaMemcpy(&nq, h->need_n.p, sizeof(u32), cudaMemcpyDeviceToHost));
+        out[11] = nq;
         h->want_stats = true;   // counters are collected from the next evaluation on
     });
 }

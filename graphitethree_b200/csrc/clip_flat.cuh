@@ -23,14 +23,13 @@
 //   reduce_pairs_kernel   : one warp per seed sums its pairs' contributions in facet order with a fixed tree —
 //                           deterministic, independent of the partition and of atomics order.
 //
-// Pairs the fast path cannot finish (more than CLIPF_MAXV vertices, more than two crossings of one
+// Pairs the fast path cannot finish (more than CLIPF_CAP vertices, more than two crossings of one
 // plane = numerically non-convex) are marked PSTAT_SLOW; their seeds are re-evaluated by the
 // warp-per-seed kernel of clip.cuh (local-memory ping-pong buffers).
 #pragma once
 #include "common.cuh"
 #include "clip.cuh"
 
-#define CLIPF_MAXV 11
 
 #define PSTAT_EXHAUSTED 1u
 #define PSTAT_SLOW 16u
@@ -90,6 +89,17 @@ compact_pairs_kernel(CompactArgs a) {
     }
 }
 
+// Correctly rounded x / N for the constants of the integration formulas (3, 6, 12, 30): q = RN(x y), y = RN(1/N),
+// r = x - N q (exact, one FMA), result RN(q + r y) — Markstein's correction step; bit-equal to the IEEE division the
+// reference executes (checked against x / N on 4e8 operands incl. boundary mantissas), 3 instructions instead of ~45.
+template <int N>
+__device__ __forceinline__ double div_exact(double x) {
+    const double y = 1.0 / (double)N;
+    const double q = x * y;
+    const double r = __fma_rn(-(double)N, q, x);
+    return __fma_rn(r, y, q);
+}
+
 // ---------------------------------------------------------------------------------------
 // integration of one fan triangle (p1, p2, p3) of seed pi, given its area:
 // ComputeCentroids / ComputeCVTFuncGrad (+Weighted) — RVD.cpp:280-296, 322-369, 575-604, 640-724
@@ -100,7 +110,7 @@ __device__ __forceinline__ void integrate_triangle(const double* p1, const doubl
     constexpr int VW = D + (WEIGHTED ? 1 : 0);
     if (mode == 0) {
         if (!WEIGHTED) {
-            const double sc = area / 3.0;
+            const double sc = div_exact<3>(area);
             acc_s += area;
 #pragma unroll
             for (int c = 0; c < D; ++c) acc_v[c] += sc * (p1[c] + p2[c] + p3[c]);
@@ -108,9 +118,9 @@ __device__ __forceinline__ void integrate_triangle(const double* p1, const doubl
             // Geom::triangle_centroid (geometry_nd.h:178-199)
             const double wa = p1[VW - 1], wb = p2[VW - 1], wc = p3[VW - 1];
             const double abc = wa + wb + wc;
-            acc_s += area / 3.0 * abc;
+            acc_s += div_exact<3>(area) * abc;
             const double wp = wa + abc, wq = wb + abc, wr = wc + abc;
-            const double sc = area / 12.0;
+            const double sc = div_exact<12>(area);
 #pragma unroll
             for (int c = 0; c < D; ++c) acc_v[c] += sc * (wp * p1[c] + wq * p2[c] + wr * p3[c]);
         }
@@ -126,7 +136,7 @@ __device__ __forceinline__ void integrate_triangle(const double* p1, const doubl
                 cur_f += u1 * (u0 + u1);
                 cur_f += u2 * (u0 + u1 + u2);
             }
-            acc_s += area * cur_f / 6.0;
+            acc_s += div_exact<6>(area * cur_f);
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 const double Gc = (1.0 / 3.0) * (p1[c] + p2[c] + p3[c]);
@@ -150,10 +160,10 @@ __device__ __forceinline__ void integrate_triangle(const double* p1, const doubl
             cur_f += (al2 + rho0) * d20;
             cur_f += (al2 + rho1) * d21;
             cur_f += (al2 + rho2) * d22;
-            acc_s += area * cur_f / 30.0;
+            acc_s += div_exact<30>(area * cur_f);
 #pragma unroll
             for (int c = 0; c < D; ++c)
-                acc_v[c] += (area / 6.0) * (4.0 * Sp * pi[c] - (al0 * p1[c] + al1 * p2[c] + al2 * p3[c]));
+                acc_v[c] += div_exact<6>(area) * (4.0 * Sp * pi[c] - (al0 * p1[c] + al1 * p2[c] + al2 * p3[c]));
         }
     }
 }
@@ -235,6 +245,8 @@ struct ClipFlatArgs {
     const void* xs;
     const u32* nbr; const u32* nbr_n; u32 kstride;
     const double* planes;       // [S][kstride][PLANE_STRIDE] bisector table
+    const float* planes32;      // [S][kstride][4 | 8] FP32 filter copy (n, |n|^2), facet_pairs.cuh
+    double vmax2;               // max |v|^2 over the mesh corners (bound of the reference's FP64 rounding)
     const double* tri;          // [T][3][D]
     const double* triw;         // [T][3] or NULL
     const double* facet_area;   // [T]
@@ -253,69 +265,205 @@ struct ClipFlatArgs {
 // ---------------------------------------------------------------------------------------
 struct ClipStats { unsigned long long planes = 0, cuts = 0, tri = 0, ne = 0; };
 
-// one candidate pair t: clip facet f by the masked bisectors of seed s and integrate. P = this thread's polygon
-// (lane-interleaved shared memory, stride 32 doubles between consecutive values)
-template <int D, bool WEIGHTED>
-__device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t, double* P, ClipStats& st) {
+// ---- packed-permutation helpers (4 bits per entry, 8 entries) ----
+__device__ __forceinline__ u32 nibmask(int L) { return L >= 8 ? 0xffffffffu : ((1u << (4 * L)) - 1u); }
+__device__ __forceinline__ u32 shr4(u32 x, int m) { return m >= 8 ? 0u : (x >> (4 * m)); }
+__device__ __forceinline__ u32 shl4(u32 x, int m) { return m >= 8 ? 0u : (x << (4 * m)); }
+// entries of `perm` at the set positions of `bits`, in index order. The set must be at most two runs, one of them
+// starting at position 0 (a cyclic interval of [0, n) or its complement); *ok is cleared otherwise.
+__device__ __forceinline__ u32 perm_compress(u32 perm, u32 bits, bool* ok) {
+    const int t = __ffs(~bits) - 1;                 // trailing ones
+    const u32 low = perm & nibmask(t);
+    const u32 rest = bits >> t;                      // bit 0 is clear
+    if (rest == 0) return low;
+    const int a = __ffs(rest) - 1;
+    const u32 run = rest >> a;
+    if (run & (run + 1u)) *ok = false;               // not one contiguous run
+    const int L = __popc(rest);
+    const u32 high = shr4(perm, t + a) & nibmask(L);
+    return low | shl4(high, t);
+}
+__device__ __forceinline__ u32 perm_insert(u32 K, int m, u32 v) {
+    return (K & nibmask(m)) | shl4(v, m) | shl4(shr4(K, m), m + 1);
+}
+
+// The polygon of one pair lives in CLIPF_CAP vertex slots of shared memory, lane-interleaved (lanes that index
+// different slots never conflict):
+//   P : FP64 coordinates (+ weight)            [slot][coord][lane]
+//   Q : FP32 shadow q = v - p_seed, w = |q|^2   [slot][lane] float4 (two float4 for D = 6)
+// Vertices never move. The cyclic order of the polygon is a packed permutation (4 bits per logical vertex -> slot) in a
+// register, entry 0 = the reference's vertex 0 (the fan apex of the integration); a cut only writes the (at most two)
+// new vertices into free slots and rebuilds the permutation in the reference's emission order
+// (generic_RVD_polygon.h:299-362).
+//
+// Side tests (the reference's sgn(2 v.n - d), generic_RVD_polygon.h:276-297) and the radius test
+// (generic_RVD.h:2155-2174) are decided by an FP32 filter on seed-local coordinates: 2 v.n - d = 2 q.n + |n|^2 with
+// n = p_i - p_j (see facet_pairs.cuh: same filter table). A value beyond the margin has the sign of the reference's own
+// FP64 evaluation (margin = FP32 evaluation error + the reference's FP64 rounding on global coordinates, both bounded
+// above); anything inside the margin is re-evaluated with the reference's FP64 expression. Intersections, areas and
+// integrals are FP64 and follow the reference operation by operation, so the polygons stay bit-identical.
+// Measured at C2 (profiles/r2_clip_variants.md): the kernel is latency-bound, its time follows the number of resident warps
+// (4 blocks 0.55 ms, 5 blocks 0.38 ms, 6 blocks 0.35 ms). 8 slots + 96 registers = 5 blocks per SM without spills; 7 slots
+// + 80 registers = 6 blocks is 7 % faster but needs a second pass for the 8-vertex polygons that eats the gain; 6 slots +
+// 72 registers = 7 blocks spills (0.40 ms). Polygons with more vertices than slots take the warp-per-seed path (clip.cuh).
+#ifndef CLIPF_CAP
+#define CLIPF_CAP 8
+#endif
+#define CLIPF_QW(D) ((D) == 3 ? 1 : 2)
+
+template <int D, bool WEIGHTED, int CAP>
+__device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t, const u32 s, const u32 f, const u32 mask_in,
+                                              double* P, float4* Q, ClipStats& st) {
     constexpr int VW = D + (WEIGHTED ? 1 : 0);
     constexpr int PS = PLANE_STRIDE(D);
+    constexpr int PS32 = (D == 3) ? 4 : 8;
+    constexpr int QW = CLIPF_QW(D);
 #define PV(k, c) P[((k) * VW + (c)) * 32]
+#define QV(k, h) Q[((k) * QW + (h)) * 32]
+#define SLOT(k) ((perm >> (4 * (k))) & 7u)
     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
-    const u32 s = a.flat_seed[t];
-    const u32 f = a.flat_facet[t];
-    const u32 mask_in = a.flat_mask[t];
     u32 mask = mask_in & 0x7fffffffu;
     double pi[D];
+    double pi2 = 0.0;
 #pragma unroll
-    for (int c = 0; c < D; ++c) pi[c] = xs[s].p[c];
+    for (int c = 0; c < D; ++c) { pi[c] = xs[s].p[c]; pi2 += pi[c] * pi[c]; }
     const u32 nn = min(min(a.nbr_n[s], a.kstride), 32u);
     const double* prow = a.planes + (size_t)s * a.kstride * PS;
+    const float* prow32 = a.planes32 + (size_t)s * a.kstride * PS32;
+    // the reference's FP64 rounding on global coordinates (facet_pairs.cuh: 4e-15 (|v|^2 + |p_i|^2)), v anywhere on the mesh
+    const float mextra = __double2float_ru(4e-15 * (a.vmax2 + pi2));
+    // bisector rows of a masked neighbour (-DCLIP_ROWPIPE requests them one iteration ahead: measured slower, the 16 extra
+    // registers cost more than the hidden latency gains)
+    float4 nrow32[PS32 / 4];
+    double2 nrow64[PS / 2];
+    auto request_rows = [&](int jj) {
+        const float4* r4 = (const float4*)(prow32 + (size_t)jj * PS32);
+#pragma unroll
+        for (int q = 0; q < PS32 / 4; ++q) nrow32[q] = __ldg(r4 + q);
+        const double2* r2 = (const double2*)(prow + (size_t)jj * PS);
+#pragma unroll
+        for (int q = 0; q < PS / 2; ++q) nrow64[q] = __ldg(r2 + q);
+    };
+#ifdef CLIP_ROWPIPE
+    if (mask) request_rows(__ffs(mask) - 1);
+#endif
     int n = 3;
-    double R2 = 0.0;
+    u32 perm = 0x76543210u & nibmask(CAP);   // entries [0, n): the polygon in cyclic order; entries [n, 8): the free slots
+    // FP32 radius^2 of the current polygon about the seed: exact (to FP32) while r2_valid, else R2lo <= radius^2 <= R2f
+    float R2f = 0.0f, R2lo = 0.0f;
+    bool r2_valid = true;
     {
         const double* tp = a.tri + (size_t)f * 3 * D;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            double v[D];
+            float qf[D];
+            float w = 0.0f;
 #pragma unroll
-            for (int c = 0; c < D; ++c) { v[c] = tp[i * D + c]; PV(i, c) = v[c]; }
+            for (int c = 0; c < D; ++c) {
+                const double v = tp[i * D + c];
+                PV(i, c) = v;
+                qf[c] = (float)(v - pi[c]);
+                w = fmaf(qf[c], qf[c], w);
+            }
             if (WEIGHTED) PV(i, D) = a.triw[(size_t)f * 3 + i];
-            R2 = fmax(R2, dist2<D>(pi, v));
+            if (D == 3) QV(i, 0) = make_float4(qf[0], qf[1], qf[2], w);
+            else { QV(i, 0) = make_float4(qf[0], qf[1], qf[2], qf[3]); QV(i, 1) = make_float4(qf[D - 2], qf[D - 1], w, 0.0f); }
+            R2f = fmaxf(R2f, w);
         }
     }
+    // exact radius^2 of the current polygon: max_k |p_i - P_k|^2 as the reference evaluates it
+    auto exact_R2 = [&]() {
+        double R2 = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const u32 sl = SLOT(k);
+            double v[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[c] = PV(sl, c);
+            R2 = fmax(R2, dist2<D>(pi, v));
+        }
+        return R2;
+    };
+    // radius test dij > 4.1 R2 (generic_RVD.h:2170): FP32 filter, exact when the two sides are within 1e-5 of each other
+    auto radius_test = [&](float dijf, u32 jj, float r2hi, float r2lo) {
+        if (r2lo > 1e-30f && dijf < 1e30f) {
+            if (dijf > 4.1f * r2hi * 1.00001f) return true;
+            if (dijf < 4.1f * r2lo * 0.99999f) return false;
+        }
+        return prow[(size_t)jj * PS + D + 1] > 4.1 * exact_R2();
+    };
     // no masked bisector: the cell contains the facet. The classification (FP32, conservative) may have certified the radius
-    // test on the unclipped facet; if it did not, the test is redone exactly below with the last neighbour
+    // test on the unclipped facet; if it did not, the test is redone below with the last neighbour
     bool sr_ok = (mask == 0) && (mask_in & 0x80000000u), slow = false, cut_any = false;
     int last_jj = -1;
     // clip_by_cell_SR (generic_RVD.h:2155-2177) over the masked bisectors, increasing distance
     while (mask) {
         const int jj = __ffs(mask) - 1;
         mask &= mask - 1;
-        double2 rowbuf[PS / 2];
+        float nf[D], dijf;
+        double nj[D], d;
+#ifndef CLIP_ROWPIPE
+        request_rows(jj);
+#endif
         {
-            const double2* r2 = (const double2*)(prow + (size_t)jj * PS);
+            const float4 r0 = nrow32[0];
+            if (D == 3) { nf[0] = r0.x; nf[1] = r0.y; nf[2] = r0.z; dijf = r0.w; }
+            else {
+                const float4 r1 = nrow32[PS32 / 4 - 1];
+                nf[0] = r0.x; nf[1] = r0.y; nf[2] = r0.z; nf[3] = r0.w; nf[D - 2] = r1.x; nf[D - 1] = r1.y; dijf = r1.z;
+            }
+            const double* pl = (const double*)nrow64;
 #pragma unroll
-            for (int q = 0; q < PS / 2; ++q) rowbuf[q] = __ldg(r2 + q);
+            for (int c = 0; c < D; ++c) nj[c] = pl[c];
+            d = pl[D];
         }
-        const double* pl = (const double*)rowbuf;
-        if (pl[D + 1] > 4.1 * R2) { sr_ok = true; break; }
+#ifdef CLIP_ROWPIPE
+        if (mask) request_rows(__ffs(mask) - 1);
+#endif
+        // one pass over the vertices: FP32 side value against its margin, and the radius of the polygon
+        u32 pos = 0, neg = 0;
+        float r2f = 0.0f;
+        u32 pp = perm, bit = 1u;
+#ifndef CLIP_SIDE_UNROLL
+#pragma unroll 1
+#endif
+        for (int k = 0; k < n; ++k, pp >>= 4, bit <<= 1) {
+            const u32 sl = pp & 7u;
+            float qf[D], w;
+            const float4 q0 = QV(sl, 0);
+            if (D == 3) { qf[0] = q0.x; qf[1] = q0.y; qf[2] = q0.z; w = q0.w; }
+            else {
+                const float4 q1 = QV(sl, 1);
+                qf[0] = q0.x; qf[1] = q0.y; qf[2] = q0.z; qf[3] = q0.w; qf[D - 2] = q1.x; qf[D - 1] = q1.y; w = q1.z;
+            }
+            float l = 0.0f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) l = fmaf(qf[c], nf[c], l);
+            const float tk = fmaf(2.0f, l, dijf);
+            const float margin = fmaf(2e-6f, w + dijf, mextra);
+            r2f = fmaxf(r2f, w);
+            if (tk > margin) pos |= bit;
+            if (tk < -margin) neg |= bit;
+        }
+        R2f = r2f; r2_valid = true;
+        if (radius_test(dijf, (u32)jj, r2f, r2f)) { sr_ok = true; break; }
         last_jj = jj;
         ++st.planes;
-        double nj[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) nj[c] = pl[c];
-        const double d = pl[D];
-        // pass 1: side of every vertex (generic_RVD_polygon.h:276-297)
-        u32 pos = 0, neg = 0;
-        for (int k = 0; k < n; ++k) {
-            double l = 0.0;
-#pragma unroll
-            for (int c = 0; c < D; ++c) l += PV(k, c) * nj[c];
-            const double tk = 2.0 * l - d;
-            pos |= (tk > 0.0 ? 1u : 0u) << k;
-            neg |= (tk < 0.0 ? 1u : 0u) << k;
-        }
         const u32 full = (1u << n) - 1u;
+        u32 unc = ~(pos | neg) & full;
+        if (unc) {
+            // inside the margin: the reference's own expression (generic_RVD_polygon.h:276-297)
+            while (unc) {
+                const int k = __ffs(unc) - 1;
+                unc &= unc - 1;
+                const u32 sl = SLOT(k);
+                double l = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) l += PV(sl, c) * nj[c];
+                const double tk = 2.0 * l - d;
+                pos |= (tk > 0.0 ? 1u : 0u) << k;
+                neg |= (tk < 0.0 ? 1u : 0u) << k;
+            }
+        }
         if (pos == full) continue;                 // nothing to cut
         ++st.cuts;
         cut_any = true;
@@ -325,9 +473,10 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
         const u32 pneg = ((neg << 1) | (neg >> (n - 1))) & full;
         const u32 X = (ppos | pneg) & ((pos ^ ppos) | (neg ^ pneg));
         const int nx = __popc(X);
-        if (nx > 2 || __popc(pos) + nx > CLIPF_MAXV) { slow = true; break; }
+        if (nx > 2 || __popc(pos) + nx > CAP) { slow = true; break; }
         double I[2][VW];
         int kx0 = -1, kx1 = -1;
+        float r2_new = 0.0f;
         {
             u32 xr = X;
 #pragma unroll
@@ -339,9 +488,10 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
                     xr &= xr - 1;
                     if (q == 0) kx0 = k; else kx1 = k;
                     const int kp = (k == 0) ? n - 1 : k - 1;
+                    const u32 sp = SLOT(kp), sc = SLOT(k);
                     double vp[VW], vc[VW];
 #pragma unroll
-                    for (int c = 0; c < VW; ++c) { vp[c] = PV(kp, c); vc[c] = PV(k, c); }
+                    for (int c = 0; c < VW; ++c) { vp[c] = PV(sp, c); vc[c] = PV(sc, c); }
                     double lp = 0.0, l = 0.0;
 #pragma unroll
                     for (int c = 0; c < D; ++c) { lp += vp[c] * nj[c]; l += vc[c] * nj[c]; }
@@ -354,37 +504,42 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
                 }
             }
         }
-        int m = 0;
-        double R2n = 0.0;
-        double vc[VW], vn[VW];
+        // new cyclic order = the reference's emission order: (crossing on edge k-1 -> k), then (vertex k if kept).
+        // The kept vertices of a convex polygon are a cyclic interval: at most two runs of the packed permutation.
+        bool runs_ok = true;
+        const int kc = __popc(pos);
+        u32 K = perm_compress(perm, pos, &runs_ok);                       // kept slots, index order
+        const u32 Dr = perm_compress(perm, ~pos & full, &runs_ok);         // dropped slots
+        if (!runs_ok) { slow = true; break; }
+        const u32 pool = Dr | shl4(shr4(perm, n), n - kc);                // dropped slots, then the old free slots
+        const int m0 = __popc(pos & ((1u << (kx0 < 0 ? 0 : kx0)) - 1u));
+        const int m1 = __popc(pos & ((1u << (kx1 < 0 ? 0 : kx1)) - 1u)) + 1;
+        if (kx0 >= 0) K = perm_insert(K, m0, pool & 7u);
+        if (kx1 >= 0) K = perm_insert(K, m1, (pool >> 4) & 7u);
+        const int m = kc + nx;
+        const u32 np = K | shl4(shr4(pool, nx), m);
 #pragma unroll
-        for (int c = 0; c < VW; ++c) { vc[c] = PV(0, c); vn[c] = 0.0; }
-        for (int k = 0; k < n; ++k) {
-            if (k + 1 < n) {
+        for (int q = 0; q < 2; ++q) {
+            if ((q == 0 ? kx0 : kx1) >= 0) {
+                const u32 sl = (q == 0 ? pool : (pool >> 4)) & 7u;
+                float qf[D];
+                float w = 0.0f;
 #pragma unroll
-                for (int c = 0; c < VW; ++c) vn[c] = PV(k + 1, c);
-            }
-            if (k == kx0 || k == kx1) {
-                // m <= k + 1: at most one crossing precedes without a dropped vertex
-                double Iq[VW];
-#pragma unroll
-                for (int c = 0; c < VW; ++c) { Iq[c] = (k == kx0) ? I[0][c] : I[1][c]; PV(m, c) = Iq[c]; }
-                R2n = fmax(R2n, dist2<D>(pi, Iq));
-                ++m;
-            }
-            if ((pos >> k) & 1u) {
-                if (m != k) {
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) PV(m, c) = vc[c];
+                for (int c = 0; c < D; ++c) {
+                    PV(sl, c) = I[q][c];
+                    qf[c] = (float)(I[q][c] - pi[c]);
+                    w = fmaf(qf[c], qf[c], w);
                 }
-                R2n = fmax(R2n, dist2<D>(pi, vc));
-                ++m;
+                if (WEIGHTED) PV(sl, D) = I[q][D];
+                if (D == 3) QV(sl, 0) = make_float4(qf[0], qf[1], qf[2], w);
+                else { QV(sl, 0) = make_float4(qf[0], qf[1], qf[2], qf[3]); QV(sl, 1) = make_float4(qf[D - 2], qf[D - 1], w, 0.0f); }
+                r2_new = fmaxf(r2_new, w);
             }
-#pragma unroll
-            for (int c = 0; c < VW; ++c) vc[c] = vn[c];
         }
+        perm = np;
         n = m;
-        R2 = R2n;
+        // radius of the new polygon: between the new vertices (it contains them) and the old radius (it shrank)
+        R2lo = r2_new; r2_valid = false;
         if (n == 0) break;
     }
 
@@ -397,7 +552,10 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
         if (!sr_ok && n > 0 && nn > 0) {
             // the reference goes on testing the remaining neighbours (unmasked: they cannot cut);
             // the list is sorted, so the radius test passes for one of them iff it passes for the last
-            if (last_jj < (int)nn - 1) sr_ok = prow[(size_t)(nn - 1) * PS + D + 1] > 4.1 * R2;
+            if (last_jj < (int)nn - 1) {
+                const float dl = __ldg(prow32 + (size_t)(nn - 1) * PS32 + D);
+                sr_ok = radius_test(dl, nn - 1, R2f, r2_valid ? R2f : R2lo);
+            }
             // list used up before the radius test passed (generic_RVD.h:2179-2181)
             if (!sr_ok) ps = PSTAT_EXHAUSTED;
         }
@@ -412,12 +570,16 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
             } else {
                 // TriangleAction fan (generic_RVD.h:452-463)
                 double p1[VW], p2[VW], p3[VW];
+                {
+                    const u32 s0 = SLOT(0), s1 = SLOT(1);
 #pragma unroll
-                for (int c = 0; c < VW; ++c) { p1[c] = PV(0, c); p3[c] = PV(1, c); }
+                    for (int c = 0; c < VW; ++c) { p1[c] = PV(s0, c); p3[c] = PV(s1, c); }
+                }
                 double ea = sqrt(dist2<D>(p1, p3));
                 for (int i = 1; i + 1 < n; ++i) {
+                    const u32 sl = SLOT(i + 1);
 #pragma unroll
-                    for (int c = 0; c < VW; ++c) { p2[c] = p3[c]; p3[c] = PV(i + 1, c); }
+                    for (int c = 0; c < VW; ++c) { p2[c] = p3[c]; p3[c] = PV(sl, c); }
                     ++st.tri;
                     const double eb = sqrt(dist2<D>(p2, p3));
                     const double ec = sqrt(dist2<D>(p3, p1));
@@ -433,6 +595,8 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
     for (int c = 0; c < D; ++c) a.contrib[(size_t)(c + 1) * a.cstride + t] = acc_v[c];
     a.pstat[t] = ps;
 #undef PV
+#undef QV
+#undef SLOT
 }
 
 // Pairs are taken in windows of CLIPW_W consecutive entries of the seed-major pair list (= a few dozen
@@ -440,7 +604,9 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
 // window stay in L1/L2). Inside a window the pairs are counting-sorted by class (number of bisectors that may cut
 // them) in shared memory, so that the lanes of a warp run the same number of plane iterations; each thread then
 // clips CLIPW_ROUNDS pairs, one from each quarter of the sorted window (equal work per warp).
+#ifndef CLIPW_THREADS
 #define CLIPW_THREADS 128
+#endif
 #ifndef CLIPW_ROUNDS
 #define CLIPW_ROUNDS 4          // measured at C2: 4 rounds 0.429 ms, 6 rounds 0.423 ms, 8 rounds 0.461 ms (shared memory)
 #endif
@@ -449,7 +615,7 @@ __device__ __forceinline__ void clip_one_pair(const ClipFlatArgs& a, const u32 t
 #define CLIPW_NCNT (8 * CLIPW_ROUNDS * CLIPW_NW)
 
 #ifndef CLIPW_MINBLK
-#define CLIPW_MINBLK 6
+#define CLIPW_MINBLK 5
 #endif
 template <int D, bool WEIGHTED>
 __global__ void __launch_bounds__(CLIPW_THREADS, (D == 3 && !WEIGHTED) ? CLIPW_MINBLK : 1)
@@ -457,8 +623,11 @@ clip_win_kernel(ClipFlatArgs a) {
     constexpr int VW = D + (WEIGHTED ? 1 : 0);
     extern __shared__ double s_dyn[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    double* P = s_dyn + (size_t)w * (CLIPF_MAXV * VW * 32) + lane;
-    unsigned short* order = (unsigned short*)(s_dyn + (size_t)CLIPW_NW * CLIPF_MAXV * VW * 32);   // [CLIPW_W]
+    constexpr int QW = CLIPF_QW(D);
+    double* P = s_dyn + (size_t)w * (CLIPF_CAP * VW * 32) + lane;
+    float4* Q = (float4*)(s_dyn + (size_t)CLIPW_NW * CLIPF_CAP * VW * 32) + (size_t)w * (CLIPF_CAP * QW * 32) + lane;
+    unsigned short* order = (unsigned short*)((float4*)(s_dyn + (size_t)CLIPW_NW * CLIPF_CAP * VW * 32) +
+                                              (size_t)CLIPW_NW * CLIPF_CAP * QW * 32);                  // [CLIPW_W]
     u32* ccnt = (u32*)(order + CLIPW_W);                                                          // [class][round][warp]
     constexpr int CPL = CLIPW_NCNT / 32;      // counters per lane in the scan below
     static_assert(CLIPW_NCNT % 32 == 0 && CLIPW_ROUNDS <= 8, "counter scan by one warp; class/rank packing");
@@ -504,9 +673,21 @@ clip_win_kernel(ClipFlatArgs a) {
             if (cls < 8) order[ccnt[(cls * CLIPW_ROUNDS + r) * CLIPW_NW + w] + rank] = (unsigned short)(r * CLIPW_THREADS + tid);
         }
         __syncthreads();
+        // Round r serves the r-th quarter of the sorted window; the warps rotate through the four 32-pair groups of a
+        // quarter (warp w takes group (w + r) mod 4), so that every warp gets the same mix of cheap and expensive
+        // groups and the barrier at the end of the window finds them together. The (pair, seed, facet, mask) record of
+        // the next round is requested while the current pair is clipped.
+        auto sorted_pos = [&](int r) { return (u32)(r * CLIPW_THREADS + (((w + r) & (CLIPW_NW - 1)) << 5) + lane); };
+        u32 tn = 0, sn = 0, fn = 0, mn = 0;
+        bool vn = sorted_pos(0) < cnt;
+        if (vn) { tn = base + order[sorted_pos(0)]; sn = a.flat_seed[tn]; fn = a.flat_facet[tn]; mn = a.flat_mask[tn]; }
+#pragma unroll 1
         for (int r = 0; r < CLIPW_ROUNDS; ++r) {
-            const u32 p = r * CLIPW_THREADS + tid;
-            if (p < cnt) clip_one_pair<D, WEIGHTED>(a, base + order[p], P, st);
+            const u32 t = tn, sd = sn, ft = fn, mk = mn;
+            const bool v = vn;
+            vn = (r + 1 < CLIPW_ROUNDS) && sorted_pos(r + 1) < cnt;
+            if (vn) { tn = base + order[sorted_pos(r + 1)]; sn = a.flat_seed[tn]; fn = a.flat_facet[tn]; mn = a.flat_mask[tn]; }
+            if (v) clip_one_pair<D, WEIGHTED, CLIPF_CAP>(a, t, sd, ft, mk, P, Q, st);
         }
         __syncthreads();
     }

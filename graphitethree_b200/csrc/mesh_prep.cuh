@@ -117,3 +117,17 @@ __global__ void mesh_soup_kernel(const double* vert, u32 stride, const u32* elem
         if (soup_w && lv < 3) soup_w[(size_t)i * 3 + lv] = weights[v];
     }
 }
+
+// max |v|^2 over the corners of the soup (all D coordinates): bounds the reference's FP64 rounding on global
+// coordinates in the FP32 side-test filter of the clip kernel (clip_flat.cuh). Positive doubles order like their bits.
+__global__ void soup_vmax2_kernel(const double* soup, size_t ncorners, int D, unsigned long long* out) {
+    double mx = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncorners; i += (size_t)gridDim.x * blockDim.x) {
+        double q = 0.0;
+        for (int c = 0; c < D; ++c) { const double v = soup[i * D + c]; q += v * v; }
+        mx = fmax(mx, q);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(B200_FULL, mx, m));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
