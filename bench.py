@@ -188,6 +188,17 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def comm_setup(h, rank, world, torch, dist, capi):
+    """N > 1: the handle becomes one rank of an in-library communicator (NCCL all-gather / reduce-scatter + peer
+    mailboxes). The 128-byte id is created by rank 0 and broadcast over the torch.distributed process group."""
+    if world == 1:
+        return
+    cid = capi.comm_unique_id() if rank == 0 else np.zeros(capi.COMM_ID_BYTES, dtype=np.uint8)
+    t = torch.from_numpy(cid).cuda()
+    dist.broadcast(t, 0)
+    h.comm_init(t.cpu().numpy(), rank, world)
+
+
 def c3_leg(args, rank, local_rank, world, torch, dist, capi, sharding):
     """BASELINE.json configs[2] as stated: procedural trefoil-knot tube, 20 M triangles, 5 M seeds, Lloyd iterations, seeds
     sharded by Morton range over the N GPUs (STRONG scaling: total size fixed). Device time, max over ranks."""
@@ -202,16 +213,7 @@ def c3_leg(args, rank, local_rank, world, torch, dist, capi, sharding):
     t0 = time.time()
     h.set_mesh(V, F)
     t_mesh = time.time() - t0
-    h.set_partition(rank, world)
-    ex = None
-    if world > 1:
-        with torch.cuda.stream(stream):
-            ex = sharding.TorchExchange(3, S, rank, world, torch.device("cuda", local_rank), sync=False)
-
-            def exchange():
-                with torch.cuda.stream(stream):
-                    return ex()
-        h.set_exchange(ex.slice.data_ptr(), ex.all.data_ptr(), ex.chunk, exchange)
+    comm_setup(h, rank, world, torch, dist, capi)
     xd = torch.from_numpy(X).cuda()
     warm, iters = 4, 20
     with torch.cuda.stream(stream):
@@ -283,17 +285,8 @@ def main():
     h = capi.Handle(3, device=local_rank)
     h.set_stream(stream.cuda_stream)
     h.set_mesh(V, F)
-    h.set_partition(rank, world)
+    comm_setup(h, rank, world, torch, dist, capi)
     x0_dev = torch.from_numpy(X).cuda()
-    ex = None
-    if world > 1:
-        with torch.cuda.stream(stream):
-            ex = sharding.TorchExchange(dim, S, rank, world, torch.device("cuda", local_rank), sync=False)
-
-            def exchange():
-                with torch.cuda.stream(stream):
-                    return ex()
-        h.set_exchange(ex.slice.data_ptr(), ex.all.data_ptr(), ex.chunk, exchange)
     x_pin = torch.empty((S, dim), dtype=torch.float64).pin_memory()
     x_pin_np = x_pin.numpy()
 

@@ -55,7 +55,19 @@ _SIGNATURES = {
     "b200cvt_get_cumulative": (C.c_int, [C.c_void_p, _dp, _qp, C.c_int]),
     "b200cvt_measure_peaks": (C.c_int, [C.c_int, _dp, _dp, _dp]),
     "b200cvt_launch_count": (C.c_uint64, [C.c_void_p]),
+    "b200cvt_comm_unique_id": (C.c_int, [_bp]),
+    "b200cvt_comm_init": (C.c_int, [C.c_void_p, _bp, C.c_uint32, C.c_uint32]),
+    "b200cvt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "b200cvt_group_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200cvt_group_destroy": (None, [C.c_void_p]),
+    "b200cvt_group_size": (C.c_uint32, [C.c_void_p]),
+    "b200cvt_group_member": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "b200cvt_group_set_mesh": (C.c_int, [C.c_void_p, _dp, C.c_uint32, C.c_uint32, _up, _ip, C.c_uint32, _dp]),
+    "b200cvt_group_lloyd": (C.c_int, [C.c_void_p, C.c_uint32, _bp, _dp, C.c_uint32, PROGRESS_CB, C.c_void_p]),
+    "b200cvt_group_newton": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _bp, _dp, C.c_uint32, PROGRESS_CB, C.c_void_p, _up]),
 }
+
+COMM_ID_BYTES = 128
 
 _LIB = None
 
@@ -212,6 +224,15 @@ class Handle:
                                     x.ctypes.data_as(_dp), self.S, cb, None, info.ctypes.data_as(_up)))
         return x, dict(iters=int(info[0]), nfev=int(info[1]), ls_info=int(info[2]))
 
+    def comm_init(self, comm_id, rank, nranks):
+        """One rank of an in-library communicator (NCCL + peer mailboxes); collective over the ranks."""
+        cid = np.ascontiguousarray(comm_id, dtype=np.uint8)
+        assert cid.size == COMM_ID_BYTES
+        _check(lib().b200cvt_comm_init(self._h, cid.ctypes.data_as(_bp), rank, nranks))
+
+    def comm_destroy(self):
+        _check(lib().b200cvt_comm_destroy(self._h))
+
     def set_partition(self, rank, nranks):
         _check(lib().b200cvt_set_partition(self._h, rank, nranks))
 
@@ -258,6 +279,60 @@ class Handle:
 
     def launch_count(self):
         return int(lib().b200cvt_launch_count(self._h))
+
+
+def comm_unique_id():
+    """128 bytes that identify a new communicator (rank 0 creates them, every rank passes them to Handle.comm_init)."""
+    cid = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    _check(lib().b200cvt_comm_unique_id(cid.ctypes.data_as(_bp)))
+    return cid
+
+
+class Group:
+    """One process, N GPUs: b200cvt_group_* (one host thread per GPU inside the library)."""
+
+    def __init__(self, n_gpus, dim=3, volumetric=False):
+        self._g = C.c_void_p()
+        self.dim = dim
+        _check(lib().b200cvt_group_create(n_gpus, dim, int(volumetric), C.byref(self._g)))
+        self.size = int(lib().b200cvt_group_size(self._g))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            lib().b200cvt_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mesh(self, vertices, elems, adjacency=None, weights=None):
+        V = _f64(vertices)
+        E = np.ascontiguousarray(elems, dtype=np.uint32)
+        adj = None if adjacency is None else np.ascontiguousarray(adjacency, dtype=np.int32)
+        w = None if weights is None else _f64(weights)
+        _check(lib().b200cvt_group_set_mesh(self._g, V.ctypes.data_as(_dp), V.shape[0], V.shape[1], E.ctypes.data_as(_up),
+                                            None if adj is None else adj.ctypes.data_as(_ip), E.shape[0],
+                                            None if w is None else w.ctypes.data_as(_dp)))
+
+    def lloyd(self, x, nb_iter, locked=None, callback=None):
+        x = np.array(x, dtype=np.float64, order="C", copy=True)
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        _check(lib().b200cvt_group_lloyd(self._g, nb_iter, None if lk is None else lk.ctypes.data_as(_bp),
+                                         x.ctypes.data_as(_dp), x.shape[0], cb, None))
+        return x
+
+    def newton(self, x, nb_iter, m=7, locked=None, callback=None):
+        x = np.array(x, dtype=np.float64, order="C", copy=True)
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        cb = PROGRESS_CB(callback) if callback else PROGRESS_CB()
+        info = np.zeros(4, dtype=np.uint32)
+        _check(lib().b200cvt_group_newton(self._g, nb_iter, m, None if lk is None else lk.ctypes.data_as(_bp),
+                                          x.ctypes.data_as(_dp), x.shape[0], cb, None, info.ctypes.data_as(_up)))
+        return x, dict(iters=int(info[0]), nfev=int(info[1]), ls_info=int(info[2]))
 
 
 def measure_peaks(device=-1):

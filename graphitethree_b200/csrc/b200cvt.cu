@@ -15,6 +15,7 @@
 #include "clip_flat.cuh"
 #include "facet_pairs.cuh"
 #include "clip_tet.cuh"
+#include "comm.cuh"
 #include "lbfgs.cuh"
 #include "rdt.cuh"
 #include "mesh_prep.cuh"
@@ -24,7 +25,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 static thread_local std::string g_last_error;
@@ -228,10 +232,35 @@ template <class T> struct DevBuf {
         CUDA_CHECK(cudaMalloc((void**)&p, want * sizeof(T)));
         cap = want;
     }
+    // like ensure(), but the first `keep` elements survive a reallocation
+    void grow_keep(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return;
+        T* np = nullptr;
+        const size_t want = n + n / 8 + 16;
+        CUDA_CHECK(cudaMalloc((void**)&np, want * sizeof(T)));
+        if (p && keep) CUDA_CHECK(cudaMemcpyAsync(np, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (p) cudaFree(p);
+        p = np; cap = want;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// shared by the member handles of a single-process group (b200cvt_group_*): one host thread per GPU
+struct GroupShared {
+    std::mutex mu; std::condition_variable cv;
+    int n = 1, waiting = 0; unsigned long long generation = 0;
+    int cancel = 0;
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long long gen = generation;
+        if (++waiting == n) { waiting = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+    }
+};
+
 struct b200cvt_ctx {
+    b200cvt_ctx() { memset(&pc, 0, sizeof(pc)); pc.nranks = 1; }
     int device = 0, dim = 3, volumetric = 0, num_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -298,6 +327,16 @@ struct b200cvt_ctx {
     double* x_slice = nullptr; double* x_all = nullptr; u64 x_chunk = 0;
     b200cvt_exchange_cb xcb = nullptr; void* xuser = nullptr;
     u64 exchanges = 0;
+    // in-library communicator (b200cvt_comm_init*): NCCL for the bulk exchanges, peer mailboxes for the L-BFGS scalars
+    ncclComm_t nccl = nullptr;
+    bool has_comm = false;
+    PeerComm pc;                                  // device view (pc.nranks == 1 without a communicator)
+    DevBuf<PeerBox> boxes;                        // this rank's mailboxes [2][B200_MAX_RANKS]
+    DevBuf<unsigned long long> pc_seq; DevBuf<double> pc_gtot; DevBuf<unsigned int> pc_err;
+    void* ipc_opened[B200_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf<double> xch_slice, xch_all, g_full;    // exchange buffers owned by the library (communicator mode)
+    GroupShared* group = nullptr;                 // member of a single-process group
     // L-BFGS
     DevBuf<double> lb_g, lb_q, lb_px, lb_pg, lb_wa, lb_s, lb_y, lb_part;
     DevBuf<LbfgsScalars> lb_sc;
@@ -888,6 +927,12 @@ static void set_seeds_common(b200cvt_ctx* h, u32 S) {
 }
 
 static void run_exchange(b200cvt_ctx* h) {
+    if (h->has_comm) {
+        // one all-gather of every rank's chunk over NVLink, ordered on the handle's stream (no host synchronisation)
+        NCCL_CHECK(nccl_api().AllGather(h->x_slice, h->x_all, (size_t)h->slice_len() * (h->dim + 1), ncclDouble, h->nccl, h->stream));
+        h->exchanges++;
+        return;
+    }
     if (!h->xcb || !h->x_slice || !h->x_all) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
     if (h->x_chunk < (u64)h->slice_len() * (h->dim + 1)) throw ArgError("exchange buffers too small");
     // the callback enqueues the all-gather on the handle's stream when the caller supplied it (b200cvt_set_stream);
@@ -903,10 +948,32 @@ static void pack_slice(b200cvt_ctx* h, const double* out_s, const double* out_v)
     LAUNCH(h, pack_slice_kernel<D>, div_up(n, 256), 256, 0, out_s, out_v, h->qbegin(), h->qend(), n, h->x_slice);
 }
 
+// A cancel request of the progress callback must stop every rank at the same iteration (the next collective would hang
+// otherwise). Group members agree through the shared flag; ranks of different processes must be given callbacks that
+// return the same value.
+static bool agree_cancel(b200cvt_ctx* h, bool mine) {
+    if (!h->group) return mine;
+    if (mine) { std::lock_guard<std::mutex> lk(h->group->mu); h->group->cancel = 1; }
+    h->group->barrier();
+    bool all;
+    { std::lock_guard<std::mutex> lk(h->group->mu); all = h->group->cancel != 0; }
+    h->group->barrier();
+    return all;
+}
+
+// communicator mode: the exchange buffers belong to the library
+static void comm_prepare(b200cvt_ctx* h) {
+    if (!h->has_comm || h->nranks <= 1) return;
+    const size_t chunk = (size_t)h->slice_len() * (h->dim + 1);
+    h->xch_slice.ensure(chunk); h->xch_all.ensure(chunk * h->nranks);
+    h->x_slice = h->xch_slice.p; h->x_all = h->xch_all.p; h->x_chunk = chunk;
+}
+
 // Lloyd_iterations (geogram/voronoi/CVT.cpp:133-167) on the device-resident seeds
 static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void* user) {
     const u32 S = h->S;
     if (nb_iter > 0) h->rdt_valid = false;      // the seeds move: a cached triangulation is stale
+    comm_prepare(h);
     for (u32 it = 0; it < nb_iter; ++it) {
         evaluate(h, 0, 0);
         u32 n = h->slice_len();
@@ -939,7 +1006,7 @@ static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void
         if (it + 1 == nb_iter) scatter_results(h, false, false, false);
         h->grid_valid = false; h->knn_valid = false;
         sync_stream(h);
-        if (cb && cb(user, it + 1, 0.0, 0.0)) throw CanceledError("canceled by the progress callback");
+        if (agree_cancel(h, cb && cb(user, it + 1, 0.0, 0.0))) throw CanceledError("canceled by the progress callback");
     }
     h->has_results = nb_iter > 0;
     h->has_energy = false;
@@ -1170,10 +1237,13 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
     });
 }
 
+static void comm_release(b200cvt_ctx* h);
+
 void b200cvt_destroy(b200cvt_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    comm_release(h);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1622,6 +1692,204 @@ int b200cvt_get_timings(b200cvt_handle h, float* ms) {
 }
 
 uint64_t b200cvt_launch_count(b200cvt_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// in-library communicator
+// ---------------------------------------------------------------------------------------
+#define B200_BOX_BYTES (2u << 20)       // the mailbox allocation (a whole 2 MiB block: its IPC handle maps exactly it)
+
+static void comm_alloc_boxes(b200cvt_ctx* h) {
+    h->boxes.ensure(B200_BOX_BYTES / sizeof(PeerBox));
+    h->pc_seq.ensure(1); h->pc_gtot.ensure(16); h->pc_err.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(h->boxes.p, 0, B200_BOX_BYTES, h->stream));
+    CUDA_CHECK(cudaMemsetAsync(h->pc_seq.p, 0, sizeof(unsigned long long), h->stream));
+    CUDA_CHECK(cudaMemsetAsync(h->pc_gtot.p, 0, 16 * sizeof(double), h->stream));
+    CUDA_CHECK(cudaMemsetAsync(h->pc_err.p, 0, sizeof(unsigned int), h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+static void comm_finish(b200cvt_ctx* h, u32 rank, u32 nranks, PeerBox** peers) {
+    memset(&h->pc, 0, sizeof(h->pc));
+    h->pc.rank = (int)rank; h->pc.nranks = (int)nranks;
+    for (u32 p = 0; p < nranks; ++p) h->pc.boxes[p] = peers[p];
+    h->pc.seq = h->pc_seq.p; h->pc.gtot = h->pc_gtot.p; h->pc.error = h->pc_err.p;
+    h->rank = rank; h->nranks = nranks; h->has_comm = true;
+    h->knn_valid = false; h->has_results = false; h->rdt_valid = false; h->prev_valid = false;
+}
+
+static void comm_release(b200cvt_ctx* h) {
+    if (!h->has_comm) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int p = 0; p < B200_MAX_RANKS; ++p)
+        if (h->ipc_opened[p]) { cudaIpcCloseMemHandle(h->ipc_opened[p]); h->ipc_opened[p] = nullptr; }
+    if (h->nccl) { nccl_api().CommDestroy(h->nccl); h->nccl = nullptr; }
+    h->has_comm = false;
+    memset(&h->pc, 0, sizeof(h->pc)); h->pc.nranks = 1;
+}
+
+struct b200cvt_group {
+    std::vector<b200cvt_ctx*> members;
+    GroupShared shared;
+};
+
+// runs fn(rank) on one host thread per member (the device loops synchronise with the host and issue collectives, so the
+// ranks must run concurrently); returns the first non-zero status and leaves its message in this thread's last error
+template <class F> static int group_run(b200cvt_group* g, F&& fn) {
+    const size_t n = g->members.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    { std::lock_guard<std::mutex> lk(g->shared.mu); g->shared.cancel = 0; }
+    for (size_t r = 0; r < n; ++r)
+        th.emplace_back([&, r] { rc[r] = fn((u32)r); if (rc[r] != 0) msg[r] = g_last_error; });
+    for (auto& t : th) t.join();
+    for (size_t r = 0; r < n; ++r)
+        if (rc[r] != 0) { g_last_error = "rank " + std::to_string(r) + ": " + msg[r]; return rc[r]; }
+    return B200CVT_OK;
+}
+
+extern "C" {
+
+int b200cvt_comm_unique_id(uint8_t* id_out) {
+    return guarded([&] {
+        if (!id_out) throw ArgError("null argument");
+        static_assert(sizeof(ncclUniqueId) == B200CVT_COMM_ID_BYTES, "ncclUniqueId size");
+        ncclUniqueId id;
+        NCCL_CHECK(nccl_api().GetUniqueId(&id));
+        memcpy(id_out, &id, sizeof(id));
+    });
+}
+
+int b200cvt_comm_init(b200cvt_handle h, const uint8_t* id_bytes, uint32_t rank, uint32_t nranks) {
+    return guarded([&] {
+        if (!h || !id_bytes) throw ArgError("null argument");
+        if (nranks == 0 || rank >= nranks || nranks > B200_MAX_RANKS) throw ArgError("bad communicator size");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        comm_release(h);
+        if (nranks == 1) { h->rank = 0; h->nranks = 1; return; }
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, sizeof(id));
+        NCCL_CHECK(nccl_api().CommInitRank(&h->nccl, (int)nranks, id, (int)rank));
+        comm_alloc_boxes(h);
+        // every rank's mailbox block, opened in this process through CUDA IPC (the handles travel with one all-gather)
+        cudaIpcMemHandle_t mine;
+        CUDA_CHECK(cudaIpcGetMemHandle(&mine, h->boxes.p));
+        DevBuf<unsigned char> d_handles;
+        d_handles.ensure(sizeof(mine) * nranks);
+        CUDA_CHECK(cudaMemcpyAsync(d_handles.p + sizeof(mine) * rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+        NCCL_CHECK(nccl_api().AllGather(d_handles.p + sizeof(mine) * rank, d_handles.p, sizeof(mine), ncclUint8, h->nccl, h->stream));
+        std::vector<cudaIpcMemHandle_t> all(nranks);
+        CUDA_CHECK(cudaMemcpyAsync(all.data(), d_handles.p, sizeof(mine) * nranks, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        PeerBox* peers[B200_MAX_RANKS];
+        for (u32 p = 0; p < nranks; ++p) {
+            if (p == rank) { peers[p] = h->boxes.p; continue; }
+            void* ptr = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened[p] = ptr;
+            peers[p] = (PeerBox*)ptr;
+        }
+        comm_finish(h, rank, nranks, peers);
+    });
+}
+
+int b200cvt_comm_destroy(b200cvt_handle h) {
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        comm_release(h);
+        h->rank = 0; h->nranks = 1; h->knn_valid = false; h->has_results = false;
+    });
+}
+
+int b200cvt_group_create(int n_gpus, int dim, int volumetric, b200cvt_group_handle* out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is NULL");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        if (n_gpus <= 0) n_gpus = ndev;
+        if (n_gpus > ndev || n_gpus > B200_MAX_RANKS) throw ArgError("more GPUs requested than visible");
+        std::unique_ptr<b200cvt_group> g(new b200cvt_group);
+        g->shared.n = n_gpus;
+        struct Cleanup { b200cvt_group* g; bool armed = true; ~Cleanup() { if (armed) for (auto* m : g->members) b200cvt_destroy(m); } } cleanup{g.get()};
+        for (int d = 0; d < n_gpus; ++d) {
+            b200cvt_handle m = nullptr;
+            if (b200cvt_create(d, dim, volumetric, &m) != B200CVT_OK) throw CudaError(g_last_error);
+            m->group = &g->shared;
+            g->members.push_back(m);
+        }
+        if (n_gpus > 1) {
+            std::vector<ncclComm_t> comms(n_gpus);
+            std::vector<int> devs(n_gpus);
+            for (int d = 0; d < n_gpus; ++d) devs[d] = d;
+            if (!nccl_api().CommInitAll) throw std::runtime_error("ncclCommInitAll is not available");
+            NCCL_CHECK(nccl_api().CommInitAll(comms.data(), n_gpus, devs.data()));
+            PeerBox* peers[B200_MAX_RANKS];
+            for (int d = 0; d < n_gpus; ++d) {
+                CUDA_CHECK(cudaSetDevice(d));
+                g->members[d]->nccl = comms[d];
+                comm_alloc_boxes(g->members[d]);
+                peers[d] = g->members[d]->boxes.p;
+                for (int o = 0; o < n_gpus; ++o) {
+                    if (o == d) continue;
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(o, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
+                    cudaGetLastError();
+                }
+            }
+            for (int d = 0; d < n_gpus; ++d) comm_finish(g->members[d], (u32)d, (u32)n_gpus, peers);
+        }
+        cleanup.armed = false;
+        *out = g.release();
+    });
+}
+
+void b200cvt_group_destroy(b200cvt_group_handle g) {
+    if (!g) return;
+    for (auto* m : g->members) { comm_release(m); b200cvt_destroy(m); }
+    delete g;
+}
+
+uint32_t b200cvt_group_size(b200cvt_group_handle g) { return g ? (uint32_t)g->members.size() : 0; }
+
+b200cvt_handle b200cvt_group_member(b200cvt_group_handle g, uint32_t rank) {
+    return (g && rank < g->members.size()) ? g->members[rank] : nullptr;
+}
+
+int b200cvt_group_set_mesh(b200cvt_group_handle g, const double* vertices, uint32_t nv, uint32_t stride, const uint32_t* elems,
+                           const int32_t* adjacency, uint32_t ne, const double* weights) {
+    if (!g) { g_last_error = "null group"; return B200CVT_ERR_ARG; }
+    return group_run(g, [&](u32 r) { return b200cvt_set_mesh(g->members[r], vertices, nv, stride, elems, adjacency, ne, weights); });
+}
+
+int b200cvt_group_lloyd(b200cvt_group_handle g, uint32_t nb_iter, const uint8_t* locked, double* x_inout, uint32_t S,
+                        b200cvt_progress_cb cb, void* user) {
+    if (!g || !x_inout) { g_last_error = "null argument"; return B200CVT_ERR_ARG; }
+    // every rank starts from the caller's seeds and ends with the same ones; rank 0 writes them back and reports progress
+    std::vector<std::vector<double>> copy(g->members.size());
+    return group_run(g, [&](u32 r) {
+        double* x = x_inout;
+        if (r != 0) { copy[r].assign(x_inout, x_inout + (size_t)S * g->members[r]->dim); x = copy[r].data(); }
+        return b200cvt_lloyd(g->members[r], nb_iter, locked, x, S, r == 0 ? cb : nullptr, user);
+    });
+}
+
+int b200cvt_group_newton(b200cvt_group_handle g, uint32_t nb_iter, uint32_t m, const uint8_t* locked, double* x_inout, uint32_t S,
+                         b200cvt_progress_cb cb, void* user, uint32_t* info_out) {
+    if (!g || !x_inout) { g_last_error = "null argument"; return B200CVT_ERR_ARG; }
+    std::vector<std::vector<double>> copy(g->members.size());
+    return group_run(g, [&](u32 r) {
+        double* x = x_inout;
+        if (r != 0) { copy[r].assign(x_inout, x_inout + (size_t)S * g->members[r]->dim); x = copy[r].data(); }
+        uint32_t info[4] = {0, 0, 0, 0};
+        const int rc = b200cvt_newton(g->members[r], nb_iter, m, locked, x, S, r == 0 ? cb : nullptr, user, info);
+        if (r == 0 && info_out) memcpy(info_out, info, sizeof(info));
+        return rc;
+    });
+}
 
 }  // extern "C"
 

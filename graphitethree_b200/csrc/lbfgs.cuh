@@ -18,6 +18,7 @@
 //                            then the MCSRCH decision (last block).
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 #include <cooperative_groups.h>
 
 #define LBFGS_MAXM 32
@@ -244,6 +245,10 @@ struct LbfgsDirArgs {
     double* s; double* y;    // [M][N]
     LbfgsScalars* sc;
     double* partials;        // [2][3 * gridDim.x]
+    // Sharded runs: N and all vectors are this rank's slice (a contiguous range of original seed indices); every dot
+    // product is the local partial followed by a sum over the ranks through the peer mailboxes (comm.cuh).
+    PeerComm pc;
+    u32 N_global;
 };
 
 // Sum over the grid of up to three per-thread values: fixed partition (grid-stride), block tree, then every block
@@ -251,7 +256,7 @@ struct LbfgsDirArgs {
 // `slot` alternates between consecutive calls (a block may enter the next reduction while others still read this one).
 template <int K>
 __device__ __forceinline__ void grid_sums(cooperative_groups::grid_group& grid, double* v, double* partials, int slot,
-                                          double* sm, double* out) {
+                                          double* sm, double* out, const PeerComm& pc) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* mine = partials + (size_t)slot * 3 * gridDim.x;
 #pragma unroll
@@ -275,6 +280,22 @@ __device__ __forceinline__ void grid_sums(cooperative_groups::grid_group& grid, 
 #pragma unroll
     for (int j = 0; j < K; ++j) out[j] = sm[32 + j];
     __syncthreads();
+    if (pc.nranks > 1) {
+        // the local totals (identical in every block) become global ones: block 0 exchanges them with the peers and
+        // publishes the sums; one more grid barrier
+        if (blockIdx.x == 0 && w == 0) {
+            double tot[K];
+            peer_allreduce<K>(pc, out, tot);
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) pc.gtot[slot * 8 + j] = tot[j];
+                __threadfence();
+            }
+        }
+        grid.sync();
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = __ldcg(pc.gtot + slot * 8 + j);
+    }
 }
 
 // HLBFGS.cpp:356-533 between two line searches, on the device (see the header of this file)
@@ -297,7 +318,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
             a.q[i] = qi; a.px[i] = a.x[i]; a.pg[i] = gi; a.wa[i] = a.x[i];
             v[0] += gi * gi; v[1] += gi * qi;
         }
-        grid_sums<2>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+        grid_sums<2>(grid, v, a.partials, slot, sm, tot, a.pc); slot ^= 1;
         if (tid == 0) {
             if (a.first) { sc->gnorm = sqrt(tot[0]); sc->stp = 1.0 / sc->gnorm; } else sc->stp = 1.0;
             sc->dot = tot[1];
@@ -320,7 +341,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
                 v[0] += yi * si; v[1] += yi * yi;
                 v[2] += qi * ((s0 == s_cur) ? si : s0[i]);
             }
-            grid_sums<3>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+            grid_sums<3>(grid, v, a.partials, slot, sm, tot, a.pc); slot ^= 1;
         }
         const double ys = tot[0], yy = tot[1];
         const double rho_cur = 1.0 / ys;
@@ -356,7 +377,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
                     v[0] += yn[k] * qk;
                 }
             }
-            grid_sums<1>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+            grid_sums<1>(grid, v, a.partials, slot, sm, tot, a.pc); slot ^= 1;
             dotv = tot[0];
         }
         // second loop (HLBFGS_UPDATE_Second_Step, :178-196): q += (alpha_i - rho_st (y_st.q)) s_st
@@ -385,7 +406,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
                     v[0] += gk * qk;
                 }
             }
-            grid_sums<1>(grid, v, a.partials, slot, sm, tot); slot ^= 1;
+            grid_sums<1>(grid, v, a.partials, slot, sm, tot, a.pc); slot ^= 1;
             dotv = tot[0];
         }
         if (tid == 0) { sc->stp = 1.0; sc->dot = dotv; }
@@ -393,7 +414,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
     // start of MCSRCH (LineSearch.cpp:60-100): info becomes -1 when a trial point is wanted
     if (tid == 0) {
         sc->info = 0;
-        mcsrch_dev(sc, N);
+        mcsrch_dev(sc, a.N_global);
         __threadfence();
     }
     grid.sync();
@@ -417,7 +438,7 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
 // Deterministic: fixed partition, per-block partials added in order by the last block.
 __global__ void __launch_bounds__(LBFGS_POST_THREADS)
 lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const double* q, const double* x,
-                       double* partials, LbfgsScalars* sc, int resume) {
+                       double* partials, LbfgsScalars* sc, int resume, PeerComm pc, u32 n_global) {
     __shared__ double sm[32];
     __shared__ bool last;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -449,6 +470,15 @@ lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const d
         tot[j] = block_sum(p, sm);
         __syncthreads();
     }
+    if (pc.nranks > 1) {
+        // sharded: fs / g, q, x are this rank's seeds / slice; totals over the ranks through the peer mailboxes
+        if (threadIdx.x < 32) {
+            double gt[4];
+            peer_allreduce<4>(pc, tot, gt);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tot[j] = gt[j];
+        }
+    }
     if (threadIdx.x == 0) {
         sc->red_counter = 0;
         sc->f = tot[0];
@@ -456,6 +486,6 @@ lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const d
         sc->gnorm = sqrt(tot[2]);
         sc->xnorm = sqrt(tot[3]);
         // a line search that could not start (info != -1 after the direction kernel) stays as it is
-        if (resume && sc->info == -1) mcsrch_dev(sc, n);
+        if (resume && sc->info == -1) mcsrch_dev(sc, n_global);
     }
 }

@@ -3,17 +3,40 @@
 // funcgrad = set_vertices + compute_CVT_func_grad(check_SR=true) + constrain_points.
 // Included at the end of b200cvt.cu.
 
-static u32 lb_blocks(u32 n) { return std::min<u32>(div_up(n, 256), 148u * 8u); }
+static u32 lb_blocks(u32 n) { return std::max<u32>(1u, std::min<u32>(div_up(n, 256), 148u * 8u)); }
 
 // funcgrad (CVT.cpp:323-338) on the device: seeds = h->x, result g -> h->lb_g, per-seed energies -> newton_fs(h)
 // (summed by lbfgs_post_eval_kernel).
 // With partitioned seeds every rank evaluates its Morton slice, the (g, f_seed) slices are
 // all-gathered, and every rank then holds the full gradient and the same energy.
+// Sharded runs with the in-library communicator: L-BFGS vectors are sharded by contiguous ranges of ORIGINAL seed indices
+// (rank r holds seeds [r L, (r+1) L), L = ceil(S / nranks)), independent of the Morton ranges the evaluation is sharded by
+// (those are re-cut at every evaluation). The gradient travels from its evaluator to its L-BFGS owner with one
+// reduce-scatter (every entry has exactly one non-zero contribution), the new positions come back with one in-place
+// all-gather on the seed array; everything else of the optimiser is local + a few doubles through the peer mailboxes.
+static u32 lb_local_seeds(b200cvt_ctx* h) {
+    const u64 L = h->slice_len(), b = std::min<u64>((u64)h->rank * L, h->S);
+    return (u32)(std::min<u64>(b + L, h->S) - b);
+}
+
 template <int D>
 static void newton_eval_t(b200cvt_ctx* h) {
     h->grid_valid = false; h->knn_valid = false;
     evaluate(h, 1, 1);
     const u32 S = h->S;
+    if (h->has_comm && h->nranks > 1) {
+        const size_t L = h->slice_len();
+        const size_t padded = L * h->nranks * D;
+        h->g_full.ensure(padded);
+        CUDA_CHECK(cudaMemsetAsync(h->g_full.p, 0, sizeof(double) * padded, h->stream));
+        const u32 nown = h->qend() - h->qbegin();
+        if (nown > 0)
+            LAUNCH(h, scatter_results_kernel<D>, div_up(nown, 256), 256, 0, (const SeedRec<D>*)h->xs.p, h->qbegin(), h->qend(), h->out_s.p,
+                   h->out_v.p, h->flags.p, h->pair_cnt.p, h->locked.p, 1, (double*)nullptr, h->g_full.p, h->flags_orig.p, h->cnt_orig.p);
+        NCCL_CHECK(nccl_api().ReduceScatter(h->g_full.p, h->lb_g.p, L * D, ncclDouble, ncclSum, h->nccl, h->stream));
+        h->exchanges++;
+        return;
+    }
     if (h->nranks == 1) {
         LAUNCH(h, scatter_results_kernel<D>, div_up(S, 256), 256, 0, (const SeedRec<D>*)h->xs.p, 0u, S, h->out_s.p, h->out_v.p,
                h->flags.p, h->pair_cnt.p, h->locked.p, 1, (double*)nullptr, h->lb_g.p, h->flags_orig.p, h->cnt_orig.p);
@@ -30,7 +53,22 @@ static void newton_eval(b200cvt_ctx* h) {
     if (h->dim == 3) newton_eval_t<3>(h); else newton_eval_t<6>(h);
 }
 
-static const double* newton_fs(b200cvt_ctx* h) { return h->nranks == 1 ? h->out_s.p : h->s_orig.p; }
+static const double* newton_fs(b200cvt_ctx* h) {
+    if (h->has_comm && h->nranks > 1) return h->out_s.p + h->qbegin();     // this rank's evaluated seeds (sorted range)
+    return h->nranks == 1 ? h->out_s.p : h->s_orig.p;
+}
+
+// the seed array with the padding the in-place all-gather needs (nranks * L rows), contents kept
+static void newton_pad_seeds(b200cvt_ctx* h) {
+    const size_t padded = (size_t)h->slice_len() * h->nranks * h->dim;
+    h->x.grow_keep(padded, (size_t)h->S * h->dim, h->stream);
+}
+
+static void newton_gather_seeds(b200cvt_ctx* h) {
+    const size_t L = h->slice_len();
+    NCCL_CHECK(nccl_api().AllGather(h->x.p + (size_t)h->rank * L * h->dim, h->x.p, L * h->dim, ncclDouble, h->nccl, h->stream));
+    h->exchanges++;
+}
 
 // HLBFGS main loop (HLBFGS.cpp:356-586) on the device-resident seeds h->x
 static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb cb, void* user, uint32_t* info_out) {
@@ -39,11 +77,19 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     h->rdt_valid = false;                    // the seeds move: a cached triangulation is stale
     const int D = h->dim;
     const u32 S = h->S;
-    const u32 N = S * (u32)D;
+    const u32 N_global = S * (u32)D;
+    const bool sharded = h->has_comm && h->nranks > 1;
+    // sharded: this rank's slice of every vector (a range of original seed indices); else the whole vectors
+    const u32 N = sharded ? lb_local_seeds(h) * (u32)D : N_global;
+    const u32 Nalloc = sharded ? h->slice_len() * (u32)D : N_global;
+    const size_t xoff = sharded ? (size_t)h->rank * h->slice_len() * D : 0;
+    if (sharded) newton_pad_seeds(h);
     const int M = (int)m;
     h->flags_orig.ensure(S); h->cnt_orig.ensure(S);
-    h->lb_g.ensure(N); h->lb_q.ensure(N); h->lb_px.ensure(N); h->lb_pg.ensure(N); h->lb_wa.ensure(N);
-    h->lb_s.ensure((size_t)std::max(M, 1) * N); h->lb_y.ensure((size_t)std::max(M, 1) * N);
+    h->lb_g.ensure(Nalloc); h->lb_q.ensure(Nalloc); h->lb_px.ensure(Nalloc); h->lb_pg.ensure(Nalloc); h->lb_wa.ensure(Nalloc);
+    h->lb_s.ensure((size_t)std::max(M, 1) * Nalloc); h->lb_y.ensure((size_t)std::max(M, 1) * Nalloc);
+    PeerComm pc = h->pc;
+    if (!sharded) { memset(&pc, 0, sizeof(pc)); pc.nranks = 1; }
     // the direction kernel needs all its blocks resident (grid barriers): one cooperative launch
     if (h->lb_dir_blocks == 0) {
         int per_sm = 0, coop = 0;
@@ -55,7 +101,7 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     }
     h->lb_part.ensure(std::max<size_t>(6 * (size_t)h->lb_dir_blocks, 4 * (size_t)LBFGS_POST_BLOCKS)); h->lb_sc.ensure(1);
     CUDA_CHECK(cudaMemsetAsync(h->lb_sc.p, 0, sizeof(LbfgsScalars), h->stream));
-    double* x = h->x.p; double* g = h->lb_g.p; double* q = h->lb_q.p;
+    double* x = h->x.p + xoff; double* g = h->lb_g.p; double* q = h->lb_q.p;
     LbfgsScalars* sc = h->lb_sc.p;
     const u32 nb = lb_blocks(N);
     const double stpmin = 1.0e-20, stpmax = 1.0e+20;
@@ -65,7 +111,9 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     bool canceled = false;
     struct { double f, dot, stp, gnorm, xnorm; int info, nfev; } hs;
     auto post_eval = [&](int resume) {
-        LAUNCH(h, lbfgs_post_eval_kernel, LBFGS_POST_BLOCKS, LBFGS_POST_THREADS, 0, S, newton_fs(h), N, g, q, x, h->lb_part.p, sc, resume);
+        const u32 nfs = sharded ? h->qend() - h->qbegin() : S;
+        LAUNCH(h, lbfgs_post_eval_kernel, LBFGS_POST_BLOCKS, LBFGS_POST_THREADS, 0, nfs, newton_fs(h), N, g, q, x, h->lb_part.p, sc, resume,
+               pc, N_global);
     };
     newton_eval(h); nfev_total++;
     post_eval(0);
@@ -83,12 +131,14 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         }
         da.x = x; da.g = g; da.q = q; da.px = h->lb_px.p; da.pg = h->lb_pg.p; da.wa = h->lb_wa.p;
         da.s = h->lb_s.p; da.y = h->lb_y.p; da.sc = sc; da.partials = h->lb_part.p;
+        da.pc = pc; da.N_global = N_global;
         {
             void* kargs[] = {(void*)&da};
             CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lbfgs_direction_kernel, dim3(h->lb_dir_blocks), dim3(LBFGS_DIR_THREADS),
                                                    kargs, 0, h->stream));
             h->launches++;
         }
+        if (sharded) newton_gather_seeds(h);          // the first trial point (written by the direction kernel)
         if (iter > 0 && M > 0) cur_pos = (cur_pos + 1) % M;
         // MCSRCH (LineSearch.cpp:100-230): the direction kernel has moved x to the first trial point, unless the search
         // could not start (info != -1; rare: the evaluation below is then wasted and not counted)
@@ -102,17 +152,24 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
             ls_info = hs.info;
             if (ls_info != -1) break;
             LAUNCH(h, step_kernel, nb, 256, 0, N, sc, h->lb_wa.p, q, x);
+            if (sharded) newton_gather_seeds(h);
         }
         if (ls_info == 0) nfev_ls = 0;                    // the search never started (a finished search reports 1..6)
         nfev_total += nfev_ls;
         iter++;
-        if (cb && cb(user, iter, hs.f, hs.gnorm)) { canceled = true; break; }
+        if (agree_cancel(h, cb && cb(user, iter, hs.f, hs.gnorm))) { canceled = true; break; }
         double xnorm = hs.xnorm < 1.0 ? 1.0 : hs.xnorm;
         if (ls_info != 1) break;                          // "Linesearch has failed"
         if (hs.gnorm / xnorm <= 0.0) break;               // PARAMETERS[5] = 0
         if (hs.gnorm < 0.0) break;                        // PARAMETERS[6] = epsg = 0
         if (hs.stp < stpmin || hs.stp > stpmax) break;
         if (iter > nb_iter) break;
+    }
+    if (sharded) {
+        unsigned int perr = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&perr, h->pc_err.p, sizeof(perr), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (perr) throw std::runtime_error("a peer GPU did not answer a mailbox reduction (timeout)");
     }
     if (info_out) { info_out[0] = iter; info_out[1] = nfev_total; info_out[2] = (u32)ls_info; info_out[3] = 0; }
     h->grid_valid = false; h->knn_valid = false; h->has_results = true;

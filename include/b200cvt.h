@@ -151,6 +151,40 @@ uint64_t b200cvt_exchange_chunk_doubles(int dim, uint32_t S, uint32_t nranks);
 int b200cvt_set_exchange(b200cvt_handle h, double* d_slice, double* d_all, uint64_t chunk_doubles,
                          b200cvt_exchange_cb cb, void* user);
 
+/* ---- multi-GPU inside the library (replaces nothing in the reference: its RVD is one process / one mesh
+ * copy, partitioned over host threads by RVD_Nd_Impl::create_threads, G/voronoi/RVD.cpp:2374-2453) ----
+ * A communicator makes the handle one rank of N: seeds are evaluated by Morton range, the mesh is replicated, seed
+ * positions travel with ONE NCCL all-gather per evaluation (Lloyd: the updated slices; Newton: the new trial point, in
+ * place on the seed array), the Newton gradient reaches the rank that owns its L-BFGS slice with one reduce-scatter, and
+ * L-BFGS vectors are sharded by ranges of original seed indices: every dot product is a local partial plus a sum of a few
+ * doubles that the cooperative L-BFGS kernels exchange through peer-memory mailboxes (stores into every peer's HBM over
+ * NVLink, CUDA IPC between processes). It supersedes b200cvt_set_partition + b200cvt_set_exchange.
+ *   one process per GPU: rank 0 calls b200cvt_comm_unique_id, the 128 bytes are sent to every rank by any means (MPI,
+ *                        torch.distributed, a file), every rank calls b200cvt_comm_init on its handle (collective).
+ *   one process, N GPUs: b200cvt_group_create (below). */
+#define B200CVT_COMM_ID_BYTES 128
+int b200cvt_comm_unique_id(uint8_t* id_out /* B200CVT_COMM_ID_BYTES */);
+int b200cvt_comm_init(b200cvt_handle h, const uint8_t* id, uint32_t rank, uint32_t nranks);
+int b200cvt_comm_destroy(b200cvt_handle h);
+
+/* One process, N GPUs (devices 0 .. n_gpus-1; n_gpus <= 0: all visible): the group owns one handle per GPU, a
+ * communicator over them (ncclCommInitAll + peer access) and runs every call on one host thread per GPU. This is what
+ * CentroidalVoronoiTesselationB200 uses when asked for more than one GPU: same signatures as
+ * b200cvt_set_mesh / b200cvt_lloyd / b200cvt_newton, the progress callback is called by rank 0's thread, and a cancel
+ * request stops all ranks at the same iteration. */
+typedef struct b200cvt_group* b200cvt_group_handle;
+int b200cvt_group_create(int n_gpus, int dim, int volumetric, b200cvt_group_handle* out);
+void b200cvt_group_destroy(b200cvt_group_handle g);
+uint32_t b200cvt_group_size(b200cvt_group_handle g);
+b200cvt_handle b200cvt_group_member(b200cvt_group_handle g, uint32_t rank);
+int b200cvt_group_set_mesh(b200cvt_group_handle g, const double* vertices, uint32_t nv, uint32_t stride_doubles,
+                           const uint32_t* elems, const int32_t* adjacency_or_null, uint32_t n_elems,
+                           const double* weights_or_null);
+int b200cvt_group_lloyd(b200cvt_group_handle g, uint32_t nb_iter, const uint8_t* locked_or_null, double* x_inout, uint32_t S,
+                        b200cvt_progress_cb cb, void* user);
+int b200cvt_group_newton(b200cvt_group_handle g, uint32_t nb_iter, uint32_t m, const uint8_t* locked_or_null, double* x_inout,
+                         uint32_t S, b200cvt_progress_cb cb, void* user, uint32_t* info_out);
+
 /* point_is_locked_ (G/voronoi/CVT.h:375-410) for the device-resident loops; NULL unlocks all. */
 int b200cvt_set_locked(b200cvt_handle h, const uint8_t* locked_or_null, uint32_t S);
 
