@@ -1560,7 +1560,7 @@ int b200cvt_get_stats(b200cvt_handle h, uint64_t* out) {
         out[5] = total; out[6] = h->pair_cap; out[7] = h->g.ncells;
         // [11] seeds served by the kNN launch of the last evaluation (sharded runs: owned range + two-cell halo)
         u32 nq = h->S;
-        if (h->nranks > 1 && h->need_n.p && h->knn_valid) CUDA_CHECK(cudaMemcpy(&nq, h->need_n.p, sizeof(u32), cudaMemcpyDeviceToHost));
+        if (h->nranks > 1 && h->need_n.p) CUDA_CHECK(cudaMemcpy(&nq, h->need_n.p, sizeof(u32), cudaMemcpyDeviceToHost));
         out[11] = nq;
         h->want_stats = true;   // counters are collected from the next evaluation on
     });

@@ -109,7 +109,8 @@ namespace {
 
     template <class CVT_T>
     void run(Mesh& M, index_t S, index_t dim, const double* seeds, index_t nl, index_t nn, index_t m, Run& out) {
-        CVT_T cvt(&M, coord_index_t(dim), "NN");
+        /* the reference with its kd-tree backend; the adapter with its default ("default" -> algo:delaunay = NN -> B200NN) */
+        CVT_T cvt(&M, coord_index_t(dim), std::is_same<CVT_T, CentroidalVoronoiTesselationB200>::value ? "default" : "NN");
         cvt.set_volumetric(g_volumetric);
         cvt.set_points(S, seeds);
         double t0 = Stopwatch::now();

@@ -10,6 +10,8 @@
 #include <geogram/basic/stopwatch.h>
 #include <geogram/mesh/mesh_remesh.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <vector>
 
@@ -133,7 +135,7 @@ namespace GEO {
         RestrictedVoronoiDiagram(
             delaunay, mesh, (mesh->vertices.nb() > 0) ? mesh->vertices.point_ptr(0) : nullptr, mesh->vertices.dimension()
         ),
-        h_(nullptr), h_vol_(nullptr), check_SR_(false), mesh_hash_(0), vol_hash_(0), mesh_uploaded_(false), vol_uploaded_(false),
+        h_(nullptr), h_vol_(nullptr), check_SR_(false), mesh_uploaded_version_(0), vol_uploaded_version_(0),
         nb_gpu_calls_(0) {
         ref_ = RestrictedVoronoiDiagram::create(delaunay, mesh);   /* also forces set_stores_neighbors(true), RVD.cpp:2552 */
         has_weights_ = mesh->vertices.attributes().is_defined("weight");
@@ -161,6 +163,12 @@ namespace GEO {
         if(h_ == nullptr || ref_->exact_predicates() || delaunay_ == nullptr || delaunay_->nb_vertices() == 0) {
             return false;
         }
+        /* The GPU path clips every cell by its nearest neighbours in distance order (and truncates at the stored list in
+         * Lloyd mode), i.e. the semantics of the "NN" backends. With a true Delaunay backend (BDEL, PDEL, ...) the reference
+         * clips by the full Delaunay neighbourhood: that stays on the reference implementation. */
+        if(dynamic_cast<Delaunay_NearestNeighbors*>(delaunay_) == nullptr) {
+            return false;
+        }
         if(volumetric_) {
             /* tets only (the reference walks any cell type through its own tet decomposition), dimension 3 */
             const bool whole_cells = (tets_begin_ == NO_INDEX && tets_end_ == NO_INDEX) ||
@@ -170,68 +178,127 @@ namespace GEO {
         return mesh_->facets.nb() > 0 && mesh_->facets.are_simplices() && whole_mesh;
     }
 
-    b200cvt_handle RestrictedVoronoiDiagramB200::handle() {
+    /* Cheap signature of the borrowed mesh: addresses, counts and a strided sample of the coordinates and corners. It is
+     * checked on every compute_* call; the element tables are rebuilt and everything is hashed only when it changes or when
+     * the caller asks for a full check (once per Lloyd_iterations / Newton_iterations / compute_RDT call, mesh_modified()). */
+    unsigned long long RestrictedVoronoiDiagramB200::quick_signature() const {
+        const index_t nv = mesh_->vertices.nb(), stride = mesh_->vertices.dimension();
+        const index_t ne = volumetric_ ? mesh_->cells.nb() : mesh_->facets.nb();
+        unsigned long long h = 0x452821E638D01377ull ^ (static_cast<unsigned long long>(nv) << 32) ^ ne ^
+            (static_cast<unsigned long long>(stride) << 58) ^ (volumetric_ ? 1ull << 57 : 0ull);
+        if(nv == 0 || ne == 0) {
+            return h;
+        }
+        const double* P = mesh_->vertices.point_ptr(0);
+        h = hash_bytes(h, &P, sizeof(P));
+        const size_t nd = size_t(nv) * stride, step = std::max<size_t>(1, nd / 2048);
+        for(size_t i = 0; i < nd; i += step) {
+            h = hash_bytes(h, P + i, sizeof(double));
+        }
+        h = hash_bytes(h, P + nd - 1, sizeof(double));
+        const index_t estep = std::max<index_t>(1, ne / 2048);
+        for(index_t e = 0; e < ne; e += estep) {
+            const index_t v = volumetric_ ? mesh_->cells.vertex(e, 0) : mesh_->facets.vertex(e, 0);
+            const index_t w = volumetric_ ? mesh_->cells.vertex(e, 3) : mesh_->facets.vertex(e, 2);
+            const unsigned long long vw = (static_cast<unsigned long long>(v) << 32) | w;
+            h = hash_bytes(h, &vw, sizeof(vw));
+        }
+        return h;
+    }
+
+    const RestrictedVoronoiDiagramB200::MeshArrays& RestrictedVoronoiDiagramB200::arrays(bool full_check) {
+        MeshArrays& A = volumetric_ ? vol_arrays_ : surf_arrays_;
+        const unsigned long long q = quick_signature();
+        if(A.valid && q == A.quick && !full_check) {
+            return A;
+        }
+        const index_t nv = mesh_->vertices.nb(), stride = mesh_->vertices.dimension();
+        const index_t per = volumetric_ ? 4 : 3;
+        const index_t ne = volumetric_ ? mesh_->cells.nb() : mesh_->facets.nb();
+        A.elems.resize(size_t(ne) * per);
+        A.adj.resize(size_t(ne) * per);
+        for(index_t e = 0; e < ne; ++e) {
+            for(index_t lv = 0; lv < per; ++lv) {
+                A.elems[size_t(e) * per + lv] = volumetric_ ? mesh_->cells.vertex(e, lv) : mesh_->facets.vertex(e, lv);
+                const index_t a = volumetric_ ? mesh_->cells.adjacent(e, lv) : mesh_->facets.adjacent(e, lv);
+                A.adj[size_t(e) * per + lv] = (a == NO_INDEX) ? -1 : int32_t(a);
+            }
+        }
+        /* the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783) */
+        A.weights.clear();
+        if(has_weights_ && !volumetric_) {
+            A.weights.resize(nv);
+            for(index_t v = 0; v < nv; ++v) {
+                A.weights[v] = vertex_weight_[v];
+            }
+        }
+        unsigned long long hsh = hash_bytes(0x243F6A8885A308D3ull + nv + (volumetric_ ? 7 : 0), mesh_->vertices.point_ptr(0),
+                                            sizeof(double) * size_t(nv) * stride);
+        hsh = hash_bytes(hsh, A.elems.data(), sizeof(uint32_t) * A.elems.size());
+        hsh = hash_bytes(hsh, A.adj.data(), sizeof(int32_t) * A.adj.size());
+        if(!A.weights.empty()) {
+            hsh = hash_bytes(hsh, A.weights.data(), sizeof(double) * A.weights.size());
+        }
+        if(!A.valid || hsh != A.full) {
+            ++A.version;
+        }
+        A.full = hsh;
+        A.quick = q;
+        A.valid = true;
+        return A;
+    }
+
+    void RestrictedVoronoiDiagramB200::mesh_modified() {
+        surf_arrays_.valid = false;
+        vol_arrays_.valid = false;
+    }
+
+    b200cvt_handle RestrictedVoronoiDiagramB200::handle(bool full_check) {
+        const MeshArrays& A = arrays(full_check);
+        const index_t nv = mesh_->vertices.nb(), stride = mesh_->vertices.dimension();
         if(volumetric_) {
-            const index_t nv = mesh_->vertices.nb(), nt = mesh_->cells.nb(), stride = mesh_->vertices.dimension();
             if(h_vol_ == nullptr) {
                 check(b200cvt_create(-1, 3, 1, &h_vol_), "b200cvt_create");
             }
-            std::vector<uint32_t> tet(size_t(nt) * 4);
-            std::vector<int32_t> adj(size_t(nt) * 4);
-            for(index_t t = 0; t < nt; ++t) {
-                for(index_t lv = 0; lv < 4; ++lv) {
-                    tet[size_t(t) * 4 + lv] = mesh_->cells.vertex(t, lv);
-                    const index_t a = mesh_->cells.adjacent(t, lv);
-                    adj[size_t(t) * 4 + lv] = (a == NO_INDEX) ? -1 : int32_t(a);
-                }
-            }
-            unsigned long long hsh = hash_bytes(0x13198A2E03707344ull + nv, mesh_->vertices.point_ptr(0), sizeof(double) * size_t(nv) * stride);
-            hsh = hash_bytes(hsh, tet.data(), sizeof(uint32_t) * tet.size());
-            hsh = hash_bytes(hsh, adj.data(), sizeof(int32_t) * adj.size());
-            if(!vol_uploaded_ || hsh != vol_hash_) {
-                /* the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783) */
+            if(vol_uploaded_version_ != A.version) {
                 check(
-                    b200cvt_set_mesh(h_vol_, mesh_->vertices.point_ptr(0), nv, stride, tet.data(), adj.data(), nt, nullptr),
+                    b200cvt_set_mesh(h_vol_, mesh_->vertices.point_ptr(0), nv, stride, A.elems.data(), A.adj.data(),
+                                     index_t(A.elems.size() / 4), nullptr),
                     "b200cvt_set_mesh"
                 );
-                vol_hash_ = hsh;
-                vol_uploaded_ = true;
+                vol_uploaded_version_ = A.version;
             }
             return h_vol_;
         }
-        const index_t nv = mesh_->vertices.nb(), nf = mesh_->facets.nb(), stride = mesh_->vertices.dimension();
-        std::vector<uint32_t> tri(size_t(nf) * 3);
-        std::vector<int32_t> adj(size_t(nf) * 3);
-        for(index_t f = 0; f < nf; ++f) {
-            for(index_t lv = 0; lv < 3; ++lv) {
-                tri[size_t(f) * 3 + lv] = mesh_->facets.vertex(f, lv);
-                const index_t a = mesh_->facets.adjacent(f, lv);
-                adj[size_t(f) * 3 + lv] = (a == NO_INDEX) ? -1 : int32_t(a);
-            }
-        }
-        std::vector<double> weights;
-        if(has_weights_) {
-            weights.resize(nv);
-            for(index_t v = 0; v < nv; ++v) {
-                weights[v] = vertex_weight_[v];
-            }
-        }
-        unsigned long long hsh = hash_bytes(0x243F6A8885A308D3ull + nv, mesh_->vertices.point_ptr(0), sizeof(double) * size_t(nv) * stride);
-        hsh = hash_bytes(hsh, tri.data(), sizeof(uint32_t) * tri.size());
-        hsh = hash_bytes(hsh, adj.data(), sizeof(int32_t) * adj.size());
-        if(has_weights_) {
-            hsh = hash_bytes(hsh, weights.data(), sizeof(double) * weights.size());
-        }
-        if(!mesh_uploaded_ || hsh != mesh_hash_) {
+        if(mesh_uploaded_version_ != A.version) {
             check(
-                b200cvt_set_mesh(h_, mesh_->vertices.point_ptr(0), nv, stride, tri.data(), adj.data(), nf,
-                                 has_weights_ ? weights.data() : nullptr),
+                b200cvt_set_mesh(h_, mesh_->vertices.point_ptr(0), nv, stride, A.elems.data(), A.adj.data(),
+                                 index_t(A.elems.size() / 3), A.weights.empty() ? nullptr : A.weights.data()),
                 "b200cvt_set_mesh"
             );
-            mesh_hash_ = hsh;
-            mesh_uploaded_ = true;
+            mesh_uploaded_version_ = A.version;
         }
         return h_;
+    }
+
+    /* status bits of the last evaluation that the caller should hear about (b200cvt.h: B200CVT_FLAG_*) */
+    void RestrictedVoronoiDiagramB200::report_flags(b200cvt_handle h, index_t nb_seeds) {
+        std::vector<uint8_t> fl(nb_seeds);
+        if(nb_seeds == 0 || b200cvt_get_flags(h, fl.data()) != B200CVT_OK) {
+            return;
+        }
+        index_t kmax = 0, overflow = 0;
+        for(index_t i = 0; i < nb_seeds; ++i) {
+            kmax += (fl[i] & B200CVT_FLAG_KMAX) ? 1 : 0;
+            overflow += (fl[i] & B200CVT_FLAG_POLY_OVERFLOW) ? 1 : 0;
+        }
+        if(kmax != 0) {
+            Logger::warn("B200") << kmax << " seed(s) needed more than " << B200CVT_KMAX
+                                 << " neighbours: their cells are truncated (the reference grows the list without bound)" << std::endl;
+        }
+        if(overflow != 0) {
+            Logger::warn("B200") << overflow << " seed(s) with a clipped polygon over the vertex budget" << std::endl;
+        }
     }
 
     void RestrictedVoronoiDiagramB200::upload_seeds() {
@@ -245,6 +312,7 @@ namespace GEO {
         }
         upload_seeds();
         check(b200cvt_centroids(h_, check_SR_ ? 1 : 0, mg, m), "b200cvt_centroids");
+        report_flags(h_, delaunay_->nb_vertices());
         ++nb_gpu_calls_;
     }
 
@@ -255,6 +323,7 @@ namespace GEO {
         }
         upload_seeds();
         check(b200cvt_funcgrad(h_, check_SR_ ? 1 : 0, &f, g), "b200cvt_funcgrad");
+        report_flags(h_, delaunay_->nb_vertices());
         ++nb_gpu_calls_;
     }
 
@@ -342,6 +411,7 @@ namespace GEO {
             ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
             return;
         }
+        handle(true);
         upload_seeds();
         uint64_t n = 0;
         check(b200cvt_rdt(h_, nullptr, 0, &n), "b200cvt_rdt");
@@ -386,16 +456,43 @@ namespace GEO {
 
     /************************ CVT ************************/
 
+    namespace {
+        /* "default" resolves to algo:delaunay (Delaunay::create); when that is the kd-tree backend "NN", the B200NN backend
+         * takes its place: same lists bit for bit, computed on the device. An explicit name is left alone. */
+        std::string resolve_delaunay(const std::string& name) {
+            b200_register();
+            if(name == "default") {
+                const std::string algo = CmdLine::arg_is_declared("algo:delaunay") ? CmdLine::get_arg("algo:delaunay") : std::string("NN");
+                if(algo == "NN" || algo == "default") {
+                    return "B200NN";
+                }
+            }
+            return name;
+        }
+    }
+
     CentroidalVoronoiTesselationB200::CentroidalVoronoiTesselationB200(Mesh* mesh, coord_index_t dimension, const std::string& delaunay) :
-        CentroidalVoronoiTesselation(mesh, dimension, delaunay), canceled_(false), last_on_gpu_(false) {
+        CentroidalVoronoiTesselation(mesh, dimension, resolve_delaunay(delaunay)), canceled_(false), last_on_gpu_(false),
+        nb_gpus_(1), group_(nullptr), group_mesh_version_(0) {
         for(int i = 0; i < 4; ++i) {
             newton_info_[i] = 0;
         }
         /* the base constructor created the reference RVD; swap in the adapter (which keeps its own reference delegate) */
         RVD_ = new RestrictedVoronoiDiagramB200(delaunay_, mesh);
+        const char* env = getenv("B200CVT_GPUS");
+        if(env != nullptr && atoi(env) > 1) {
+            nb_gpus_ = index_t(atoi(env));
+        }
     }
 
     CentroidalVoronoiTesselationB200::~CentroidalVoronoiTesselationB200() {
+        if(group_ != nullptr) {
+            b200cvt_group_destroy(group_);
+        }
+    }
+
+    void CentroidalVoronoiTesselationB200::set_nb_gpus(index_t n) {
+        nb_gpus_ = std::max<index_t>(n, 1);
     }
 
     RestrictedVoronoiDiagramB200* CentroidalVoronoiTesselationB200::rvd_b200() {
@@ -413,74 +510,110 @@ namespace GEO {
         return 0;
     }
 
-    void CentroidalVoronoiTesselationB200::Lloyd_iterations(index_t nb_iter) {
+    /* the multi-GPU group with the current surface mesh (surfacic mode only), or nullptr: one GPU */
+    b200cvt_group_handle CentroidalVoronoiTesselationB200::group(RestrictedVoronoiDiagramB200* rvd) {
+        if(nb_gpus_ <= 1 || volumetric() || (dimension_ != 3 && dimension_ != 6)) {
+            return nullptr;
+        }
+        if(group_ == nullptr) {
+            check(b200cvt_group_create(int(nb_gpus_), int(dimension_), 0, &group_), "b200cvt_group_create");
+        }
+        const RestrictedVoronoiDiagramB200::MeshArrays& A = rvd->arrays(true);
+        if(group_mesh_version_ != A.version) {
+            check(
+                b200cvt_group_set_mesh(group_, mesh_->vertices.point_ptr(0), mesh_->vertices.nb(), mesh_->vertices.dimension(),
+                                       A.elems.data(), A.adj.data(), index_t(A.elems.size() / 3),
+                                       A.weights.empty() ? nullptr : A.weights.data()),
+                "b200cvt_group_set_mesh"
+            );
+            group_mesh_version_ = A.version;
+        }
+        return group_;
+    }
+
+    bool CentroidalVoronoiTesselationB200::begin_gpu_loop(index_t nb_iter, std::vector<uint8_t>& locked) {
         RestrictedVoronoiDiagramB200* rvd = rvd_b200();
         const index_t nb = nb_points();
         last_on_gpu_ = false;
-        if(rvd != nullptr && nb > 0) {
+        /* The device loops never read the Delaunay object; it only has to be attached to the points for gpu_eligible() and
+         * for whoever reads it afterwards. (The reference calls set_vertices — a kd-tree build plus S queries — at every
+         * iteration, CVT.cpp:147.) */
+        if(rvd != nullptr && nb > 0 && (delaunay_->nb_vertices() != nb || delaunay_->vertices_ptr() != points_.data())) {
             delaunay_->set_vertices(nb, points_.data());
         }
         if(rvd == nullptr || nb == 0 || !rvd->gpu_eligible()) {
+            return false;
+        }
+        if(progress_ != nullptr) {
+            progress_->reset(nb_iter);
+        }
+        cur_iter_ = 0;
+        nb_iter_ = nb_iter;
+        locked.clear();
+        if(point_is_locked_.size() != 0) {
+            locked.resize(nb);
+            for(index_t i = 0; i < nb; ++i) {
+                locked[i] = point_is_locked_[i] ? 1 : 0;
+            }
+        }
+        canceled_ = false;
+        return true;
+    }
+
+    void CentroidalVoronoiTesselationB200::end_gpu_loop(b200cvt_handle h, int status, const char* what) {
+        const index_t nb = nb_points();
+        last_on_gpu_ = true;
+        /* leave the Delaunay object as the reference loop does: attached to the final points, lists rebuilt */
+        delaunay_->set_vertices(nb, points_.data());
+        progress_ = nullptr;
+        check(status, what);
+        if(h != nullptr) {
+            RestrictedVoronoiDiagramB200::report_flags(h, nb);
+        }
+    }
+
+    void CentroidalVoronoiTesselationB200::Lloyd_iterations(index_t nb_iter) {
+        std::vector<uint8_t> locked;
+        if(!begin_gpu_loop(nb_iter, locked)) {
             CentroidalVoronoiTesselation::Lloyd_iterations(nb_iter);
             return;
         }
+        RestrictedVoronoiDiagramB200* rvd = rvd_b200();
+        const index_t nb = nb_points();
         RVD_->set_check_SR(false);
-        if(progress_ != nullptr) {
-            progress_->reset(nb_iter);
+        b200cvt_group_handle g = group(rvd);
+        if(g != nullptr) {
+            int status = b200cvt_group_lloyd(g, nb_iter, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this);
+            end_gpu_loop(nullptr, status, "b200cvt_group_lloyd");
+            return;
         }
-        cur_iter_ = 0;
-        nb_iter_ = nb_iter;
-        std::vector<uint8_t> locked;
-        if(point_is_locked_.size() != 0) {
-            locked.resize(nb);
-            for(index_t i = 0; i < nb; ++i) {
-                locked[i] = point_is_locked_[i] ? 1 : 0;
-            }
-        }
-        canceled_ = false;
-        int status = b200cvt_lloyd(
-            rvd->handle(), nb_iter, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this
-        );
-        last_on_gpu_ = true;
-        /* leave the Delaunay object as the reference loop does: attached to the current points */
-        delaunay_->set_vertices(nb, points_.data());
-        progress_ = nullptr;
-        check(status, "b200cvt_lloyd");
+        b200cvt_handle h = rvd->handle(true);
+        int status = b200cvt_lloyd(h, nb_iter, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this);
+        end_gpu_loop(h, status, "b200cvt_lloyd");
     }
 
     void CentroidalVoronoiTesselationB200::Newton_iterations(index_t nb_iter, index_t m) {
-        RestrictedVoronoiDiagramB200* rvd = rvd_b200();
-        const index_t nb = nb_points();
-        last_on_gpu_ = false;
-        if(rvd != nullptr && nb > 0) {
-            delaunay_->set_vertices(nb, points_.data());
-        }
-        if(rvd == nullptr || nb == 0 || !rvd->gpu_eligible() || !simplex_func_.is_null()) {
+        std::vector<uint8_t> locked;
+        if(!simplex_func_.is_null() || !begin_gpu_loop(nb_iter, locked)) {
             CentroidalVoronoiTesselation::Newton_iterations(nb_iter, m);
             return;
         }
+        RestrictedVoronoiDiagramB200* rvd = rvd_b200();
+        const index_t nb = nb_points();
         RVD_->set_check_SR(true);
-        if(progress_ != nullptr) {
-            progress_->reset(nb_iter);
+        b200cvt_group_handle g = group(rvd);
+        if(g != nullptr) {
+            int status = b200cvt_group_newton(
+                g, nb_iter, m, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this, newton_info_
+            );
+            end_gpu_loop(nullptr, status, "b200cvt_group_newton");
+            return;
         }
-        cur_iter_ = 0;
-        nb_iter_ = nb_iter;
-        std::vector<uint8_t> locked;
-        if(point_is_locked_.size() != 0) {
-            locked.resize(nb);
-            for(index_t i = 0; i < nb; ++i) {
-                locked[i] = point_is_locked_[i] ? 1 : 0;
-            }
-        }
-        canceled_ = false;
+        b200cvt_handle h = rvd->handle(true);
         int status = b200cvt_newton(
-            rvd->handle(), nb_iter, m, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this,
-            newton_info_
+            h, nb_iter, m, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this, newton_info_
         );
-        last_on_gpu_ = true;
-        delaunay_->set_vertices(nb, points_.data());
-        progress_ = nullptr;
-        check(status, "b200cvt_newton");
+        end_gpu_loop(h, status, "b200cvt_newton");
     }
 
     /************************ remesh_smooth ************************/

@@ -34,6 +34,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace GEO {
 
@@ -72,8 +73,23 @@ namespace GEO {
          *  triangulated surface, whole facet range) or volumetric mode (dimension 3, tetrahedral cells, whole tet range);
          *  otherwise the call is delegated to the reference. */
         bool gpu_eligible() const;
-        /** the C-ABI handle with the current mesh uploaded (re-uploaded when the mesh changed) */
-        b200cvt_handle handle();
+        /** the element tables the C-ABI takes, rebuilt only when the borrowed mesh changed */
+        struct MeshArrays {
+            std::vector<uint32_t> elems;
+            std::vector<int32_t> adj;
+            std::vector<double> weights;
+            unsigned long long quick = 0, full = 0;
+            unsigned version = 0;     /* bumped when the content changed */
+            bool valid = false;
+        };
+        /** the C-ABI handle with the current mesh uploaded. Every call checks a cheap signature of the borrowed mesh (addresses,
+         *  counts, a strided sample); full_check also hashes all of it (done once per Lloyd_iterations / Newton_iterations /
+         *  compute_RDT call). A caller that edits coordinates in place between two compute_* calls says so with mesh_modified(). */
+        b200cvt_handle handle(bool full_check = false);
+        const MeshArrays& arrays(bool full_check = false);
+        void mesh_modified();
+        /** logs the status bits a caller should hear about (neighbour cap reached, polygon budget exceeded) */
+        static void report_flags(b200cvt_handle h, index_t nb_seeds);
         /** counts the compute_* calls served by the GPU (tests) */
         index_t nb_gpu_calls() const { return nb_gpu_calls_; }
 
@@ -115,8 +131,9 @@ namespace GEO {
         b200cvt_handle h_;                   /* surfacic handle */
         b200cvt_handle h_vol_;               /* volumetric handle (created on first use) */
         bool check_SR_;
-        unsigned long long mesh_hash_, vol_hash_;
-        bool mesh_uploaded_, vol_uploaded_;
+        unsigned long long quick_signature() const;
+        MeshArrays surf_arrays_, vol_arrays_;
+        unsigned mesh_uploaded_version_, vol_uploaded_version_;
         index_t nb_gpu_calls_;
     };
 
@@ -135,8 +152,18 @@ namespace GEO {
         const unsigned* last_newton_info() const { return newton_info_; }
         /** true if the last Lloyd/Newton call ran on the GPU */
         bool last_call_on_gpu() const { return last_on_gpu_; }
+        /** number of GPUs of this process the optimisation loops use (default 1, or the environment variable B200CVT_GPUS):
+         *  more than one runs them through b200cvt_group_* — seeds sharded by Morton range, mesh replicated */
+        void set_nb_gpus(index_t n);
+        index_t nb_gpus() const { return nb_gpus_; }
     private:
         RestrictedVoronoiDiagramB200* rvd_b200();
+        b200cvt_group_handle group(RestrictedVoronoiDiagramB200* rvd);
+        bool begin_gpu_loop(index_t nb_iter, std::vector<uint8_t>& locked);
+        void end_gpu_loop(b200cvt_handle h, int status, const char* what);
+        index_t nb_gpus_;
+        b200cvt_group_handle group_;
+        unsigned group_mesh_version_;
         static int progress_trampoline(void* user, uint32_t iter, double f, double gnorm);
         bool canceled_;
         bool last_on_gpu_;
