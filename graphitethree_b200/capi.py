@@ -36,6 +36,8 @@ _SIGNATURES = {
     "b200cvt_centroids": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "b200cvt_funcgrad": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "b200cvt_rdt": (C.c_int, [C.c_void_p, _up, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "b200cvt_rdt_multinerve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _bp, _up, C.c_uint64, C.POINTER(C.c_uint64), _dp, _up,
+                                         C.c_uint64, C.POINTER(C.c_uint64)]),
     "b200cvt_get_flags": (C.c_int, [C.c_void_p, _bp]),
     "b200cvt_get_seed_energy": (C.c_int, [C.c_void_p, _dp]),
     "b200cvt_get_stats": (C.c_int, [C.c_void_p, _qp]),
@@ -180,6 +182,19 @@ class Handle:
         if n.value:
             _check(lib().b200cvt_rdt(self._h, tri.ctypes.data_as(_up), n.value, C.byref(n)))
         return tri
+
+    def rdt_multinerve(self, use_centroids=True, prefer_seeds=True, locked=None):
+        """compute_RDT with RDT_MULTINERVE (RVD.cpp:1901-2264): (triangles [n, 3], vertices [nc, dim], seed of each vertex)."""
+        lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+        lkp = None if lk is None else lk.ctypes.data_as(_bp)
+        nt, nv = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().b200cvt_rdt_multinerve(self._h, int(use_centroids), int(prefer_seeds), lkp, None, 0, C.byref(nt), None, None, 0, C.byref(nv)))
+        tri = np.empty((int(nt.value), 3), dtype=np.uint32)
+        vert = np.empty((int(nv.value), self.dim))
+        vseed = np.empty(int(nv.value), dtype=np.uint32)
+        _check(lib().b200cvt_rdt_multinerve(self._h, int(use_centroids), int(prefer_seeds), lkp, tri.ctypes.data_as(_up), nt.value,
+                                            C.byref(nt), vert.ctypes.data_as(_dp), vseed.ctypes.data_as(_up), nv.value, C.byref(nv)))
+        return tri, vert, vseed
 
     def flags(self):
         fl = np.empty(self.S, dtype=np.uint8)

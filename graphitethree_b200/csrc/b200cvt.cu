@@ -18,6 +18,7 @@
 #include "comm.cuh"
 #include "lbfgs.cuh"
 #include "rdt.cuh"
+#include "rdt_mn.cuh"
 #include "mesh_prep.cuh"
 #include "../../include/b200cvt.h"
 
@@ -277,6 +278,13 @@ struct b200cvt_ctx {
     DevBuf<int> facet_adj; bool facet_adj_valid = false;
     DevBuf<u32> rdt_dev, rdt_n;
     std::vector<u32> rdt_host; bool rdt_valid = false;
+    // multinerve RDT (rdt_mn.cuh): device scratch and the cached host result
+    DevBuf<uint8_t> mn_pair_comp, mn_comp_border;
+    DevBuf<u32> mn_ncomp, mn_comp_base, mn_vert_n, mn_tri, mn_tri_n, mn_vert_seed;
+    DevBuf<double> mn_comp_m, mn_comp_mg, mn_emb;
+    DevBuf<uint4> mn_vert;
+    std::vector<u32> mn_tri_host, mn_vseed_host; std::vector<double> mn_emb_host;
+    int mn_mode = -1; bool rdt_valid_mn = false;
     double bb_lo[3], bb_hi[3], mesh_measure = 0.0, mesh_vmax2 = 0.0;
     // seeds
     u32 S = 0;
@@ -919,7 +927,7 @@ static void upload_locked(b200cvt_ctx* h, const uint8_t* locked, u32 S) {
 }
 
 static void set_seeds_common(b200cvt_ctx* h, u32 S) {
-    h->rdt_valid = false;
+    h->rdt_valid = false; h->rdt_valid_mn = false;
     if (S != h->S) { h->pair_cap = 0; h->prev_valid = false; }
     h->S = S;
     h->has_seeds = true;
@@ -972,7 +980,7 @@ static void comm_prepare(b200cvt_ctx* h) {
 // Lloyd_iterations (geogram/voronoi/CVT.cpp:133-167) on the device-resident seeds
 static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void* user) {
     const u32 S = h->S;
-    if (nb_iter > 0) h->rdt_valid = false;      // the seeds move: a cached triangulation is stale
+    if (nb_iter > 0) h->rdt_valid = false; h->rdt_valid_mn = false;      // the seeds move: a cached triangulation is stale
     comm_prepare(h);
     for (u32 it = 0; it < nb_iter; ++it) {
         evaluate(h, 0, 0);
@@ -1149,6 +1157,133 @@ static void compute_rdt_t(b200cvt_ctx* h) {
         return;
     }
     throw CapacityError("RDT triangle list keeps overflowing");
+}
+
+// RestrictedVoronoiDiagram::compute_RDT with RDT_MULTINERVE (RVD.cpp:2338-2352) on the device (rdt_mn.cuh).
+// Result in h->mn_tri_host (rows sorted, duplicates removed), h->mn_emb_host, h->mn_vseed_host.
+template <int D>
+static void compute_rdt_mn_t(b200cvt_ctx* h, int use_centroids, int prefer_seeds, const uint8_t* locked) {
+    if (h->volumetric) throw ArgError("compute_RDT of a volumetric diagram stays on the reference implementation");
+    if (h->nranks != 1) throw StateError("the multinerve RDT needs the whole seed range (nranks == 1)");
+    if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
+    if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
+    ensure_facet_adj(h);
+    evaluate_t<D>(h, 2, 1);
+    const u32 S = h->S;
+    const u32 cap = h->pair_cap;
+    upload_locked(h, locked, S);
+    h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4);
+    h->mn_pair_comp.ensure((size_t)S * cap);
+    h->mn_ncomp.ensure((size_t)S + 1); h->mn_comp_base.ensure((size_t)S + 2);
+    h->mn_comp_m.ensure((size_t)S * MN_MAXC); h->mn_comp_mg.ensure((size_t)S * MN_MAXC * D); h->mn_comp_border.ensure((size_t)S * MN_MAXC);
+    h->mn_vert_n.ensure(1); h->mn_tri_n.ensure(1);
+    size_t vcap = std::max<size_t>(h->mn_vert.cap, (size_t)8 * S + 1024);
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        h->mn_vert.ensure(vcap);
+        vcap = std::min<size_t>(h->mn_vert.cap, 0xffffffffu);
+        CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->mn_vert_n.p, 0, sizeof(u32), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->mn_ncomp.p, 0, sizeof(u32) * ((size_t)S + 1), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->mn_pair_comp.p, 0xff, (size_t)S * cap, h->stream));
+        RdtMnArgs m;
+        memset(&m, 0, sizeof(m));
+        RdtArgs& r = m.r;
+        r.xs = h->xs.p; r.nbr = h->nbr.p; r.nbr_n = h->nbr_n.p; r.kstride = h->kstride; r.nbr_by_slot = 0;
+        r.tri = h->tri.p; r.facet_adj = h->facet_adj.p; r.T = h->T;
+        r.pair_cnt = h->pair_cnt.p; r.pair_facet = h->pair_facet.p; r.cap = cap;
+        r.seed_list = nullptr; r.nseeds = S; r.qbegin = 0; r.S = S; r.flags = h->flags.p;
+        r.redo_list = h->redo_a.p; r.redo_n = h->redo_n.p;
+        m.pair_comp = h->mn_pair_comp.p; m.ncomp = h->mn_ncomp.p; m.comp_m = h->mn_comp_m.p; m.comp_mg = h->mn_comp_mg.p;
+        m.comp_border = h->mn_comp_border.p; m.vert = h->mn_vert.p; m.vert_cap = (u32)vcap; m.vert_n = h->mn_vert_n.p;
+        auto launch = [&](RdtMnArgs& q) {
+            if (q.r.nseeds == 0) return;
+            const size_t smem = (size_t)CLIP_WARPS * mn_warp_doubles<D>(q.r.kstride, q.r.cap) * sizeof(double);
+            if (smem > 200 * 1024) throw CapacityError("candidate rows too long for the multinerve RDT kernel");
+            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(rdt_mn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(h, rdt_mn_kernel<D>, div_up(q.r.nseeds, CLIP_WARPS), CLIP_WARPS * 32, smem, q);
+        };
+        launch(m);
+        // enlarge_neighborhood (generic_RVD.h:2183-2197), batched over the seeds that need it
+        u32 kbig = 40;
+        u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
+        int cur_slot = 0;
+        for (;;) {
+            u32 nredo = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            if (nredo == 0) break;
+            kbig = std::min<u32>(std::min<u32>(kbig, B200CVT_KMAX), S - 1);
+            h->nbr_big.ensure((size_t)nredo * kbig);
+            h->nbr_big_n.ensure(nredo);
+            KnnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
+            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
+            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+            launch_knn<D>(h, a, nredo);
+            const int nslot = cur_slot ^ 1;
+            CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
+            RdtMnArgs mm = m;
+            mm.r.nbr = h->nbr_big.p; mm.r.nbr_n = h->nbr_big_n.p; mm.r.kstride = kbig; mm.r.nbr_by_slot = 1;
+            mm.r.seed_list = cur_list; mm.r.nseeds = nredo;
+            mm.r.redo_list = nxt_list; mm.r.redo_n = h->redo_n.p + nslot;
+            launch(mm);
+            std::swap(cur_list, nxt_list);
+            cur_slot = nslot;
+            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) break;
+            kbig *= 2;
+        }
+        u32 nvtx = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&nvtx, h->mn_vert_n.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (nvtx > vcap) { vcap = (size_t)nvtx + nvtx / 8 + 1024; continue; }
+        // component numbering: by original seed index, then by smallest facet inside the cell
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->mn_ncomp.p, h->mn_comp_base.p, (int)S + 1, h->stream);
+        h->cub_tmp.ensure(scan_bytes);
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, scan_bytes, h->mn_ncomp.p, h->mn_comp_base.p, (int)S + 1, h->stream));
+        h->launches += 1;
+        u32 ncomp_total = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&ncomp_total, h->mn_comp_base.p + S, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->mn_tri.ensure(std::max<size_t>((size_t)nvtx * 3, 3));
+        h->mn_emb.ensure(std::max<size_t>((size_t)ncomp_total * D, 1)); h->mn_vert_seed.ensure(std::max<size_t>(ncomp_total, 1));
+        CUDA_CHECK(cudaMemsetAsync(h->mn_tri_n.p, 0, sizeof(u32), h->stream));
+        if (nvtx > 0) {
+            MnTriArgs t;
+            memset(&t, 0, sizeof(t));
+            t.vert = h->mn_vert.p; t.vert_n = h->mn_vert_n.p; t.vert_cap = (u32)vcap; t.xs = h->xs.p; t.rank_of = h->rank_of.p;
+            t.pair_cnt = h->pair_cnt.p; t.pair_facet = h->pair_facet.p; t.pair_comp = h->mn_pair_comp.p; t.cap = cap;
+            t.comp_base = h->mn_comp_base.p; t.out_tri = h->mn_tri.p; t.out_cap = nvtx; t.out_n = h->mn_tri_n.p;
+            LAUNCH(h, mn_triangles_kernel<D>, std::min<u32>(div_up(nvtx, 128), (u32)h->num_sms * 16u), 128, 0, t);
+        }
+        LAUNCH(h, mn_embedding_kernel<D>, div_up(S, 128), 128, 0, h->xs.p, h->rank_of.p, S, h->mn_ncomp.p, h->mn_comp_base.p,
+               h->mn_comp_m.p, h->mn_comp_mg.p, h->mn_comp_border.p, locked ? h->locked.p : (const uint8_t*)nullptr,
+               use_centroids, prefer_seeds, h->mn_emb.p, h->mn_vert_seed.p);
+        u32 ntri = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&ntri, h->mn_tri_n.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->mn_tri_host.resize((size_t)ntri * 3);
+        h->mn_emb_host.resize((size_t)ncomp_total * D); h->mn_vseed_host.resize(ncomp_total);
+        if (ntri) CUDA_CHECK(cudaMemcpy(h->mn_tri_host.data(), h->mn_tri.p, sizeof(u32) * 3 * (size_t)ntri, cudaMemcpyDeviceToHost));
+        if (ncomp_total) {
+            CUDA_CHECK(cudaMemcpy(h->mn_emb_host.data(), h->mn_emb.p, sizeof(double) * (size_t)ncomp_total * D, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(h->mn_vseed_host.data(), h->mn_vert_seed.p, sizeof(u32) * ncomp_total, cudaMemcpyDeviceToHost));
+        }
+        // every restricted Voronoi vertex is reported by each of its (up to three) cells: sort, drop the copies
+        struct T3 { u32 a, b, c; };
+        T3* t = reinterpret_cast<T3*>(h->mn_tri_host.data());
+        auto less = [](const T3& x, const T3& y) { return x.a != y.a ? x.a < y.a : (x.b != y.b ? x.b < y.b : x.c < y.c); };
+        std::sort(t, t + ntri, less);
+        T3* e = std::unique(t, t + ntri, [](const T3& x, const T3& y) { return x.a == y.a && x.b == y.b && x.c == y.c; });
+        h->mn_tri_host.resize((size_t)(e - t) * 3);
+        scatter_results(h, false, false, false);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->has_results = true; h->has_energy = false;
+        return;
+    }
+    throw CapacityError("restricted Voronoi vertex list keeps overflowing");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1354,7 +1489,7 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             }
             for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[perm[i]];
         }
-        h->host_elems.clear(); h->host_perm.clear(); h->host_adj.clear(); h->facet_adj_valid = false; h->rdt_valid = false;
+        h->host_elems.clear(); h->host_perm.clear(); h->host_adj.clear(); h->facet_adj_valid = false; h->rdt_valid = false; h->rdt_valid_mn = false;
         if (!h->volumetric) {
             h->host_elems.assign(elems, elems + (size_t)ne * 3);
             h->host_perm = perm;
@@ -1404,6 +1539,29 @@ int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uin
         *n_out = n;
         if (tri_out && cap_triangles > 0)
             memcpy(tri_out, h->rdt_host.data(), sizeof(u32) * 3 * (size_t)std::min<uint64_t>(n, cap_triangles));
+    });
+}
+
+int b200cvt_rdt_multinerve(b200cvt_handle h, int use_rvc_centroids, int prefer_seeds, const uint8_t* locked,
+                           uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_tri,
+                           double* vertices_out, uint32_t* vertex_seed_out, uint64_t cap_vertices, uint64_t* n_vertices) {
+    return guarded([&] {
+        if (!h || !n_tri || !n_vertices) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        const int mode = (use_rvc_centroids ? 1 : 0) | (prefer_seeds ? 2 : 0) | (locked ? 4 : 0);
+        // a call without output buffers (or the first call) computes; a call with buffers copies what the last one computed
+        if (!tri_out || h->mn_mode != mode || !h->rdt_valid_mn) {
+            if (h->dim == 3) compute_rdt_mn_t<3>(h, use_rvc_centroids, prefer_seeds, locked);
+            else compute_rdt_mn_t<6>(h, use_rvc_centroids, prefer_seeds, locked);
+            h->mn_mode = mode; h->rdt_valid_mn = true;
+        }
+        const uint64_t nt = h->mn_tri_host.size() / 3, nv = h->mn_vseed_host.size();
+        *n_tri = nt; *n_vertices = nv;
+        if (tri_out && cap_triangles > 0) memcpy(tri_out, h->mn_tri_host.data(), sizeof(u32) * 3 * (size_t)std::min<uint64_t>(nt, cap_triangles));
+        if (vertices_out && cap_vertices > 0)
+            memcpy(vertices_out, h->mn_emb_host.data(), sizeof(double) * h->dim * (size_t)std::min<uint64_t>(nv, cap_vertices));
+        if (vertex_seed_out && cap_vertices > 0)
+            memcpy(vertex_seed_out, h->mn_vseed_host.data(), sizeof(u32) * (size_t)std::min<uint64_t>(nv, cap_vertices));
     });
 }
 
@@ -1571,7 +1729,7 @@ int b200cvt_set_partition(b200cvt_handle h, uint32_t rank, uint32_t nranks) {
         if (!h) throw ArgError("null handle");
         if (nranks == 0 || rank >= nranks) throw ArgError("bad partition");
         h->rank = rank; h->nranks = nranks;
-        h->knn_valid = false; h->has_results = false; h->rdt_valid = false;
+        h->knn_valid = false; h->has_results = false; h->rdt_valid = false; h->rdt_valid_mn = false;
     });
 }
 
@@ -1716,7 +1874,7 @@ static void comm_finish(b200cvt_ctx* h, u32 rank, u32 nranks, PeerBox** peers) {
     for (u32 p = 0; p < nranks; ++p) h->pc.boxes[p] = peers[p];
     h->pc.seq = h->pc_seq.p; h->pc.gtot = h->pc_gtot.p; h->pc.error = h->pc_err.p;
     h->rank = rank; h->nranks = nranks; h->has_comm = true;
-    h->knn_valid = false; h->has_results = false; h->rdt_valid = false; h->prev_valid = false;
+    h->knn_valid = false; h->has_results = false; h->rdt_valid = false; h->rdt_valid_mn = false; h->prev_valid = false;
 }
 
 static void comm_release(b200cvt_ctx* h) {

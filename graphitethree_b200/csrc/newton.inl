@@ -74,7 +74,7 @@ static void newton_gather_seeds(b200cvt_ctx* h) {
 static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb cb, void* user, uint32_t* info_out) {
     if (m > LBFGS_MAXM) throw ArgError("m too large");
     if (nb_iter < 1) return;                 // HLBFGS: INFO[4] < 1 -> "check your input parameters", no work
-    h->rdt_valid = false;                    // the seeds move: a cached triangulation is stale
+    h->rdt_valid = false; h->rdt_valid_mn = false;                    // the seeds move: a cached triangulation is stale
     const int D = h->dim;
     const u32 S = h->S;
     const u32 N_global = S * (u32)D;

@@ -110,6 +110,20 @@ int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_
  * Needs the facet adjacency: the one given to b200cvt_set_mesh, else it is rebuilt from shared edges. */
 int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_out);
 
+/* Replaces: RestrictedVoronoiDiagram::compute_RDT with RDT_MULTINERVE (| RDT_RVC_CENTROIDS | RDT_PREFER_SEEDS), the mode
+ * CentroidalVoronoiTesselation::compute_surface asks for by default (G/voronoi/CVT.cpp:180-197; remesh:multi_nerve,
+ * remesh:RVC_centroids) — GetConnectedComponentsPrimalTriangles, G/voronoi/RVD.cpp:1901-2264, over
+ * compute_surfacic_with_cnx_priority, G/voronoi/generic_RVD.h:1856-2001; check_SR = true. One vertex per connected
+ * component of every restricted Voronoi cell, one triangle (3 vertex indices) per restricted Voronoi vertex.
+ * vertices_out: n_vertices x dim positions (seed, or centroid of the component: RVD.cpp:2195-2237, 2123-2146);
+ * vertex_seed_out (optional): the original seed index of every vertex. The reference numbers vertices and orders rows by
+ * its sequential traversal; here vertices are numbered by (seed, smallest facet of the component) and rows are sorted,
+ * duplicates removed (the reference leaves that to mesh_postprocess_RDT). RDT_SELECT_NEAREST / RDT_PROJECT_ON_SURFACE
+ * stay on the reference. Call with tri_out = NULL to compute and get the counts, then with buffers. */
+int b200cvt_rdt_multinerve(b200cvt_handle h, int use_rvc_centroids, int prefer_seeds, const uint8_t* locked_or_null,
+                           uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_tri,
+                           double* vertices_out, uint32_t* vertex_seed_out_or_null, uint64_t cap_vertices, uint64_t* n_vertices);
+
 int b200cvt_get_flags(b200cvt_handle h, uint8_t* flags_out);
 int b200cvt_get_seed_energy(b200cvt_handle h, double* f_seed_out);
 int b200cvt_get_stats(b200cvt_handle h, uint64_t* stats_out /* 16 entries, see b200cvt.cu */);

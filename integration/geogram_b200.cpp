@@ -405,10 +405,38 @@ namespace GEO {
     void RestrictedVoronoiDiagramB200::compute_RDT(
         vector<index_t>& simplices, vector<double>& embedding, RDTMode mode, const vector<bool>& seed_is_locked, MeshFacetsAABB* AABB
     ) {
-        /* simple mode (RVD.cpp:2353-2370) with check_SR = true, as compute_surface asks for it (CVT.cpp:194): on the device.
-         * Multinerve / RVC-centroid modes walk connected components of the cells on the host: reference implementation. */
-        if(volumetric_ || !gpu_eligible() || mode != RDTMode(0) || !check_SR_) {
+        /* On the device: the simple mode (RVD.cpp:2353-2370) and the multinerve mode with or without RVC centroids / seed
+         * preference (RVD.cpp:1901-2264) — the one CentroidalVoronoiTesselation::compute_surface takes by default — both with
+         * check_SR = true as compute_surface sets it (CVT.cpp:194). RDT_SELECT_NEAREST / RDT_PROJECT_ON_SURFACE need the AABB
+         * tree of the input surface: reference implementation. */
+        const bool multinerve = (mode & RDT_MULTINERVE) != 0;
+        const bool needs_aabb = (mode & (RDT_SELECT_NEAREST | RDT_PROJECT_ON_SURFACE)) != 0;
+        if(volumetric_ || !gpu_eligible() || !check_SR_ || needs_aabb || (!multinerve && mode != RDTMode(0))) {
             ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
+            return;
+        }
+        if(multinerve) {
+            handle(true);
+            upload_seeds();
+            const index_t nb = delaunay_->nb_vertices();
+            std::vector<uint8_t> locked;
+            if(seed_is_locked.size() != 0) {
+                locked.resize(nb);
+                for(index_t i = 0; i < nb; ++i) {
+                    locked[i] = seed_is_locked[i] ? 1 : 0;
+                }
+            }
+            const int centroids = (mode & RDT_RVC_CENTROIDS) ? 1 : 0, prefer = (mode & RDT_PREFER_SEEDS) ? 1 : 0;
+            uint64_t nt = 0, nv = 0;
+            check(b200cvt_rdt_multinerve(h_, centroids, prefer, locked.empty() ? nullptr : locked.data(), nullptr, 0, &nt,
+                                         nullptr, nullptr, 0, &nv), "b200cvt_rdt_multinerve");
+            std::vector<uint32_t> tri(size_t(nt) * 3);
+            embedding.resize(size_t(nv) * dimension_);
+            check(b200cvt_rdt_multinerve(h_, centroids, prefer, locked.empty() ? nullptr : locked.data(), tri.data(), nt, &nt,
+                                         embedding.data(), nullptr, nv, &nv), "b200cvt_rdt_multinerve");
+            simplices.assign(tri.begin(), tri.end());
+            report_flags(h_, nb);
+            ++nb_gpu_calls_;
             return;
         }
         handle(true);

@@ -1145,6 +1145,226 @@ int orc_rdt(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int32_
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Multinerve RDT: connected components of the restricted Voronoi cells       */
+/* ------------------------------------------------------------------------- */
+
+/* FacetSeedMarking (generic_RVD.h): (facet, seed) -> connected component, here an open-addressing table */
+typedef struct { u64* key; u32* val; u64 cap, n; } orc_fsmap;
+static void fsmap_init(orc_fsmap* M, u64 cap) {
+    M->cap = 64; while (M->cap < 2 * cap) M->cap <<= 1;
+    M->key = (u64*)malloc(sizeof(u64) * M->cap); M->val = (u32*)malloc(sizeof(u32) * M->cap);
+    memset(M->key, 0xff, sizeof(u64) * M->cap); M->n = 0;
+}
+static void fsmap_grow(orc_fsmap* M);
+static u64 fsmap_slot(const orc_fsmap* M, u64 k) {
+    u64 h = (k * 0x9E3779B97F4A7C15ull) >> 17;
+    u64 i = h & (M->cap - 1);
+    while (M->key[i] != ~0ull && M->key[i] != k) i = (i + 1) & (M->cap - 1);
+    return i;
+}
+static int fsmap_get(const orc_fsmap* M, u32 f, u32 s, u32* val) {
+    u64 k = ((u64)f << 32) | s, i = fsmap_slot(M, k);
+    if (M->key[i] != k) return 0;
+    if (val) *val = M->val[i];
+    return 1;
+}
+static void fsmap_put(orc_fsmap* M, u32 f, u32 s, u32 val) {
+    if (2 * (M->n + 1) > M->cap) fsmap_grow(M);
+    u64 k = ((u64)f << 32) | s, i = fsmap_slot(M, k);
+    if (M->key[i] != k) { M->key[i] = k; M->n++; }
+    M->val[i] = val;
+}
+static void fsmap_grow(orc_fsmap* M) {
+    orc_fsmap N; fsmap_init(&N, M->cap);
+    for (u64 i = 0; i < M->cap; ++i) if (M->key[i] != ~0ull) { u64 j = fsmap_slot(&N, M->key[i]); N.key[j] = M->key[i]; N.val[j] = M->val[i]; N.n++; }
+    free(M->key); free(M->val); *M = N;
+}
+
+/* GetConnectedComponentsPrimalTriangles (G/voronoi/RVD.cpp:1901-2264) without RDT_SELECT_NEAREST / RDT_PROJECT_ON_SURFACE
+ * (CentroidalVoronoiTesselation::compute_surface never sets them, CVT.cpp:180-197) */
+#define ORC_UNINITIALIZED 0xffffffffu
+#define ORC_MULTI_COMP 0xfffffffeu
+#define ORC_ON_BORDER 0xfffffffdu
+typedef struct {
+    int dim, use_centroids, prefer_seeds;
+    const uint8_t* locked;
+    u32* tri; u64 tri_cap, tri_n;
+    double* vert; u64 vert_cap;          /* rows of dim doubles */
+    u32* vert_seed;                       /* optional: seed of every vertex */
+    double m; u32 cur_seed, cur_vertex; int on_border;
+    u32* seed_to_vertex;
+} orc_mn;
+
+static void mn_end_component(orc_mn* A, const orc_rvd* R) {                    /* RVD.cpp:2195-2237 */
+    const int dim = A->dim;
+    if (A->cur_vertex < A->vert_cap) {
+        double* v = A->vert + (size_t)A->cur_vertex * dim;
+        if (!A->use_centroids || (A->locked && A->locked[A->cur_seed]) || A->on_border)
+            memcpy(v, R->x + (size_t)A->cur_seed * dim, sizeof(double) * dim);
+        else {
+            double scal = (A->m < 1e-30 ? 0.0 : 1.0 / A->m);
+            for (int c = 0; c < dim; ++c) v[c] *= scal;
+        }
+        if (A->vert_seed) A->vert_seed[A->cur_vertex] = A->cur_seed;
+    }
+    if (A->prefer_seeds) {
+        if (A->on_border) A->seed_to_vertex[A->cur_seed] = ORC_ON_BORDER;
+        switch (A->seed_to_vertex[A->cur_seed]) {
+        case ORC_UNINITIALIZED: A->seed_to_vertex[A->cur_seed] = A->cur_vertex; break;
+        case ORC_ON_BORDER: break;
+        default: A->seed_to_vertex[A->cur_seed] = ORC_MULTI_COMP; break;
+        }
+    }
+    A->cur_vertex++;
+}
+
+static void mn_action(orc_mn* A, const orc_rvd* R, u32 s1, u32 cf, const orc_polygon* P, int changed, u32 cc, const orc_fsmap* visited) {
+    const int dim = A->dim;
+    (void)cf;
+    if (changed) {                                                               /* RVD.cpp:1961-1967 */
+        if (A->cur_seed != 0xffffffffu) mn_end_component(A, R);
+        A->cur_seed = s1;                                                        /* begin_connected_component, :2180-2190 */
+        if (A->cur_vertex < A->vert_cap) memset(A->vert + (size_t)A->cur_vertex * dim, 0, sizeof(double) * dim);
+        A->m = 0.0; A->on_border = 0;
+    }
+    if (A->prefer_seeds && !A->on_border) {                                     /* :1969-1986 */
+        for (int i = 0; i < P->n; ++i) {
+            int j = (i + 1) % P->n;
+            if (P->v[i].adj_facet == -1 && P->v[j].adj_seed == -1) { A->on_border = 1; break; }
+        }
+    }
+    for (int i = 1; i + 1 < P->n; ++i) {                                        /* :1988-2006 */
+        double cur_m = triangle_area(P->v[0].p, P->v[i].p, P->v[i + 1].p, dim);
+        if (A->cur_vertex < A->vert_cap) {
+            double* v = A->vert + (size_t)A->cur_vertex * dim;
+            for (int c = 0; c < dim; ++c) v[c] += cur_m / 3.0 * (P->v[0].p[c] + P->v[i].p[c] + P->v[i + 1].p[c]);
+        }
+        A->m += cur_m;
+    }
+    for (int i = 0; i < P->n; ++i) {                                            /* :2017-2039 */
+        const orc_vertex* ve = &P->v[i];
+        int nbis = 0, nfac = 0;
+        for (int q = 0; q < ve->nsym && q < 3; ++q) { nbis += ve->sym[q] > 0; nfac += ve->sym[q] < 0; }
+        if (nbis == 2 && nfac >= 1) {
+            int top = (ve->nsym < 3 ? ve->nsym : 3) - 1;
+            u32 s2 = (u32)(ve->sym[top] - 1), s3 = (u32)(ve->sym[top - 1] - 1);
+            u32 f = (u32)(-ve->sym[0] - 1);                                      /* boundary_facet(0) */
+            u32 v2, v3;
+            if (fsmap_get(visited, f, s2, &v2) && fsmap_get(visited, f, s3, &v3)) {
+                if (A->tri_n < A->tri_cap) { u32* o = A->tri + 3 * A->tri_n; o[0] = cc; o[1] = v2; o[2] = v3; }
+                A->tri_n++;
+            }
+        }
+    }
+}
+
+/* compute_surfacic_with_cnx_priority (G/voronoi/generic_RVD.h:1856-2001) driving the action above, then the tail of the
+ * action's destructor (RVD.cpp:2050-2146, prefer-seeds branch). Outputs in the reference's own order: triangles as emitted
+ * (duplicates included), one vertex per connected component in order of discovery. */
+int orc_rdt_multinerve(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int32_t* adj, u32 S, const double* x,
+                       u32 k, u32 kcap, int use_centroids, int prefer_seeds, const uint8_t* locked,
+                       u32* tri_out, u64 tri_cap, u64* ntri_out, double* vert_out, u32* vert_seed_out, u64 vert_cap, u64* nvert_out) {
+    if (dim > ORC_MAXDIM || orc_volumetric_mode) return 1;
+    orc_rvd Rv; orc_rvd* R = &Rv;
+    uint8_t* fl = (uint8_t*)calloc(S ? S : 1, 1);
+    rvd_init(R, dim, nv, V, nt, T, adj, NULL, S, x, k, kcap, NULL, 1, fl);
+    orc_symbolic = 1;
+    orc_mn A;
+    memset(&A, 0, sizeof(A));
+    A.dim = dim; A.use_centroids = use_centroids; A.prefer_seeds = prefer_seeds; A.locked = locked;
+    A.tri = tri_out; A.tri_cap = tri_cap; A.vert = vert_out; A.vert_cap = vert_cap; A.vert_seed = vert_seed_out;
+    A.cur_seed = 0xffffffffu;
+    A.seed_to_vertex = (u32*)malloc(sizeof(u32) * (S ? S : 1));
+    memset(A.seed_to_vertex, 0xff, sizeof(u32) * (S ? S : 1));
+
+    u32* facet_stamp = (u32*)malloc(sizeof(u32) * (nt ? nt : 1));
+    memset(facet_stamp, 0xff, sizeof(u32) * (nt ? nt : 1));
+    orc_fsmap visited; fsmap_init(&visited, (u64)nt * 2 + 64);
+    u64 dq_cap = 4096, dq_head = 0, dq_tail = 0;           /* deque<FacetSeed> as a growing array */
+    u32* dq = (u32*)malloc(sizeof(u32) * 2 * dq_cap);
+    u32 st_cap = 1024, st_n = 0;
+    u32* st = (u32*)malloc(sizeof(u32) * st_cap);
+    orc_polygon* P = (orc_polygon*)malloc(sizeof(orc_polygon) * 3);
+    u32 cc = 0;
+
+    for (u32 f = 0; f < nt; ++f) {
+        if (facet_stamp[f] != 0xffffffffu) continue;
+        u32 s0; double d0;
+        grid_knn(&R->grid, V + (size_t)T[3 * f] * dim, 1, &s0, &d0, NULL);       /* find_seed_near_facet */
+        dq_head = dq_tail = 0;
+        dq[0] = f; dq[1] = s0; dq_tail = 1;
+        while (dq_head < dq_tail) {
+            u32 cf = dq[2 * dq_head], cs = dq[2 * dq_head + 1];
+            dq_head++;
+            if (facet_stamp[cf] == cs) continue;
+            if (fsmap_get(&visited, cf, cs, NULL)) continue;
+            int changed = 1;
+            st[0] = cf; st_n = 1;
+            facet_stamp[cf] = cs;
+            while (st_n > 0) {
+                cf = st[--st_n];
+                P[0].n = 3;
+                for (int lv = 0; lv < 3; ++lv) {
+                    u32 vid = T[3 * cf + lv];
+                    memcpy(P[0].v[lv].p, V + (size_t)vid * dim, sizeof(double) * dim);
+                    P[0].v[lv].w = 1.0;
+                    P[0].v[lv].adj_facet = adj[3 * cf + lv];
+                    P[0].v[lv].adj_seed = -1;
+                    P[0].v[lv].nsym = 0;
+                }
+                for (int i1 = 0; i1 < 3; ++i1) {
+                    int i2 = (i1 + 1) % 3;
+                    orc_vertex* v2 = &P[0].v[i2];
+                    int32_t a1 = P[0].v[i1].adj_facet, a2 = v2->adj_facet;
+                    sym_insert(v2, -(int32_t)cf - 1);
+                    sym_insert(v2, -(a1 >= 0 ? a1 : (int32_t)(nt + i1)) - 1);
+                    sym_insert(v2, -(a2 >= 0 ? a2 : (int32_t)(nt + i2)) - 1);
+                }
+                int res = clip_by_cell_SR(R, cs, P);
+                const orc_polygon* Q = &P[res];
+                mn_action(&A, R, cs, cf, Q, changed, cc, &visited);
+                changed = 0;
+                int touches = 0;
+                for (int v = 0; v < Q->n; ++v) {
+                    int32_t nf = Q->v[v].adj_facet;
+                    if (nf >= 0 && (u32)nf < nt && facet_stamp[nf] != cs) {
+                        facet_stamp[nf] = cs;
+                        if (st_n == st_cap) { st_cap *= 2; st = (u32*)realloc(st, sizeof(u32) * st_cap); }
+                        st[st_n++] = (u32)nf;
+                    }
+                    int32_t ns = Q->v[v].adj_seed;
+                    if (ns != -1) {
+                        touches = 1;
+                        if (!fsmap_get(&visited, cf, (u32)ns, NULL)) {
+                            if (dq_tail == dq_cap) { dq_cap *= 2; dq = (u32*)realloc(dq, sizeof(u32) * 2 * dq_cap); }
+                            dq[2 * dq_tail] = cf; dq[2 * dq_tail + 1] = (u32)ns; dq_tail++;
+                        }
+                    }
+                }
+                if (touches) fsmap_put(&visited, cf, cs, cc);
+            }
+            ++cc;
+        }
+    }
+    if (A.cur_seed != 0xffffffffu) mn_end_component(&A, R);
+    if (A.prefer_seeds) {                                                        /* RVD.cpp:2123-2146 */
+        for (u32 s = 0; s < S; ++s) {
+            u32 v = A.seed_to_vertex[s];
+            if (v != ORC_MULTI_COMP && v != ORC_UNINITIALIZED && v != ORC_ON_BORDER && v < A.vert_cap)
+                memcpy(A.vert + (size_t)v * dim, x + (size_t)s * dim, sizeof(double) * dim);
+        }
+    }
+    orc_symbolic = 0;
+    if (ntri_out) *ntri_out = A.tri_n;
+    if (nvert_out) *nvert_out = A.cur_vertex;
+    free(A.seed_to_vertex); free(facet_stamp); free(visited.key); free(visited.val); free(dq); free(st); free(P);
+    rvd_free(R, NULL);
+    free(fl);
+    return 0;
+}
+
+
 /* CentroidalVoronoiTesselation::Lloyd_iterations — G/voronoi/CVT.cpp:133-167 */
 int orc_lloyd(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int32_t* adj,
               const double* weights, u32 S, double* x, u32 k, u32 nb_iter, const uint8_t* locked,

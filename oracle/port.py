@@ -157,6 +157,42 @@ def rdt(V, T, x, k=20, kcap=256, adj=None):
     return tri[:n.value].copy()
 
 
+def rdt_multinerve(V, T, x, use_centroids=True, prefer_seeds=True, locked=None, k=20, kcap=256, adj=None):
+    """compute_RDT with RDT_MULTINERVE (| RDT_RVC_CENTROIDS | RDT_PREFER_SEEDS), RVD.cpp:1901-2264, in the reference's own
+    order: (triangles [n, 3] of component indices as emitted, vertices [nc, dim], seed of every vertex [nc])."""
+    V, x = _f64(V), _f64(x)
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    if adj is None:
+        adj = _adjacency(T)
+    S, dim = x.shape
+    tcap, vcap = 12 * S + 64, 2 * S + 64
+    tri = np.zeros((tcap, 3), dtype=np.uint32)
+    vert = np.zeros((vcap, dim))
+    vseed = np.zeros(vcap, dtype=np.uint32)
+    nt_, nv_ = C.c_uint64(0), C.c_uint64(0)
+    lk = None if locked is None else np.ascontiguousarray(locked, dtype=np.uint8)
+    rc = _lib().orc_rdt_multinerve(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up), _p(adj, _ip),
+                                   C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(min(kcap, max(S - 1, 1))),
+                                   C.c_int(int(use_centroids)), C.c_int(int(prefer_seeds)), _p(lk, _bp),
+                                   _p(tri, _up), C.c_uint64(tcap), C.byref(nt_), _p(vert, _dp), _p(vseed, _up), C.c_uint64(vcap), C.byref(nv_))
+    assert rc == 0 and nt_.value <= tcap and nv_.value <= vcap
+    return tri[:nt_.value].copy(), vert[:nv_.value].copy(), vseed[:nv_.value].copy()
+
+
+def canonical_multinerve(tri, vert, vseed):
+    """Order-independent form of a multinerve RDT: components sorted by (seed, coordinates), triangles rotated to their
+    smallest vertex, duplicates dropped, rows sorted. The reference numbers components in traversal order."""
+    order = np.lexsort(tuple(vert[:, c] for c in range(vert.shape[1] - 1, -1, -1)) + (vseed,))
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    t = rank[tri.astype(np.int64)] if len(tri) else np.zeros((0, 3), dtype=np.int64)
+    if len(t):
+        k = np.argmin(t, axis=1)
+        t = np.stack([t[np.arange(len(t)), (k + i) % 3] for i in range(3)], 1)
+        t = np.unique(t, axis=0)
+    return t, vert[order], vseed[order]
+
+
 def lloyd(V, T, x, nb_iter, k=20, locked=None, weights=None, adj=None):
     V = _f64(V)
     x = np.array(x, dtype=np.float64, order="C", copy=True)
