@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <set>
 #include <type_traits>
 #include <vector>
@@ -99,9 +100,21 @@ namespace {
         return s;
     }
 
+    /* distinct triangles as unordered vertex triples */
+    std::set<Tri> ta_all(const vector<index_t>& tris) {
+        std::set<Tri> s;
+        for(index_t f = 0; f + 2 < tris.size(); f += 3) {
+            Tri t = {{tris[f], tris[f + 1], tris[f + 2]}};
+            std::sort(t.begin(), t.end());
+            s.insert(t);
+        }
+        return s;
+    }
+
     struct Run {
         std::vector<double> x_lloyd, x_final;
-        Mesh surface;
+        Mesh surface;          /* compute_surface(simple mode, seeds as vertices) */
+        Mesh surface_mn;       /* compute_surface as remesh_smooth calls it: multinerve + RVC centroids (CVT.cpp:180-229) */
         vector<index_t> rdt;
         double t_lloyd = 0.0, t_newton = 0.0;
         bool on_gpu = false;
@@ -134,6 +147,8 @@ namespace {
         cvt.compute_surface(&out.surface, false);
         vector<double> emb;
         cvt.RVD()->compute_RDT(out.rdt, emb, RestrictedVoronoiDiagram::RDTMode(0));
+        cvt.set_use_RVC_centroids(true);
+        cvt.compute_surface(&out.surface_mn, true);
         if constexpr (std::is_same<CVT_T, CentroidalVoronoiTesselationB200>::value) {
             out.on_gpu = cvt.last_call_on_gpu();
         }
@@ -241,7 +256,63 @@ int main(int argc, char** argv) {
         }
     }
     double diag = (ref.surface.vertices.nb() > 0) ? bbox_diagonal(ref.surface) : 0.0;
-    double h_ab = 0.0, h_ba = 0.0, h_ctrl = 0.0;
+    double h_ab = 0.0, h_ba = 0.0, h_ctrl = 0.0, h_raw_ab = 0.0, h_raw_ba = 0.0, h_mn_ab = 0.0, h_mn_ba = 0.0;
+    size_t nonmanifold_edges = 0;
+    /* A seed without any restricted Delaunay triangle stays in the remesh as an isolated vertex (assign_triangle_mesh keeps
+     * all seeds, mesh_repair does not remove them), and mesh_one_sided_Hausdorff_distance measures every vertex of a mesh
+     * without cells: one such seed puts a seed spacing into the "distance" of two identical surfaces — of the reference to
+     * itself too. They are counted (flagged) and removed before the surfaces are compared. */
+    index_t isolated_ref = 0, isolated_b200 = 0;
+    auto drop_isolated = [](Mesh& M) -> index_t {
+        const index_t before = M.vertices.nb();
+        if(before != 0 && M.facets.nb() != 0) {
+            M.vertices.remove_isolated();
+        }
+        return before - M.vertices.nb();
+    };
+    isolated_ref = drop_isolated(ref.surface);
+    isolated_b200 = drop_isolated(b200.surface);
+    drop_isolated(ref.surface_mn);
+    drop_isolated(b200.surface_mn);
+    if(!g_volumetric && !ref.rdt.empty() && !b200.rdt.empty()) {
+        /* the RAW restricted Delaunay triangulations (no mesh_repair): the north-star criterion on what the path itself
+         * produces. mesh_repair, which compute_surface runs afterwards in simple mode, resolves non-manifold edges by
+         * dropping triangles in an order that depends on the ROW order of its input (the reference's is its traversal
+         * order); those edges are counted here so that the configurations are flagged explicitly. */
+        auto soup = [&](const vector<index_t>& tris, const std::vector<double>& x, Mesh& M) {
+            vector<double> v3(size_t(S) * 3);
+            for(index_t i = 0; i < S; ++i) {
+                for(index_t c = 0; c < 3; ++c) {
+                    v3[index_t(i * 3 + c)] = x[size_t(i) * dim + c];
+                }
+            }
+            vector<index_t> t = tris;
+            M.facets.assign_triangle_mesh(3, v3, t, true);
+        };
+        Mesh A, B;
+        soup(ref.rdt, ref.x_final, A);
+        soup(b200.rdt, b200.x_final, B);
+        drop_isolated(A);
+        drop_isolated(B);
+        const double sampling = 0.01 * bbox_diagonal(A);
+        h_raw_ab = mesh_one_sided_Hausdorff_distance(A, B, sampling);
+        h_raw_ba = mesh_one_sided_Hausdorff_distance(B, A, sampling);
+        std::map<std::pair<index_t, index_t>, int> edges;
+        for(const Tri& t : ta_all(ref.rdt)) {
+            for(int e = 0; e < 3; ++e) {
+                index_t a = t[e], b = t[(e + 1) % 3];
+                ++edges[std::make_pair(std::min(a, b), std::max(a, b))];
+            }
+        }
+        for(const auto& kv : edges) {
+            nonmanifold_edges += kv.second > 2 ? 1 : 0;
+        }
+    }
+    if(ref.surface_mn.facets.nb() > 0 && b200.surface_mn.facets.nb() > 0) {
+        const double sampling = 0.01 * bbox_diagonal(ref.surface_mn);
+        h_mn_ab = mesh_one_sided_Hausdorff_distance(ref.surface_mn, b200.surface_mn, sampling);
+        h_mn_ba = mesh_one_sided_Hausdorff_distance(b200.surface_mn, ref.surface_mn, sampling);
+    }
     if(ref.surface.facets.nb() > 0 && b200.surface.facets.nb() > 0) {
         double sampling = 0.01 * diag;
         /* control: the REFERENCE's own triangles in lexicographic order instead of traversal order, through the same
@@ -266,6 +337,7 @@ int main(int argc, char** argv) {
             Mesh ctrl;
             ctrl.facets.assign_triangle_mesh(3, v3, tris, true);
             mesh_repair(ctrl, MESH_REPAIR_DEFAULT, 1e-6 * bbox_diagonal(ctrl));
+            drop_isolated(ctrl);
             h_ctrl = mesh_one_sided_Hausdorff_distance(ref.surface, ctrl, sampling);
         }
         h_ab = mesh_one_sided_Hausdorff_distance(ref.surface, b200.surface, sampling);
@@ -277,13 +349,19 @@ int main(int argc, char** argv) {
         "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
         "\"ref_vertices\": %u, \"b200_vertices\": %u, "
         "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"hausdorff_ref_to_ref_sorted\": %.3e, \"bbox_diagonal\": %.6e, "
+        "\"hausdorff_raw_rdt_ref_to_b200\": %.3e, \"hausdorff_raw_rdt_b200_to_ref\": %.3e, \"nonmanifold_edges\": %zu, \"isolated_seeds_ref\": %u, \"isolated_seeds_b200\": %u, "
+        "\"multinerve_ref_vertices\": %u, \"multinerve_b200_vertices\": %u, \"multinerve_ref_facets\": %u, \"multinerve_b200_facets\": %u, "
+        "\"hausdorff_multinerve_ref_to_b200\": %.3e, \"hausdorff_multinerve_b200_to_ref\": %.3e, "
         "\"nn_rows\": %u, \"nn_mismatch\": %u, "
         "\"t_ref_lloyd\": %.4f, \"t_ref_newton\": %.4f, \"t_b200_lloyd\": %.4f, \"t_b200_newton\": %.4f, \"ref_threads\": %u}\n",
         g_volumetric ? "true" : "false", S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
         max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
         ta.size(), tb.size(), only_ref, only_b200,
         ref.surface.vertices.nb(), b200.surface.vertices.nb(),
-        h_ab, h_ba, h_ctrl, diag, nn_rows, nn_mismatch,
+        h_ab, h_ba, h_ctrl, diag,
+        h_raw_ab, h_raw_ba, nonmanifold_edges, isolated_ref, isolated_b200,
+        ref.surface_mn.vertices.nb(), b200.surface_mn.vertices.nb(), ref.surface_mn.facets.nb(), b200.surface_mn.facets.nb(),
+        h_mn_ab, h_mn_ba, nn_rows, nn_mismatch,
         ref.t_lloyd, ref.t_newton, b200.t_lloyd, b200.t_newton, unsigned(Process::maximum_concurrent_threads())
     );
     return 0;

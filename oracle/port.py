@@ -182,7 +182,9 @@ def rdt_multinerve(V, T, x, use_centroids=True, prefer_seeds=True, locked=None, 
 def canonical_multinerve(tri, vert, vseed):
     """Order-independent form of a multinerve RDT: components sorted by (seed, coordinates), triangles rotated to their
     smallest vertex, duplicates dropped, rows sorted. The reference numbers components in traversal order."""
-    order = np.lexsort(tuple(vert[:, c] for c in range(vert.shape[1] - 1, -1, -1)) + (vseed,))
+    # (seed, coordinates rounded to 1e-6): two sides that differ by rounding noise must order the components of one seed alike
+    q = np.round(vert * 1e6)
+    order = np.lexsort(tuple(q[:, c] for c in range(vert.shape[1] - 1, -1, -1)) + (vseed,))
     rank = np.empty(len(order), dtype=np.int64)
     rank[order] = np.arange(len(order))
     t = rank[tri.astype(np.int64)] if len(tri) else np.zeros((0, 3), dtype=np.int64)

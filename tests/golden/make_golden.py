@@ -59,6 +59,23 @@ def case(V, F, X, weights=None, lloyd_iters=5, newton_iters=4):
     tri, vtx = r.rdt(0)
     out["rdt_tri"] = tri
     r.close()
+    # the mode compute_surface uses by default: RDT_MULTINERVE | RDT_RVC_CENTROIDS | RDT_PREFER_SEEDS (CVT.cpp:180-197)
+    r = fresh(out["x_lloyd"]); r.update_delaunay()
+    out["rdt_mn_tri"], out["rdt_mn_vert"] = r.rdt(7)
+    r.close()
+    return out
+
+
+def multinerve_case(V, F, X, lloyd_iters=2):
+    """A surface whose cells have several connected components (two sheets closer than the seed spacing)."""
+    out = dict(V=V, F=F, X=X)
+    r = RefCVT(V, F, multithread=False); r.set_points(X); r.lloyd(lloyd_iters)
+    out["x_lloyd"] = r.points()
+    r.close()
+    for mode in (1, 3, 7):       # multinerve with seeds / with centroids / with centroids and seed preference
+        r = RefCVT(V, F, multithread=False); r.set_points(out["x_lloyd"]); r.update_delaunay()
+        out["rdt_mn%d_tri" % mode], out["rdt_mn%d_vert" % mode] = r.rdt(mode)
+        r.close()
     return out
 
 
@@ -106,6 +123,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sphere6d_s120.npz"), **case(V6, F, shapes.sample_surface(V6, F, 120, 7)))
     V, F = shapes.trefoil_tube(48, 10)
     np.savez_compressed(os.path.join(HERE, "trefoil_s200.npz"), **case(V, F, shapes.sample_surface(V, F, 200, 9)))
+    V, F = shapes.box_surface(8, (1.0, 1.0, 0.02))
+    np.savez_compressed(os.path.join(HERE, "thinbox_multinerve_s150.npz"), **multinerve_case(V, F, shapes.sample_surface(V, F, 150, 3)))
     V, T = shapes.kuhn_cube(6)
     X = np.random.default_rng(13).random((130, 3))
     np.savez_compressed(os.path.join(HERE, "volume_cube_s130.npz"), **volume_case(V, T, X))

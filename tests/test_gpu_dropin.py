@@ -84,3 +84,25 @@ def test_dropin_volumetric_lloyd_newton(tmp_path):
     r = run_check(tmp_path, V, T, X, 0, 5, pre=3, volumetric=True)
     assert r["volumetric"] and r["on_gpu"]
     assert r["max_abs_dx_final"] <= 1e-7
+
+
+def test_dropin_c2_full_size(tmp_path):
+    """BASELINE.json configs[1] through the reference's C++ API: 2 M triangles, 200 k seeds, 10 Lloyd + 30 Newton (m = 7), both
+    arms from the sampling after two stock Lloyd iterations (no truncated cell is left there). north_star acceptance:
+    bit-exact neighbour lists, identical restricted-Delaunay triangle sets, Hausdorff <= 1e-6 of the bounding-box diagonal —
+    on the raw RDT, on the simple-mode remesh and on the remesh remesh_smooth produces by default (multinerve + RVC
+    centroids). Seeds without any RDT triangle (isolated vertices of BOTH remeshes) are the flagged configurations."""
+    import bench
+    V, F, X = bench.workload(1, False)
+    r = run_check(tmp_path, V, F, X, 10, 30, 7, pre=2)
+    assert r["on_gpu"] and r["nn_mismatch"] == 0
+    assert r["max_abs_dx_lloyd"] <= 1e-9 and r["max_abs_dx_final"] <= 1e-8
+    assert r["only_ref"] == 0 and r["only_b200"] == 0 and r["ref_triangles"] == r["b200_triangles"]
+    assert r["isolated_seeds_ref"] == r["isolated_seeds_b200"] <= 10
+    tol = 1e-6 * r["bbox_diagonal"]
+    for k in ("hausdorff_raw_rdt_ref_to_b200", "hausdorff_raw_rdt_b200_to_ref", "hausdorff_ref_to_b200", "hausdorff_b200_to_ref",
+              "hausdorff_multinerve_ref_to_b200", "hausdorff_multinerve_b200_to_ref"):
+        assert r[k] <= tol, (k, r[k], tol)
+    assert r["multinerve_ref_vertices"] == r["multinerve_b200_vertices"] and r["multinerve_ref_facets"] == r["multinerve_b200_facets"]
+    # the whole job through the adapter (mesh upload, Delaunay hand-over included) against the stock classes on this box's cores
+    assert (r["t_ref_lloyd"] + r["t_ref_newton"]) / (r["t_b200_lloyd"] + r["t_b200_newton"]) > 5.0

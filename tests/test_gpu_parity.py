@@ -23,7 +23,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("volume_")]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -623,3 +623,84 @@ def test_sharded_volumetric_two_partitions_one_gpu(built):
     assert np.array_equal(results[0][0], results[1][0])          # both ranks hold the same seeds
     assert np.abs(results[0][0] - x1).max() <= 1e-12             # and the unsharded run's
     assert results[0][1] == info
+
+
+# ---------------------------------------------------------------------------------------
+# multinerve RDT (the default mode of remesh_smooth): rdt_mn.cuh against the reference's golden rows and the oracle
+# ---------------------------------------------------------------------------------------
+def assert_same_multinerve(gpu, ref_rows, S, centroids):
+    """Order-independent comparison: the reference numbers components and orders / orients rows by its traversal."""
+    tg, vg, sg = gpu
+    tr, vr, sr = ref_rows
+    assert len(vg) == len(vr)
+    assert np.array_equal(np.bincount(sg, minlength=S), np.bincount(sr, minlength=S))      # components per seed
+    cg, cr = port.canonical_multinerve(tg, vg, sg), port.canonical_multinerve(tr, vr, sr)
+    assert np.array_equal(cg[2], cr[2])
+    assert np.abs(cg[1] - cr[1]).max() <= 1e-12 * max(1.0, np.abs(cr[1]).max())              # positions of the components
+    # components of one seed that share a position (no centroids, locked seeds, border) cannot be told apart by position:
+    # triangles are then compared through the seeds of their vertices
+    q = np.round(cr[1] * 1e6)
+    key = np.concatenate([cr[2][:, None].astype(np.float64), q], 1)
+    coincident = len(np.unique(key, axis=0)) != len(key)
+    if centroids and not coincident:
+        a = np.unique(np.sort(cg[0], axis=1), axis=0)
+        b = np.unique(np.sort(cr[0], axis=1), axis=0)
+    else:
+        a = np.unique(np.sort(sg[tg.astype(np.int64)], axis=1), axis=0)
+        b = np.unique(np.sort(sr[tr.astype(np.int64)], axis=1), axis=0)
+    assert np.array_equal(a, b)                                                              # identical triangle sets
+
+
+MN_GOLDEN = [p for p in GOLDEN if "rdt_mn_tri" in np.load(p).files]
+
+
+@pytest.mark.parametrize("path", MN_GOLDEN, ids=[os.path.basename(p) for p in MN_GOLDEN])
+def test_rdt_multinerve_against_reference_golden(built, path):
+    d = load(path)
+    V, F, x = d["V"], d["F"], d["x_lloyd"]
+    # the oracle returns the golden rows bit for bit (tests/test_oracle_cpu.py) and, in addition, the seed of every vertex
+    to, vo, so = port.rdt_multinerve(V, F, x, True, True)
+    assert np.array_equal(to, d["rdt_mn_tri"]) and np.array_equal(vo, d["rdt_mn_vert"])
+    h = capi.Handle(x.shape[1])
+    h.set_mesh(V, F)
+    h.set_seeds(x)
+    got = h.rdt_multinerve(True, True)
+    assert (h.flags() & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    h.close()
+    assert_same_multinerve(got, (to, vo, so), x.shape[0], True)
+
+
+def test_rdt_multinerve_thin_plate_components(built):
+    d = load(os.path.join(os.path.dirname(GOLDEN[0]), "thinbox_multinerve_s150.npz"))
+    V, F, x = d["V"], d["F"], d["x_lloyd"]
+    S = x.shape[0]
+    locked = np.zeros(S, dtype=np.uint8)
+    locked[::7] = 1
+    for mode, (uc, ps) in {1: (False, False), 3: (True, False), 7: (True, True)}.items():
+        to, vo, so = port.rdt_multinerve(V, F, x, uc, ps)
+        assert np.array_equal(to, d["rdt_mn%d_tri" % mode]) and np.array_equal(vo, d["rdt_mn%d_vert" % mode])
+        h = handle_for(V, F)
+        h.set_seeds(x)
+        got = h.rdt_multinerve(uc, ps)
+        assert (np.bincount(got[2], minlength=S) > 1).sum() > 50        # most cells of the thin plate have two components
+        assert_same_multinerve(got, (to, vo, so), S, uc)
+        if uc:
+            # locked seeds keep their position (RVD.cpp:2199-2203)
+            gotl = h.rdt_multinerve(uc, ps, locked=locked)
+            assert_same_multinerve(gotl, port.rdt_multinerve(V, F, x, uc, ps, locked=locked), S, True)
+            assert np.array_equal(gotl[1][locked[gotl[2]] == 1], x[gotl[2][locked[gotl[2]] == 1]])
+        h.close()
+
+
+def test_rdt_multinerve_against_oracle_raw_and_relaxed(built):
+    # a raw sampling (enlarged neighbourhoods, check_SR = true) and a relaxed one; closed genus-0 surface: 2 S - 4 triangles
+    V, F = shapes.noise_sphere(60)
+    X = shapes.sample_surface(V, F, 8000, 2)
+    xl, _ = port.lloyd(V, F, X, 2)
+    for x in (X, xl):
+        h = handle_for(V, F)
+        h.set_seeds(x)
+        got = h.rdt_multinerve(True, True)
+        h.close()
+        assert_same_multinerve(got, port.rdt_multinerve(V, F, x, True, True), 8000, True)
+    assert np.unique(np.sort(got[0], axis=1), axis=0).shape[0] == 2 * 8000 - 4

@@ -11,7 +11,7 @@ from graphitethree_b200 import shapes
 from oracle import port, ref
 
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("volume_")]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -208,3 +208,45 @@ def test_oracle_rdt_matches_live_reference():
     # closed genus-0 surface after Lloyd: 2 S - 4 distinct triangles
     t = np.unique(np.sort(port.rdt(V, F, xl).astype(np.int64), axis=1), axis=0)
     assert t.shape[0] == 2 * 2000 - 4
+
+
+# ---------------------------------------------------------------------------------------
+# multinerve RDT (RVD.cpp:1901-2264): the restatement returns the reference's own rows and vertices
+# ---------------------------------------------------------------------------------------
+MN_GOLDEN = [p for p in GOLDEN if "rdt_mn_tri" in np.load(p).files]
+
+
+@pytest.mark.parametrize("path", MN_GOLDEN, ids=[os.path.basename(p) for p in MN_GOLDEN])
+def test_oracle_multinerve_matches_reference_golden(path):
+    d = load(path)
+    tri, vert, vseed = port.rdt_multinerve(d["V"], d["F"], d["x_lloyd"], True, True)
+    assert np.array_equal(tri, d["rdt_mn_tri"])            # same rows in the reference's traversal order
+    assert np.array_equal(vert, d["rdt_mn_vert"])          # same vertices bit for bit, in order of discovery
+
+
+def test_oracle_multinerve_thin_plate_golden():
+    # two sheets closer than the seed spacing: most cells have two connected components
+    d = load(os.path.join(os.path.dirname(GOLDEN[0]), "thinbox_multinerve_s150.npz"))
+    for mode, (uc, ps) in {1: (False, False), 3: (True, False), 7: (True, True)}.items():
+        tri, vert, vseed = port.rdt_multinerve(d["V"], d["F"], d["x_lloyd"], uc, ps)
+        assert np.array_equal(tri, d["rdt_mn%d_tri" % mode])
+        assert np.array_equal(vert, d["rdt_mn%d_vert" % mode])
+        assert (np.bincount(vseed, minlength=d["X"].shape[0]) > 1).sum() > 50
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_multinerve_matches_live_reference():
+    V, F = shapes.trefoil_tube(120, 16)
+    X = shapes.sample_surface(V, F, 700, 4)
+    xl, _ = port.lloyd(V, F, X, 2)
+    for x in (X, xl):
+        for mode, (uc, ps) in {1: (False, False), 7: (True, True)}.items():
+            r = ref.RefCVT(V, F, multithread=False)
+            try:
+                r.set_points(x)
+                r.update_delaunay()
+                tri, vert = r.rdt(mode)
+            finally:
+                r.close()
+            to, vo, _ = port.rdt_multinerve(V, F, x, uc, ps)
+            assert np.array_equal(to, tri) and np.array_equal(vo, vert)
