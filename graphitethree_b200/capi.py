@@ -31,6 +31,7 @@ _SIGNATURES = {
     "b200cvt_last_error": (C.c_char_p, []),
     "b200cvt_set_mesh": (C.c_int, [C.c_void_p, _dp, C.c_uint32, C.c_uint32, _up, _ip, C.c_uint32, _dp]),
     "b200cvt_set_seeds": (C.c_int, [C.c_void_p, _dp, C.c_uint32]),
+    "b200cvt_initial_sampling": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.POINTER(C.c_int)]),
     "b200cvt_knn": (C.c_int, [C.c_void_p, C.c_uint32, _up, _up, _dp, _bp]),
     "b200cvt_nearest": (C.c_int, [C.c_void_p, _dp, C.c_uint32, _up]),
     "b200cvt_centroids": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
@@ -142,6 +143,14 @@ class Handle:
         x = _f64(x)
         self.S = x.shape[0]
         _check(lib().b200cvt_set_seeds(self._h, x.ctypes.data_as(_dp), self.S))
+
+    def initial_sampling(self, S):
+        """compute_initial_sampling (RVD.cpp:1658-1698): (seeds [S, dim], ok); the seeds become the handle's current seeds."""
+        x = np.empty((S, self.dim))
+        ok = C.c_int(1)
+        _check(lib().b200cvt_initial_sampling(self._h, S, x.ctypes.data_as(_dp), C.byref(ok)))
+        self.S = S
+        return x, bool(ok.value)
 
     def set_seeds_device(self, ptr, S):
         self.S = S

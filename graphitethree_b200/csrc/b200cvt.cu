@@ -20,6 +20,7 @@
 #include "rdt.cuh"
 #include "rdt_mn.cuh"
 #include "mesh_prep.cuh"
+#include "sampling.cuh"
 #include "../../include/b200cvt.h"
 
 #include <cub/cub.cuh>
@@ -29,6 +30,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <thread>
 #include <vector>
 
@@ -276,6 +278,7 @@ struct b200cvt_ctx {
     std::vector<u32> host_elems, host_perm;
     std::vector<int32_t> host_adj;
     DevBuf<int> facet_adj; bool facet_adj_valid = false;
+    DevBuf<u32> perm_dev, inv_perm_dev; bool perm_dev_valid = false, vol_weights_dropped = false;
     DevBuf<u32> rdt_dev, rdt_n;
     std::vector<u32> rdt_host; bool rdt_valid = false;
     // multinerve RDT (rdt_mn.cuh): device scratch and the cached host result
@@ -1394,6 +1397,7 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         const int D = h->dim;
         const int per = h->volumetric ? 4 : 3;
         // the volumetric actions ignore the "weight" attribute (RVD.cpp:420,783)
+        const double* weights_in = weights;
         if (h->volumetric) weights = nullptr;
         // On the device (mesh_prep.cuh): pass 1 validates the indices and reduces the bounding box and the total area /
         // volume; pass 2 sorts the elements in Morton order of their centroids (10 bits per axis, stable: ties keep the
@@ -1490,9 +1494,11 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             for (u32 i = 0; i < ne; ++i) inner[i] = by_elem[perm[i]];
         }
         h->host_elems.clear(); h->host_perm.clear(); h->host_adj.clear(); h->facet_adj_valid = false; h->rdt_valid = false; h->rdt_valid_mn = false;
+        h->host_perm = perm;
+        h->perm_dev_valid = false;
+        h->vol_weights_dropped = h->volumetric && weights_in != nullptr;
         if (!h->volumetric) {
             h->host_elems.assign(elems, elems + (size_t)ne * 3);
-            h->host_perm = perm;
             if (adjacency) h->host_adj.assign(adjacency, adjacency + (size_t)ne * 3);
         }
         h->nv = nv; h->T = ne; h->weighted = weights != nullptr; h->mesh_measure = measure;
@@ -1576,6 +1582,82 @@ int b200cvt_set_seeds(b200cvt_handle h, const double* x, uint32_t S) {
         set_seeds_common(h, S);
         build_grid(h);
         run_knn_main(h, 20, false, true);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int b200cvt_initial_sampling(b200cvt_handle h, uint32_t nb_points, double* x_out, int* ok_out) {
+    return guarded([&] {
+        if (!h) throw ArgError("null handle");
+        if (!h->has_mesh || h->T == 0) throw StateError("no mesh: call b200cvt_set_mesh first");
+        if (nb_points == 0) throw ArgError("no points");
+        if (h->vol_weights_dropped) throw ArgError("weighted volumetric sampling stays on the reference implementation");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        const u32 T = h->T, S = nb_points;
+        const int D = h->dim, per = h->volumetric ? 4 : 3;
+        if (!h->perm_dev_valid) {
+            std::vector<u32> inv(T);
+            for (u32 i = 0; i < T; ++i) inv[h->host_perm[i]] = i;
+            h->perm_dev.ensure(T); h->inv_perm_dev.ensure(T);
+            CUDA_CHECK(cudaMemcpyAsync(h->perm_dev.p, h->host_perm.data(), sizeof(u32) * T, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h->inv_perm_dev.p, inv.data(), sizeof(u32) * T, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            h->perm_dev_valid = true;
+        }
+        // 1. element masses in the caller's element order (device)
+        DevBuf<double> d_mass, d_lam; DevBuf<u32> d_elem;
+        d_mass.ensure(T);
+        const double* w = (h->weighted && !h->volumetric) ? h->triw.p : nullptr;
+        if (per == 4) LAUNCH(h, (sampling_mass_kernel<3, 4>), div_up(T, 256), 256, 0, h->tri.p, (const double*)nullptr, T, h->perm_dev.p, d_mass.p);
+        else if (D == 3) LAUNCH(h, (sampling_mass_kernel<3, 3>), div_up(T, 256), 256, 0, h->tri.p, w, T, h->perm_dev.p, d_mass.p);
+        else LAUNCH(h, (sampling_mass_kernel<6, 3>), div_up(T, 256), 256, 0, h->tri.p, w, T, h->perm_dev.p, d_mass.p);
+        std::vector<double> mass(T);
+        CUDA_CHECK(cudaMemcpyAsync(mass.data(), d_mass.p, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
+        // 2. the recurrences (host): mt19937_64 stream, sorted uniforms, running sum of mass / total in element order
+        std::mt19937_64 engine;                                       // Numeric::random_reset()
+        auto rnd = [&] { return std::uniform_real_distribution<double>(0, 1)(engine); };   // Numeric::random_float64()
+        std::vector<double> su(S);
+        for (u32 i = 0; i < S; ++i) su[i] = rnd();
+        std::sort(su.begin(), su.end());
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        double Atot = 0.0;
+        for (u32 t = 0; t < T; ++t) Atot += mass[t];
+        std::vector<u32> elem(S);
+        std::vector<double> lam((size_t)S * 4, 0.0);
+        u32 first_t = B200_NONE, last_t = 0, cur_t = 0;
+        double cur_s = mass[0] / Atot;
+        for (u32 i = 0; i < S; ++i) {
+            while (su[i] > cur_s && cur_t < T - 1) { cur_t++; cur_s += mass[cur_t] / Atot; }
+            if (first_t == B200_NONE) first_t = cur_t;
+            last_t = std::max(last_t, cur_t);
+            elem[i] = cur_t;
+            double* l = lam.data() + (size_t)i * 4;
+            if (per == 3) {
+                double l1 = rnd(), l2 = rnd();
+                if (l1 + l2 > 1.0) { l1 = 1.0 - l1; l2 = 1.0 - l2; }
+                const double l3 = 1.0 - l1 - l2;
+                // DIM = 3 takes the vec3 overload: the two draws weight the second and third corner (geometry.h:602-619)
+                if (D == 3) { l[0] = l3; l[1] = l1; l[2] = l2; } else { l[0] = l1; l[1] = l2; l[2] = l3; }
+            } else {
+                double ss = rnd(), tt = rnd(), uu = rnd();
+                if (ss + tt > 1.0) { ss = 1.0 - ss; tt = 1.0 - tt; }
+                if (tt + uu > 1.0) { const double tmp = uu; uu = 1.0 - ss - tt; tt = 1.0 - tmp; }
+                else if (ss + tt + uu > 1.0) { const double tmp = uu; uu = ss + tt + uu - 1.0; ss = 1.0 - tt - tmp; }
+                l[0] = 1.0 - ss - tt - uu; l[1] = ss; l[2] = tt; l[3] = uu;
+            }
+        }
+        if (ok_out) *ok_out = (T > 1 && last_t == first_t) ? 0 : 1;
+        // 3. the sample points (device), written into the seed array of the handle
+        d_elem.ensure(S); d_lam.ensure((size_t)S * 4);
+        CUDA_CHECK(cudaMemcpyAsync(d_elem.p, elem.data(), sizeof(u32) * S, cudaMemcpyHostToDevice, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_lam.p, lam.data(), sizeof(double) * (size_t)S * 4, cudaMemcpyHostToDevice, h->stream));
+        h->x.ensure(std::max<size_t>((size_t)S * D, (size_t)h->slice_len() * h->nranks * D));
+        if (per == 4) LAUNCH(h, (sampling_points_kernel<3, 4>), div_up(S, 256), 256, 0, h->tri.p, h->inv_perm_dev.p, d_elem.p, d_lam.p, S, h->x.p);
+        else if (D == 3) LAUNCH(h, (sampling_points_kernel<3, 3>), div_up(S, 256), 256, 0, h->tri.p, h->inv_perm_dev.p, d_elem.p, d_lam.p, S, h->x.p);
+        else LAUNCH(h, (sampling_points_kernel<6, 3>), div_up(S, 256), 256, 0, h->tri.p, h->inv_perm_dev.p, d_elem.p, d_lam.p, S, h->x.p);
+        if (S != h->S && h->facet_guess.p) LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)h->T, B200_NONE);
+        set_seeds_common(h, S);
+        if (x_out) CUDA_CHECK(cudaMemcpyAsync(x_out, h->x.p, sizeof(double) * (size_t)S * D, cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });
 }

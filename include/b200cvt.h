@@ -76,6 +76,15 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
  * at its current (sticky) size, default 20 (delaunay_nn.cpp:49, G/delaunay/delaunay.cpp:259-274). */
 int b200cvt_set_seeds(b200cvt_handle h, const double* x, uint32_t S);
 
+/* Replaces: RestrictedVoronoiDiagram::compute_initial_sampling (G/voronoi/RVD.h:193-207) = compute_initial_sampling_on_surface /
+ * _in_volume (G/voronoi/RVD.cpp:1658-1698) = mesh_generate_random_samples_on_surface / _in_volume
+ * (G/mesh/mesh_sampling.h:119-199, 280-360) on the mesh of the handle: nb_points seeds, the reference's own points bit for
+ * bit (same mt19937_64 stream, same element order, same arithmetic; the reference's multithreaded create_threads() reorders
+ * the caller's mesh first — this path never does, so the match is with the reference on the mesh as given). The seeds become
+ * the handle's current seeds (as b200cvt_set_seeds_device) and are copied to x_out (nb_points x dim, may be NULL).
+ * *ok_out (optional) = 0 when every sample fell into one element (the reference returns false and warns), 1 otherwise. */
+int b200cvt_initial_sampling(b200cvt_handle h, uint32_t nb_points, double* x_out, int* ok_out);
+
 /* Replaces: Delaunay::get_neighbors over all seeds (G/delaunay/delaunay.h:477-484) after a
  * set_vertices with k stored neighbours: idx_out is S x k (original seed indices, ascending
  * distance, padded with 0xffffffff), count_out is S, sqdist_out (optional) S x k squared

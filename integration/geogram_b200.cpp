@@ -366,12 +366,52 @@ namespace GEO {
 
     /* ---- everything off the hot path: the unmodified reference ---- */
 
+    /* the initial sampling runs on the device when the optimisation loops would: whole element range, simplices, dimension 3
+     * or 6 (volumes: dimension 3, no vertex weights). It does not need the Delaunay object. */
+    bool RestrictedVoronoiDiagramB200::sampling_eligible() const {
+        if(h_ == nullptr) {
+            return false;
+        }
+        if(volumetric_) {
+            const bool whole_cells = (tets_begin_ == NO_INDEX && tets_end_ == NO_INDEX) ||
+                (tets_begin_ == 0 && tets_end_ == mesh_->cells.nb());
+            return dimension_ == 3 && mesh_->cells.nb() > 0 && mesh_->cells.are_simplices() && whole_cells && !has_weights_;
+        }
+        const bool whole_mesh = (facets_begin_ == NO_INDEX && facets_end_ == NO_INDEX) ||
+            (facets_begin_ == 0 && facets_end_ == mesh_->facets.nb());
+        return mesh_->facets.nb() > 0 && mesh_->facets.are_simplices() && whole_mesh;
+    }
+
     bool RestrictedVoronoiDiagramB200::compute_initial_sampling_on_surface(double* p, index_t nb_points, bool verbose) {
-        return ref_->compute_initial_sampling_on_surface(p, nb_points, verbose);
+        if(volumetric_ || !sampling_eligible() || nb_points == 0) {
+            return ref_->compute_initial_sampling_on_surface(p, nb_points, verbose);
+        }
+        if(verbose) {
+            Logger::out("RVD") << "Computing initial sampling on surface (B200), using dimension=" << index_t(dimension_) << std::endl;
+        }
+        int ok = 1;
+        check(b200cvt_initial_sampling(handle(true), nb_points, p, &ok), "b200cvt_initial_sampling");
+        if(ok == 0) {
+            Logger::warn("Sampler") << "Did put all the points in the same triangle" << std::endl;
+        }
+        ++nb_gpu_calls_;
+        return ok != 0;
     }
 
     bool RestrictedVoronoiDiagramB200::compute_initial_sampling_in_volume(double* p, index_t nb_points, bool verbose) {
-        return ref_->compute_initial_sampling_in_volume(p, nb_points, verbose);
+        if(!volumetric_ || !sampling_eligible() || nb_points == 0) {
+            return ref_->compute_initial_sampling_in_volume(p, nb_points, verbose);
+        }
+        if(verbose) {
+            Logger::out("RVD") << "Computing initial sampling in volume (B200), using dimension=" << index_t(dimension_) << std::endl;
+        }
+        int ok = 1;
+        check(b200cvt_initial_sampling(handle(true), nb_points, p, &ok), "b200cvt_initial_sampling");
+        if(ok == 0) {
+            Logger::warn("Sampler") << "Did put all the points in the same tetrahedron" << std::endl;
+        }
+        ++nb_gpu_calls_;
+        return ok != 0;
     }
 
     void RestrictedVoronoiDiagramB200::compute_centroids_in_volume(double* mg, double* m) {

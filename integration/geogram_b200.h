@@ -73,6 +73,8 @@ namespace GEO {
          *  triangulated surface, whole facet range) or volumetric mode (dimension 3, tetrahedral cells, whole tet range);
          *  otherwise the call is delegated to the reference. */
         bool gpu_eligible() const;
+        /** true if the GPU path takes the next compute_initial_sampling call */
+        bool sampling_eligible() const;
         /** the element tables the C-ABI takes, rebuilt only when the borrowed mesh changed */
         struct MeshArrays {
             std::vector<uint32_t> elems;

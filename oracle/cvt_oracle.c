@@ -1714,3 +1714,117 @@ int orc_newton(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int
     free(C.ksize);
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* Initial sampling: compute_initial_sampling_on_surface / _in_volume          */
+/* G/voronoi/RVD.cpp:1658-1698 -> G/mesh/mesh_sampling.h:119-199, 280-360       */
+/* ------------------------------------------------------------------------- */
+
+/* std::mt19937_64, default seed 5489 (Numeric::random_reset, G/basic/numeric.cpp:71-73) */
+typedef struct { u64 mt[312]; int idx; } orc_mt64;
+static void mt64_seed(orc_mt64* g, u64 seed) {
+    g->mt[0] = seed;
+    for (int i = 1; i < 312; ++i) g->mt[i] = 6364136223846793005ull * (g->mt[i - 1] ^ (g->mt[i - 1] >> 62)) + (u64)i;
+    g->idx = 312;
+}
+static u64 mt64_next(orc_mt64* g) {
+    if (g->idx >= 312) {
+        for (int i = 0; i < 312; ++i) {
+            u64 x = (g->mt[i] & 0xFFFFFFFF80000000ull) | (g->mt[(i + 1) % 312] & 0x7FFFFFFFull);
+            u64 xa = x >> 1;
+            if (x & 1ull) xa ^= 0xB5026F5AA96619E9ull;
+            g->mt[i] = g->mt[(i + 156) % 312] ^ xa;
+        }
+        g->idx = 0;
+    }
+    u64 y = g->mt[g->idx++];
+    y ^= (y >> 29) & 0x5555555555555555ull;
+    y ^= (y << 17) & 0x71D67FFFEDA60000ull;
+    y ^= (y << 37) & 0xFFF7EEE000000000ull;
+    y ^= y >> 43;
+    return y;
+}
+/* Numeric::random_float64 = std::uniform_real_distribution<double>(0, 1) over mt19937_64 (libstdc++ generate_canonical:
+ * one draw, double(x) / 2^64, clamped below 1) */
+static double mt64_float64(orc_mt64* g) {
+    double r = (double)mt64_next(g) * 0x1p-64;
+    if (r >= 1.0) r = nextafter(1.0, 0.0);
+    return r;
+}
+static int cmp_double(const void* a, const void* b) { double x = *(const double*)a, y = *(const double*)b; return (x > y) - (x < y); }
+
+/* mesh_facet_mass<DIM> (mesh_sampling.h:67-96): Geom::triangle_area — the vec3 overload for DIM = 3 (cross product,
+ * G/basic/geometry.h:346-372), Heron otherwise (geometry_nd.h:143-156) — or Geom::triangle_mass with vertex weights
+ * (geometry_nd.h:237-252: a template defined before geometry.h's vec3 overload is declared, so its qualified call
+ * resolves to the Heron template in every dimension). The two area formulas agree to rounding; no test input separates them. */
+static double sampling_facet_mass(const double* p1, const double* p2, const double* p3, int dim, const double* w3) {
+    double area;
+    if (dim == 3 && !w3) {
+        double Ux = p2[0] - p1[0], Uy = p2[1] - p1[1], Uz = p2[2] - p1[2];
+        double Vx = p3[0] - p1[0], Vy = p3[1] - p1[1], Vz = p3[2] - p1[2];
+        double Nx = Uy * Vz - Uz * Vy, Ny = Uz * Vx - Ux * Vz, Nz = Ux * Vy - Uy * Vx;
+        area = 0.5 * sqrt(Nx * Nx + Ny * Ny + Nz * Nz);
+    } else area = triangle_area(p1, p2, p3, dim);
+    if (w3) return area / 3.0 * (sqrt(fabs(w3[0])) + sqrt(fabs(w3[1])) + sqrt(fabs(w3[2])));
+    return area;
+}
+/* mesh_tetra_mass<3> (mesh_sampling.h:213-262): |dot(p2 - p1, cross(p3 - p1, p4 - p1)) / 6| (geometry.h:483-525) */
+static double sampling_tet_mass(const double* p1, const double* p2, const double* p3, const double* p4, const double* w4) {
+    double a[3], b[3], c[3];
+    for (int k = 0; k < 3; ++k) { a[k] = p2[k] - p1[k]; b[k] = p3[k] - p1[k]; c[k] = p4[k] - p1[k]; }
+    double cx = b[1] * c[2] - c[1] * b[2], cy = b[2] * c[0] - c[2] * b[0], cz = b[0] * c[1] - c[0] * b[1];
+    double v = fabs((a[0] * cx + a[1] * cy + a[2] * cz) / 6.0);
+    if (w4) v *= (w4[0] + w4[1] + w4[2] + w4[3]) / 4.0;
+    return v;
+}
+
+/* mesh_generate_random_samples_on_surface<DIM> / _in_volume<DIM>. per = 3: triangles, 4: tetrahedra (dim 3).
+ * x_out: S*dim. elem_out (optional): element of every sample. Returns 0, or 1 when all samples fell into one element. */
+int orc_initial_sampling(int dim, u32 nv, const double* V, u32 ne, const u32* E, int per, const double* weights, u32 S,
+                         double* x_out, u32* elem_out) {
+    (void)nv;
+    if (ne == 0 || (per == 4 && dim != 3)) return 2;
+    orc_mt64 g; mt64_seed(&g, 5489ull);
+    double* s = (double*)malloc(sizeof(double) * (S ? S : 1));
+    for (u32 i = 0; i < S; ++i) s[i] = mt64_float64(&g);
+    qsort(s, S, sizeof(double), cmp_double);
+    double* mass = (double*)malloc(sizeof(double) * ne);
+    double Atot = 0.0;
+    for (u32 t = 0; t < ne; ++t) {
+        const u32* e = E + (size_t)t * per;
+        double w[4];
+        if (weights) for (int k = 0; k < per; ++k) w[k] = weights[e[k]];
+        mass[t] = per == 3 ? sampling_facet_mass(V + (size_t)e[0] * dim, V + (size_t)e[1] * dim, V + (size_t)e[2] * dim, dim, weights ? w : NULL)
+                           : sampling_tet_mass(V + (size_t)e[0] * dim, V + (size_t)e[1] * dim, V + (size_t)e[2] * dim, V + (size_t)e[3] * dim, weights ? w : NULL);
+        Atot += mass[t];
+    }
+    u32 first_t = 0xffffffffu, last_t = 0, cur_t = 0;
+    double cur_s = mass[0] / Atot;
+    for (u32 i = 0; i < S; ++i) {
+        while (s[i] > cur_s && cur_t < ne - 1) { cur_t++; cur_s += mass[cur_t] / Atot; }
+        if (first_t == 0xffffffffu) first_t = cur_t;
+        if (cur_t > last_t) last_t = cur_t;
+        const u32* e = E + (size_t)cur_t * per;
+        const double* p1 = V + (size_t)e[0] * dim; const double* p2 = V + (size_t)e[1] * dim; const double* p3 = V + (size_t)e[2] * dim;
+        if (per == 3) {                                                   /* Geom::random_point_in_triangle, geometry_nd.h:337-349 */
+            double l1 = mt64_float64(&g), l2 = mt64_float64(&g);
+            if (l1 + l2 > 1.0) { l1 = 1.0 - l1; l2 = 1.0 - l2; }
+            double l3 = 1.0 - l1 - l2;
+            /* the vec3 overload (G/basic/geometry.h:602-619) weights p2, p3 with the two draws and p1 with the remainder */
+            if (dim == 3) for (int c = 0; c < 3; ++c) x_out[(size_t)i * 3 + c] = l3 * p1[c] + l1 * p2[c] + l2 * p3[c];
+            else for (int c = 0; c < dim; ++c) x_out[(size_t)i * dim + c] = l1 * p1[c] + l2 * p2[c] + l3 * p3[c];
+        } else {                                                          /* Geom::random_point_in_tetra, :363-385 */
+            const double* p4 = V + (size_t)e[3] * dim;
+            double ss = mt64_float64(&g), tt = mt64_float64(&g), uu = mt64_float64(&g);
+            if (ss + tt > 1.0) { ss = 1.0 - ss; tt = 1.0 - tt; }
+            if (tt + uu > 1.0) { double tmp = uu; uu = 1.0 - ss - tt; tt = 1.0 - tmp; }
+            else if (ss + tt + uu > 1.0) { double tmp = uu; uu = ss + tt + uu - 1.0; ss = 1.0 - tt - tmp; }
+            double a = 1.0 - ss - tt - uu;
+            for (int c = 0; c < dim; ++c) x_out[(size_t)i * dim + c] = a * p1[c] + ss * p2[c] + tt * p3[c] + uu * p4[c];
+        }
+        if (elem_out) elem_out[i] = cur_t;
+    }
+    free(s); free(mass);
+    return (ne > 1 && S > 0 && last_t == first_t) ? 1 : 0;
+}

@@ -195,6 +195,21 @@ def canonical_multinerve(tri, vert, vseed):
     return t, vert[order], vseed[order]
 
 
+def initial_sampling(V, E, S, weights=None):
+    """compute_initial_sampling_on_surface / _in_volume (RVD.cpp:1658-1698, mesh_sampling.h): (x [S, dim], element of each
+    sample, ok). Elements with 4 ids are tetrahedra."""
+    V = _f64(V)
+    E = np.ascontiguousarray(E, dtype=np.uint32)
+    dim = V.shape[1]
+    x = np.zeros((S, dim))
+    elem = np.zeros(S, dtype=np.uint32)
+    w = None if weights is None else _f64(weights)
+    rc = _lib().orc_initial_sampling(C.c_int(dim), C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(E.shape[0]), _p(E, _up),
+                                     C.c_int(E.shape[1]), _p(w, _dp), C.c_uint32(S), _p(x, _dp), _p(elem, _up))
+    assert rc in (0, 1)
+    return x, elem, rc == 0
+
+
 def lloyd(V, T, x, nb_iter, k=20, locked=None, weights=None, adj=None):
     V = _f64(V)
     x = np.array(x, dtype=np.float64, order="C", copy=True)

@@ -79,6 +79,22 @@ def multinerve_case(V, F, X, lloyd_iters=2):
     return out
 
 
+def sampling_cases():
+    """compute_initial_sampling of the reference (single thread: no Hilbert reordering of the mesh) on small meshes."""
+    out = {}
+    for name, V, E, S, kw in [("noise3d", *shapes.noise_sphere(10), 300, {}),
+                              ("sphere6d", shapes.lift_anisotropic(*shapes.icosphere(6), 0.04), shapes.icosphere(6)[1], 200, {}),
+                              ("boxw", *shapes.box_surface(6), 250, dict(weights=1.0 + shapes.box_surface(6)[0][:, 0] + 0.5 * shapes.box_surface(6)[0][:, 1])),
+                              ("kuhn", *shapes.kuhn_cube(5), 200, dict(volumetric=True))]:
+        r = RefCVT(V, E, multithread=False, **kw)
+        r.initial_sampling(S)
+        out[name + "_V"], out[name + "_E"], out[name + "_x"] = V, E, r.points()
+        if "weights" in kw:
+            out[name + "_w"] = kw["weights"]
+        r.close()
+    return out
+
+
 def volume_case(V, T, X, lloyd_iters=4, newton_iters=3):
     """Volumetric mode (RestrictedVoronoiDiagram::set_volumetric(true)): T holds tetrahedra."""
     out = dict(V=V, F=T, X=X, volumetric=np.int32(1))
@@ -125,6 +141,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "trefoil_s200.npz"), **case(V, F, shapes.sample_surface(V, F, 200, 9)))
     V, F = shapes.box_surface(8, (1.0, 1.0, 0.02))
     np.savez_compressed(os.path.join(HERE, "thinbox_multinerve_s150.npz"), **multinerve_case(V, F, shapes.sample_surface(V, F, 150, 3)))
+    np.savez_compressed(os.path.join(HERE, "sampling.npz"), **sampling_cases())
     V, T = shapes.kuhn_cube(6)
     X = np.random.default_rng(13).random((130, 3))
     np.savez_compressed(os.path.join(HERE, "volume_cube_s130.npz"), **volume_case(V, T, X))

@@ -23,7 +23,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve"))]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -704,3 +704,38 @@ def test_rdt_multinerve_against_oracle_raw_and_relaxed(built):
         h.close()
         assert_same_multinerve(got, port.rdt_multinerve(V, F, x, True, True), 8000, True)
     assert np.unique(np.sort(got[0], axis=1), axis=0).shape[0] == 2 * 8000 - 4
+
+
+# ---------------------------------------------------------------------------------------
+# initial sampling (sampling.cuh): the reference's points bit for bit
+# ---------------------------------------------------------------------------------------
+def test_initial_sampling_bit_exact(built):
+    d = np.load(os.path.join(os.path.dirname(ALL_GOLDEN[0]), "sampling.npz"))
+    for name in ("noise3d", "sphere6d", "boxw", "kuhn"):
+        V, E, x = d[name + "_V"], d[name + "_E"], d[name + "_x"]
+        w = d[name + "_w"] if name + "_w" in d.files else None
+        h = capi.Handle(V.shape[1], volumetric=(E.shape[1] == 4))
+        h.set_mesh(V, E, weights=w)
+        got, ok = h.initial_sampling(x.shape[0])
+        assert ok and np.array_equal(got, x), name                # the reference's own output (tests/golden/make_golden.py)
+        assert np.array_equal(h.get_seeds(), x)                   # ... and they are the handle's current seeds
+        h.close()
+    # larger, against the oracle restatement; then straight into the optimisation
+    V, F = shapes.noise_sphere(120)
+    h = handle_for(V, F)
+    got, ok = h.initial_sampling(30000)
+    assert ok and np.array_equal(got, port.initial_sampling(V, F, 30000)[0])
+    h.lloyd_device(2)
+    x1 = h.get_seeds()
+    h.close()
+    h = handle_for(V, F)
+    assert np.array_equal(h.lloyd(got, 2), x1)
+    h.close()
+    # every sample in one element: the reference reports failure
+    V1 = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [5.0, 5.0, 0.0], [5.0 + 1e-9, 5.0, 0.0], [5.0, 5.0 + 1e-9, 0.0]])
+    F1 = np.array([[0, 1, 2], [3, 4, 5]], dtype=np.uint32)
+    h = handle_for(V1, F1)
+    got, ok = h.initial_sampling(5)
+    xo, _, oko = port.initial_sampling(V1, F1, 5)
+    assert ok == oko and not ok and np.array_equal(got, xo)
+    h.close()

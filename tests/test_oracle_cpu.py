@@ -11,7 +11,7 @@ from graphitethree_b200 import shapes
 from oracle import port, ref
 
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve"))]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -250,3 +250,31 @@ def test_oracle_multinerve_matches_live_reference():
                 r.close()
             to, vo, _ = port.rdt_multinerve(V, F, x, uc, ps)
             assert np.array_equal(to, tri) and np.array_equal(vo, vert)
+
+
+# ---------------------------------------------------------------------------------------
+# initial sampling (RVD.cpp:1658-1698, mesh_sampling.h): the restatement returns the reference's points bit for bit
+# ---------------------------------------------------------------------------------------
+def sampling_golden():
+    d = np.load(os.path.join(os.path.dirname(ALL_GOLDEN[0]), "sampling.npz"))
+    for name in ("noise3d", "sphere6d", "boxw", "kuhn"):
+        yield name, d[name + "_V"], d[name + "_E"], d[name + "_x"], (d[name + "_w"] if name + "_w" in d.files else None)
+
+
+def test_oracle_initial_sampling_matches_reference_golden():
+    for name, V, E, x, w in sampling_golden():
+        xo, elem, ok = port.initial_sampling(V, E, x.shape[0], weights=w)
+        assert ok and np.array_equal(xo, x), name
+        assert np.all(np.diff(elem.astype(np.int64)) >= 0)       # sorted uniforms walk the elements in order
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_initial_sampling_matches_live_reference():
+    for V, E, S, kw in [(*shapes.noise_sphere(40), 20000, {}), (*shapes.trefoil_tube(300, 24), 5000, {}), (*shapes.kuhn_cube(6), 2000, dict(volumetric=True))]:
+        r = ref.RefCVT(V, E, multithread=False, **kw)
+        try:
+            r.initial_sampling(S)
+            xr = r.points()
+        finally:
+            r.close()
+        assert np.array_equal(port.initial_sampling(V, E, S)[0], xr)
