@@ -164,50 +164,65 @@ __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u3
     if (flags_out) flags_out[o] = flags[s];
 }
 
-// Sharded runs. cellflag[(m-1) * ncells + c] = 1: an owned seed lies within m cells of cell c, m = 1, 2, 3
-// (facet filter); seeds within two cells get neighbour lists and bisector rows.
+// Sharded runs. One byte per grid cell (CELLF_*): an owned seed lies within 1 / 2 / 3 cells of it, and whether any seed at
+// all lies in it. Seeds within two cells of an owned one get neighbour lists and bisector rows; the facet filter
+// (facet_pairs.cuh) reads all four bits. Bytes are OR-ed four to a word with atomicOr, after a plain load that finds most
+// of them already set.
+__device__ __forceinline__ void cellflag_or(u32* words, u32 cid, u32 bits) {
+    const u32 sh = 8u * (cid & 3u);
+    if (((__ldcg(words + (cid >> 2)) >> sh) & bits) != bits) atomicOr(words + (cid >> 2), bits << sh);
+}
+
 // One thread per owned seed that is the first of its cell.
-__global__ void mark_cells_kernel(const u32* sorted_keys, u32 qbegin, u32 qend, GridParams g, uint8_t* cellflag) {
+template <int D>
+__global__ void mark_cells_kernel(const u32* sorted_keys, const void* xs_, u32 qbegin, u32 qend, GridParams g, u32* cellflag_words) {
     // A warp takes 32 consecutive owned seeds; every first seed of a grid cell (~1 in 9) has the cells within three cells
-    // of its own marked by the WHOLE warp, 11 of the 343 neighbours per lane (one thread per cell ran 3 lanes wide).
+    // of its own marked by the WHOLE warp, 11 of the 343 neighbours per lane. The kernel is bound by instruction issue:
+    // the offsets of a lane's 11 neighbours are unpacked once, and the cell coordinates come from the seed record
+    // instead of a bit-by-bit decode of the Morton id.
+    const SeedRec<D>* xs = (const SeedRec<D>*)xs_;
     const int lane = threadIdx.x & 31;
     const u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
+    u32 off[11];            // (dx + 3) | (dy + 3) << 4 | (dz + 3) << 8 | bits << 12, 0xffffffff: none
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+        const int e = lane + 32 * i;
+        const int dz = e / 49, dy = (e / 7) % 7, dx = e % 7;
+        const int m = max(max(abs(dx - 3), abs(dy - 3)), abs(dz - 3));
+        off[i] = e < 343 ? (u32)(dx | (dy << 4) | (dz << 8) | ((m <= 1 ? 7 : (m <= 2 ? 6 : 4)) << 12)) : 0xffffffffu;
+    }
     u32 key = 0;
+    int c0 = 0, c1 = 0, c2 = 0;
     bool first = false;
     if (s < qend) {
         key = sorted_keys[s];
         first = (s == qbegin) || (sorted_keys[s - 1] != key);
+        if (first) { c0 = grid_coord(g, xs[s].p[0], 0); c1 = grid_coord(g, xs[s].p[1], 1); c2 = grid_coord(g, xs[s].p[2], 2); }
     }
     u32 todo = __ballot_sync(B200_FULL, first);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const u32 k = __shfl_sync(B200_FULL, key, src);
-        // decode the Morton cell id
-        int c[3] = {0, 0, 0};
-        int in = 0;
-        for (int b = 0; b < 11; ++b)
-            for (int ax = 0; ax < 3; ++ax)
-                if (b < g.bits[ax]) { c[ax] |= (int)((k >> in) & 1u) << b; ++in; }
-        for (int e = lane; e < 343; e += 32) {
-            const int dz = e / 49 - 3, dy = (e / 7) % 7 - 3, dx = e % 7 - 3;
-            const int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
-            if (cx < 0 || cx >= g.res[0] || cy < 0 || cy >= g.res[1] || cz < 0 || cz >= g.res[2]) continue;
-            const int m = max(max(abs(dx), abs(dy)), abs(dz));
-            const u32 cid = morton_encode(g, cx, cy, cz);
-            // three byte planes (within one / two / three cells): every writer stores the same value 1, so concurrent
-            // writes are harmless; a cell that already reads as marked is not written again
-            uint8_t* f1 = cellflag + cid; uint8_t* f2 = f1 + g.ncells; uint8_t* f3 = f2 + g.ncells;
-            if (m <= 1 && !*f1) *f1 = 1;
-            if (m <= 2 && !*f2) *f2 = 1;
-            if (!*f3) *f3 = 1;
+        const int bx = __shfl_sync(B200_FULL, c0, src) - 3, by = __shfl_sync(B200_FULL, c1, src) - 3, bz = __shfl_sync(B200_FULL, c2, src) - 3;
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+            const u32 o = off[i];
+            if (o == 0xffffffffu) continue;
+            const int cx = bx + (int)(o & 15u), cy = by + (int)((o >> 4) & 15u), cz = bz + (int)((o >> 8) & 15u);
+            if ((unsigned)cx >= (unsigned)g.res[0] || (unsigned)cy >= (unsigned)g.res[1] || (unsigned)cz >= (unsigned)g.res[2]) continue;
+            cellflag_or(cellflag_words, morton_encode(g, cx, cy, cz), o >> 12);
         }
     }
 }
 
-__global__ void need_flags_kernel(const u32* sorted_keys, u32 S, const uint8_t* cellflag, uint8_t* has_planes) {
+// every seed: does it need lists / rows (an owned seed within two cells)? The first seed of a cell also records that the
+// cell is occupied.
+__global__ void need_flags_kernel(const u32* sorted_keys, u32 S, u32* cellflag_words, uint8_t* has_planes) {
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) has_planes[s] = cellflag[sorted_keys[s]];
+    if (s >= S) return;
+    const u32 cid = sorted_keys[s];
+    has_planes[s] = (uint8_t)(((__ldcg(cellflag_words + (cid >> 2)) >> (8u * (cid & 3u))) >> 1) & 1u);
+    if (s == 0 || sorted_keys[s - 1] != cid) cellflag_or(cellflag_words, cid, CELLF_OCCUPIED);
 }
 
 __global__ void iota_u32_kernel(u32* p, size_t n) {
@@ -303,7 +318,8 @@ struct b200cvt_ctx {
     // kNN
     u32 k = 20, kstride = 20;
     bool knn_valid = false, planes_valid = false;   // planes_valid: the bisector table matches nbr (written by the kNN kernel)
-    DevBuf<uint8_t> cellflag, has_planes;   // sharded runs only
+    DevBuf<u32> cellflag;                   // sharded runs only: one byte per cell, four to a word
+    DevBuf<uint8_t> has_planes;
     DevBuf<float4> facet_ball; DevBuf<u32> facet_cell, facet_list, facet_list_n;
     bool facet_cell_valid = false;
     DevBuf<u32> need_list, need_n;
@@ -595,10 +611,10 @@ static void run_pairs_t(b200cvt_ctx* h) {
             }
             CUDA_CHECK(cudaMemsetAsync(h->facet_list_n.p, 0, sizeof(u32), h->stream));
             FacetFilterArgs fl;
-            fl.ball = h->facet_ball.p; fl.facet_cell = h->facet_cell.p; fl.T = h->T; fl.cellflag = h->cellflag.p;
+            fl.ball = h->facet_ball.p; fl.facet_cell = h->facet_cell.p; fl.T = h->T; fl.cellflag = (const uint8_t*)h->cellflag.p;
             fl.cell_range = h->cell_range.p; fl.facet_guess = h->facet_guess.p; fl.rank_of = h->rank_of.p; fl.xs = h->xs.p;
             fl.g = h->g; fl.list = h->facet_list.p; fl.list_n = h->facet_list_n.p;
-            LAUNCH(h, facet_filter_kernel<D>, div_up(h->T, 256), 256, 0, fl);
+            LAUNCH(h, facet_filter_kernel<D>, div_up(h->T, 256 * FFILT_PER_THREAD), 256, 0, fl);
             a.facet_list = h->facet_list.p; a.facet_list_n = h->facet_list_n.p;
         }
         if (h->T > 0) {
@@ -742,15 +758,15 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     } else {
         // sharded: only the seeds within two grid cells of the owned Morton range get lists and bisector rows
         const u32 nown0 = h->qend() - h->qbegin();
-        h->cellflag.ensure((size_t)h->g.ncells * 3); h->has_planes.ensure(S); h->need_list.ensure(S); h->need_n.ensure(1);
+        h->cellflag.ensure((size_t)h->g.ncells / 4 + 1); h->has_planes.ensure(S); h->need_list.ensure(S); h->need_n.ensure(1);
         h->iota.ensure(S);
         if (h->iota_filled < h->iota.cap) {
             LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
             h->iota_filled = h->iota.cap;
         }
-        CUDA_CHECK(cudaMemsetAsync(h->cellflag.p, 0, (size_t)h->g.ncells * 3, h->stream));
-        if (nown0 > 0) LAUNCH(h, mark_cells_kernel, div_up(nown0, 256), 256, 0, h->keys2.p, h->qbegin(), h->qend(), h->g, h->cellflag.p);
-        LAUNCH(h, need_flags_kernel, div_up(S, 256), 256, 0, h->keys2.p, S, h->cellflag.p + h->g.ncells, h->has_planes.p);
+        CUDA_CHECK(cudaMemsetAsync(h->cellflag.p, 0, sizeof(u32) * ((size_t)h->g.ncells / 4 + 1), h->stream));
+        if (nown0 > 0) LAUNCH(h, mark_cells_kernel<D>, div_up(nown0, 256), 256, 0, h->keys2.p, h->xs.p, h->qbegin(), h->qend(), h->g, h->cellflag.p);
+        LAUNCH(h, need_flags_kernel, div_up(S, 256), 256, 0, h->keys2.p, S, h->cellflag.p, h->has_planes.p);
         size_t sel_bytes = 0;
         cub::DeviceSelect::Flagged(nullptr, sel_bytes, h->iota.p, h->has_planes.p, h->need_list.p, h->need_n.p, (int)S, h->stream);
         h->sort_tmp.ensure(sel_bytes);

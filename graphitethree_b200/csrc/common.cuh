@@ -58,6 +58,12 @@ __host__ __device__ inline int grid_coord(const GridParams& g, double v, int a) 
     return c;
 }
 
+// per-cell status byte of sharded runs (b200cvt.cu: mark_cells_kernel; facet_pairs.cuh: facet_filter_kernel)
+#define CELLF_WITHIN1 1u      // an owned seed within one cell
+#define CELLF_WITHIN2 2u
+#define CELLF_WITHIN3 4u
+#define CELLF_OCCUPIED 8u     // some seed lies in the cell
+
 // One sorted seed record: D coordinates + original index. 32 B for D=3, 64 B for D=6.
 template <int D> struct SeedRec;
 template <> struct __align__(32) SeedRec<3> { double p[3]; long long orig; };

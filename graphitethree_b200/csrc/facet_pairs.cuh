@@ -541,7 +541,7 @@ facet_home_kernel(const __grid_constant__ FacetPairArgs a) {
             if (!done) grid_candidates<D, NC>(a, vv, vmax2, s0, f);
         }
     }
-    // candidate tasks (seed, facet), appended with one atomic per warp
+    // candidate tasks (seed, facet), appended with one atomic per warp (one per block measured the same: 0.334 vs 0.325 ms)
     const u32 nc = __popc(cand);
     u32 incl = nc;
 #pragma unroll
@@ -644,7 +644,7 @@ __global__ void facet_cell_kernel(const double* tri, u32 T, GridParams g, u32* f
 
 struct FacetFilterArgs {
     const float4* ball; const u32* facet_cell; u32 T;
-    const uint8_t* cellflag;      // [3][ncells]: an owned seed within 1 / 2 / 3 cells
+    const uint8_t* cellflag;      // [ncells] CELLF_* bits: an owned seed within 1 / 2 / 3 cells, cell occupied
     const uint2* cell_range;
     const u32* facet_guess; const u32* rank_of; const void* xs;
     GridParams g;
@@ -655,44 +655,74 @@ struct FacetFilterArgs {
 // delta = distance from g to ANY seed). A ball of radius R <= m h about g stays within m cells of g's cell, so
 // the facet is irrelevant to this rank if no owned seed lies within m cells. Level 1 uses static data only
 // (a non-empty home cell bounds delta by sqrt(3) h); level 2 uses the facet's previous home seed.
+// Most facets of a sharded run are far from the rank's seeds: they leave after three coalesced loads (cell id, ball,
+// one status byte); only the rest follows the previous home seed.
+#define FFILT_PER_THREAD 4       // facets per thread: their loads are in flight together (the kernel is latency-bound)
 template <int D>
 __global__ void __launch_bounds__(256)
 facet_filter_kernel(FacetFilterArgs a) {
-    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool rel = false;
-    if (f < a.T) {
-        // the kernel is bound by load latency: everything that does not depend on a decision is requested up front
-        const u32 cid = a.facet_cell[f];
-        const float4 b = a.ball[f];
-        const u32 guess = a.facet_guess[f];
-        const uint8_t* f1 = a.cellflag; const uint8_t* f2 = f1 + a.g.ncells; const uint8_t* f3 = f2 + a.g.ncells;
-        const uint8_t l1 = f1[cid], l2 = f2[cid], l3 = f3[cid];
-        const uint2 rg = a.cell_range[cid];
-        const u32 gpos = (guess != B200_NONE) ? a.rank_of[guess] : 0u;
-        const double h = a.g.h;
-        // (D > 3: the grid only sees the first three coordinates and the float ball only stores those, so neither
-        // bound on delta holds in the facet's own space: every facet stays relevant)
-        if (D > 3) rel = true;
-        else if (!l3 && (double)b.w <= 0.6 * h && rg.y > rg.x) rel = false;
-        else {
-            rel = true;
-            if (guess != B200_NONE) {
-                const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
-                const SeedRec<D>* r = xs + gpos;
-                const double qx = r->p[0] - (double)b.x, qy = r->p[1] - (double)b.y, qz = r->p[2] - (double)b.z;
-                const double d2 = qx * qx + qy * qy + qz * qz;
-                const double R = (2.0 * (double)b.w + sqrt(d2)) * (1.0 + 1e-6);
-                if (R <= h) rel = l1 != 0;
-                else if (R <= 2.0 * h) rel = l2 != 0;
-                else if (R <= 3.0 * h) rel = l3 != 0;
+    const u32 base_f = blockIdx.x * (256u * FFILT_PER_THREAD) + threadIdx.x;
+    u32 cid[FFILT_PER_THREAD], fl[FFILT_PER_THREAD];
+    float4 b[FFILT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < FFILT_PER_THREAD; ++k) {
+        const u32 f = base_f + 256u * k;
+        cid[k] = f < a.T ? a.facet_cell[f] : 0u;
+        b[k] = f < a.T ? a.ball[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < FFILT_PER_THREAD; ++k) fl[k] = a.cellflag[cid[k]];
+    const double h = a.g.h;
+    u32 relmask = 0;
+#pragma unroll
+    for (int k = 0; k < FFILT_PER_THREAD; ++k) {
+        const u32 f = base_f + 256u * k;
+        bool rel = false;
+        if (f < a.T) {
+            // (D > 3: the grid only sees the first three coordinates and the float ball only stores those, so neither
+            // bound on delta holds in the facet's own space: every facet stays relevant)
+            if (D > 3) rel = true;
+            else if (!(fl[k] & CELLF_WITHIN3) && (double)b[k].w <= 0.6 * h && (fl[k] & CELLF_OCCUPIED)) rel = false;
+            else if (fl[k] & CELLF_WITHIN1) rel = true;      // an owned seed next to the facet: relevant whatever R is
+            else {
+                rel = true;
+                const u32 guess = a.facet_guess[f];
+                if (guess != B200_NONE) {
+                    const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
+                    const SeedRec<D>* r = xs + a.rank_of[guess];
+                    const double qx = r->p[0] - (double)b[k].x, qy = r->p[1] - (double)b[k].y, qz = r->p[2] - (double)b[k].z;
+                    const double d2 = qx * qx + qy * qy + qz * qz;
+                    const double R = (2.0 * (double)b[k].w + sqrt(d2)) * (1.0 + 1e-6);
+                    if (R <= h) rel = (fl[k] & CELLF_WITHIN1) != 0;
+                    else if (R <= 2.0 * h) rel = (fl[k] & CELLF_WITHIN2) != 0;
+                    else if (R <= 3.0 * h) rel = (fl[k] & CELLF_WITHIN3) != 0;
+                }
             }
         }
+        relmask |= (rel ? 1u : 0u) << k;
     }
-    const u32 m = __ballot_sync(B200_FULL, rel);
-    if (m == 0) return;
-    u32 base = 0;
-    if (lane == 0) base = atomicAdd(a.list_n, (u32)__popc(m));
-    base = __shfl_sync(B200_FULL, base, 0);
-    if (rel) a.list[base + __popc(m & ((1u << lane) - 1u))] = f;
+    // one append per BLOCK: half of the facets of a two-rank run are relevant, and one atomic per warp on the same counter
+    // was the whole cost of this kernel
+    __shared__ u32 s_cnt[8], s_base;
+    const int w = threadIdx.x >> 5;
+    const u32 mine = (u32)__popc(relmask);
+    u32 incl = mine;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const u32 o = __shfl_up_sync(B200_FULL, incl, m);
+        if (lane >= m) incl += o;
+    }
+    if (lane == 31) s_cnt[w] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int i = 0; i < 8; ++i) { const u32 c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+        s_base = tot ? atomicAdd(a.list_n, tot) : 0u;
+    }
+    __syncthreads();
+    u32 pos = s_base + s_cnt[w] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < FFILT_PER_THREAD; ++k)
+        if ((relmask >> k) & 1u) a.list[pos++] = base_f + 256u * k;
 }
