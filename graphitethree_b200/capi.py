@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libb200cvt.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200cvt.h")
 
 FLAG_EXHAUSTED, FLAG_TIE, FLAG_POLY_OVERFLOW, FLAG_KMAX = 1, 2, 4, 8
-KMAX = 124
+KMAX = 252
 
 _dp = C.POINTER(C.c_double)
 _up = C.POINTER(C.c_uint32)

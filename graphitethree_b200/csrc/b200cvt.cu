@@ -24,6 +24,7 @@
 #include "../../include/b200cvt.h"
 
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -391,6 +392,13 @@ struct b200cvt_ctx {
 
 static inline u32 div_up(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 
+// NVTX range per phase of an evaluation and per optimiser iteration (header-only NVTX 3: a no-op unless a profiler is
+// attached), so that an Nsight Systems timeline reads like DESIGN.md §4
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct ArgError : public std::runtime_error { explicit ArgError(const std::string& s) : std::runtime_error(s) {} };
 struct StateError : public std::runtime_error { explicit StateError(const std::string& s) : std::runtime_error(s) {} };
 struct CapacityError : public std::runtime_error { explicit CapacityError(const std::string& s) : std::runtime_error(s) {} };
@@ -532,7 +540,8 @@ static void launch_knn(b200cvt_ctx* h, const KnnArgs& a, u32 nq) {
     u32 blocks = std::min<u32>(div_up(nq, KNN_WARPS), 148u * 16u);
     if (kneed <= 32) LAUNCH(h, (knn_kernel<D, 1>), blocks, KNN_WARPS * 32, 0, a);
     else if (kneed <= 64) LAUNCH(h, (knn_kernel<D, 2>), blocks, KNN_WARPS * 32, 0, a);
-    else LAUNCH(h, (knn_kernel<D, 4>), blocks, KNN_WARPS * 32, 0, a);
+    else if (kneed <= 128) LAUNCH(h, (knn_kernel<D, 4>), blocks, KNN_WARPS * 32, 0, a);
+    else LAUNCH(h, (knn_kernel<D, 8>), blocks, KNN_WARPS * 32, 0, a);
 }
 
 static void run_knn_main(b200cvt_ctx* h, u32 k, bool want_sqd, bool all_seeds, bool want_planes = false) {
@@ -741,9 +750,11 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&h->evk[i]));
     }
     for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventRecord(h->evk[i], h->stream));
+    NvtxRange nvtx_eval(mode == 0 ? "b200cvt:evaluate(centroids)" : (mode == 1 ? "b200cvt:evaluate(func_grad)" : "b200cvt:evaluate(pairs)"));
     CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-    if (!h->grid_valid) build_grid(h);
+    { NvtxRange r("b200cvt:sort+grid"); if (!h->grid_valid) build_grid(h); }
     CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+    nvtxRangePushA("b200cvt:kNN+bisectors");
     h->planes.ensure((size_t)S * h->kstride * PLANE_STRIDE(D));
     h->planes32.ensure((size_t)S * h->kstride * PLANE32_STRIDE(D));
     if (h->nranks == 1) {
@@ -788,6 +799,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         launch_knn<D>(h, a, S);
         h->prev_valid = true; h->knn_valid = true; h->planes_valid = true;
     }
+    nvtxRangePop();
     CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
     h->stats.ensure(16);
     if (h->want_stats) CUDA_CHECK(cudaMemsetAsync(h->stats.p, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -795,8 +807,9 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         if (D == 3) evaluate_volume(h, mode, check_SR);
         return;
     }
-    run_pairs_t<D, 3>(h);
+    { NvtxRange r("b200cvt:facet walk (pairs)"); run_pairs_t<D, 3>(h); }
     CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+    NvtxRange nvtx_clip("b200cvt:clip+integrate");
     if (mode == 2) {            // candidate rows only (RDT extraction)
         CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
         return;
@@ -1002,6 +1015,7 @@ static void lloyd_loop(b200cvt_ctx* h, u32 nb_iter, b200cvt_progress_cb cb, void
     if (nb_iter > 0) h->rdt_valid = false; h->rdt_valid_mn = false;      // the seeds move: a cached triangulation is stale
     comm_prepare(h);
     for (u32 it = 0; it < nb_iter; ++it) {
+        NvtxRange nvtx_it("b200cvt:Lloyd iteration");
         evaluate(h, 0, 0);
         u32 n = h->slice_len();
         const uint8_t* lk = h->locked.p;

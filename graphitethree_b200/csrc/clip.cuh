@@ -24,7 +24,7 @@
 
 #define CLIP_WARPS 4
 #define CLIP_MAXV 24
-#define B200CVT_KMAX_DEV 124u
+#define B200CVT_KMAX_DEV 252u
 
 // ---------------------------------------------------------------------------------------
 // clip + integrate: one warp per seed, one lane per candidate facet

@@ -279,6 +279,9 @@ facet_big_kernel(const __grid_constant__ FacetPairArgs a) {
             } else {
                 const u32 height = s_cnt[w][1];
                 if (height == 0) break;
+                // the counter runs past the stack when a split found it full (the pieces were not stored): give up on the
+                // bisection before anything is read from beyond the stack; the facet takes the whole-facet grid scan below
+                if (height > BIG_STACK) { ok = false; break; }
                 const u32 take = min(height, 32u);
                 active = (u32)lane < take;
                 if (active) {

@@ -118,6 +118,7 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     newton_eval(h); nfev_total++;
     post_eval(0);
     for (;;) {
+        NvtxRange nvtx_it("b200cvt:L-BFGS iteration");
         LbfgsDirArgs da;
         memset(&da, 0, sizeof(da));
         da.N = N; da.first = (iter == 0) ? 1 : 0; da.M = M; da.cur_pos = cur_pos; da.bound = -1;

@@ -47,7 +47,7 @@ enum {
     B200CVT_FLAG_KMAX = 8       /* check_SR=1 but the neighbourhood hit the implementation cap (B200CVT_KMAX) */
 };
 
-#define B200CVT_KMAX 124u       /* largest neighbour list (reference: unbounded, S-1) */
+#define B200CVT_KMAX 252u       /* largest neighbour list (reference: unbounded, S-1); a seed that needs more is flagged */
 
 /* progress callback: called after each Lloyd iteration / each L-BFGS iteration
  * (CentroidalVoronoiTesselation::newiteration, G/voronoi/CVT.cpp:340-345).

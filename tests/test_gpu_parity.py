@@ -739,3 +739,90 @@ def test_initial_sampling_bit_exact(built):
     xo, _, oko = port.initial_sampling(V1, F1, 5)
     assert ok == oko and not ok and np.array_equal(got, xo)
     h.close()
+
+
+# ---------------------------------------------------------------------------------------
+# full-size configurations, seed by seed against the UNMODIFIED reference (oracle/_ref, all host threads)
+# ---------------------------------------------------------------------------------------
+def per_seed_vs_reference(V, E, x, volumetric=False):
+    """exact cells (check_SR = true: the reference's result does not depend on its thread count there, only the order of
+    its per-seed sums does), masses / centroids / energy / gradient of EVERY seed at 1e-9"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    r = ref.RefCVT(V, E, volumetric=volumetric, multithread=True)
+    try:
+        r.set_points(x)
+        r.update_delaunay()
+        mg_r, m_r, _ = r.centroids(True)
+        f_r, g_r, _ = r.funcgrad(True)
+    finally:
+        r.close()
+    h = capi.Handle(x.shape[1], volumetric=volumetric)
+    h.set_mesh(V, E)
+    h.set_seeds(x)
+    mg, m = h.centroids(True)
+    fl = h.flags()
+    h.set_seeds(x)
+    f, g = h.funcgrad(True)
+    h.close()
+    assert (fl & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    assert_close(m, m_r, what="mass")
+    assert_close(mg, mg_r, what="mass*centroid")
+    assert abs(f - f_r) <= RTOL * abs(f_r)
+    assert_close(g, g_r, what="gradient")
+
+
+def test_full_size_c2_per_seed_against_reference(built):
+    V, F = shapes.noise_sphere(316)                                   # 2.0 M triangles
+    h = handle_for(V, F)
+    x = h.lloyd(shapes.sample_surface(V, F, 200000, 1), 3)
+    h.close()
+    per_seed_vs_reference(V, F, x)
+
+
+def test_full_size_c4_6d_per_seed_against_reference(built):
+    V3, F = shapes.cad_like(268)                                      # 2.0 M triangles, sharp creases
+    V = shapes.lift_anisotropic(V3, F, 0.04)
+    h = capi.Handle(6)
+    h.set_mesh(V, F)
+    x = h.lloyd(shapes.sample_surface(V, F, 500000, 1), 3)
+    h.close()
+    per_seed_vs_reference(V, F, x)
+
+
+def test_c5_volumetric_62k_per_seed_against_reference(built):
+    V, T = shapes.kuhn_cube(47)                                       # 623 k tetrahedra, T / S = 10 as in C5
+    X = 0.01 + 0.98 * np.random.default_rng(5).random((62000, 3))
+    h = volume_handle(V, T)
+    x = h.lloyd(X, 2)
+    h.close()
+    per_seed_vs_reference(V, T, x, volumetric=True)
+
+
+def test_neighbour_cap_is_flagged(built):
+    # Seeds on a line next to a facet much longer than their spacing: every cell is a strip whose security radius reaches all
+    # the other seeds, so check_SR asks for all S - 1 neighbours (the reference grows the list without bound,
+    # generic_RVD.h:2183-2197). Up to B200CVT_KMAX neighbours the library follows (exact cells, Newton trajectory included);
+    # beyond the cap every seed that ran into it is flagged. The strips are bounded by the two adjacent bisectors only, so
+    # the values of a single evaluation are still the exact ones.
+    V = np.array([[-1.0, -5.0, 0.0], [2.0, -5.0, 0.0], [2.0, 5.0, 0.0], [-1.0, 5.0, 0.0]])
+    F = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
+    for S in (200, 400):
+        x = np.column_stack([(np.arange(S) + 0.5) / S, 1e-3 * np.sin(np.arange(S)), np.zeros(S)])
+        h = handle_for(V, F)
+        h.set_seeds(x)
+        f, g = h.funcgrad(True)
+        fl = h.flags()
+        e = port.surface_eval(V, F, x, 1, True, kcap=S - 1)
+        assert abs(f - e.f) <= RTOL * abs(e.f)
+        assert_close(g, e.g, what="gradient")
+        assert_close(h.seed_energy(), e.f_seed, what="per-seed energy")
+        if S - 1 <= capi.KMAX:
+            assert (fl & capi.FLAG_KMAX).sum() == 0                      # 199 neighbours: below the cap, nothing to flag
+            x1, info = h.newton(x, 3, 7)
+            x1o, infoo = port.newton(V, F, x, 3, 7, kcap=S - 1)
+            assert info["iters"] == infoo["iters"] and info["nfev"] == infoo["nfev"] and np.abs(x1 - x1o).max() <= 1e-8
+        else:
+            assert (fl & capi.FLAG_KMAX).sum() >= S - 2 * capi.KMAX      # flagged: the cap was reached
+        h.close()
