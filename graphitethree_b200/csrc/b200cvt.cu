@@ -323,7 +323,7 @@ struct b200cvt_ctx {
     DevBuf<uint8_t> has_planes;
     DevBuf<float4> facet_ball; DevBuf<u32> facet_cell, facet_list, facet_list_n;
     bool facet_cell_valid = false;
-    DevBuf<u32> need_list, need_n;
+    DevBuf<u32> need_list, need_n;   // knn_fb: [0] count, [1..] queries knn_tile_kernel left to knn_kernel
     DevBuf<u32> nbr, nbr_n, nbr_prev;   // nbr_prev: lists of the previous evaluation, original indices, rows by original index
     bool prev_valid = false;
     DevBuf<double> sqd;

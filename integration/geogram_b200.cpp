@@ -32,6 +32,25 @@ namespace {
         throw std::runtime_error(msg);
     }
 
+    unsigned long long hash_bytes(unsigned long long h, const void* p, size_t n);
+
+    /* the same hash over large arrays: 1 MiB chunks hashed in parallel (OpenMP), chunk hashes combined in order */
+    unsigned long long hash_bytes_parallel(unsigned long long h, const void* p, size_t n) {
+        const size_t chunk = size_t(1) << 20;
+        const size_t nchunks = (n + chunk - 1) / chunk;
+        if(nchunks <= 4) {
+            return hash_bytes(h, p, n);
+        }
+        std::vector<unsigned long long> part(nchunks);
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        #pragma omp parallel for schedule(static)
+        for(long long c = 0; c < (long long)nchunks; ++c) {
+            const size_t off = size_t(c) * chunk;
+            part[size_t(c)] = hash_bytes(0x9E3779B97F4A7C15ull + (unsigned long long)c, b + off, std::min(chunk, n - off));
+        }
+        return hash_bytes(h, part.data(), sizeof(unsigned long long) * nchunks);
+    }
+
     unsigned long long hash_bytes(unsigned long long h, const void* p, size_t n) {
         /* word-wise multiply-xorshift: only used to notice that the caller edited the mesh */
         const unsigned long long* w = static_cast<const unsigned long long*>(p);
@@ -209,7 +228,9 @@ namespace GEO {
     const RestrictedVoronoiDiagramB200::MeshArrays& RestrictedVoronoiDiagramB200::arrays(bool full_check) {
         MeshArrays& A = volumetric_ ? vol_arrays_ : surf_arrays_;
         const unsigned long long q = quick_signature();
-        if(A.valid && q == A.quick && !full_check) {
+        /* the full hash is taken once per quick signature: a caller that edits coordinates in place without changing any
+         * sampled value must call mesh_modified() */
+        if(A.valid && q == A.quick && (!full_check || A.full_checked)) {
             return A;
         }
         const index_t nv = mesh_->vertices.nb(), stride = mesh_->vertices.dimension();
@@ -217,7 +238,9 @@ namespace GEO {
         const index_t ne = volumetric_ ? mesh_->cells.nb() : mesh_->facets.nb();
         A.elems.resize(size_t(ne) * per);
         A.adj.resize(size_t(ne) * per);
-        for(index_t e = 0; e < ne; ++e) {
+        #pragma omp parallel for schedule(static)
+        for(long long ee = 0; ee < (long long)ne; ++ee) {
+            const index_t e = index_t(ee);
             for(index_t lv = 0; lv < per; ++lv) {
                 A.elems[size_t(e) * per + lv] = volumetric_ ? mesh_->cells.vertex(e, lv) : mesh_->facets.vertex(e, lv);
                 const index_t a = volumetric_ ? mesh_->cells.adjacent(e, lv) : mesh_->facets.adjacent(e, lv);
@@ -232,10 +255,10 @@ namespace GEO {
                 A.weights[v] = vertex_weight_[v];
             }
         }
-        unsigned long long hsh = hash_bytes(0x243F6A8885A308D3ull + nv + (volumetric_ ? 7 : 0), mesh_->vertices.point_ptr(0),
-                                            sizeof(double) * size_t(nv) * stride);
-        hsh = hash_bytes(hsh, A.elems.data(), sizeof(uint32_t) * A.elems.size());
-        hsh = hash_bytes(hsh, A.adj.data(), sizeof(int32_t) * A.adj.size());
+        unsigned long long hsh = hash_bytes_parallel(0x243F6A8885A308D3ull + nv + (volumetric_ ? 7 : 0), mesh_->vertices.point_ptr(0),
+                                                     sizeof(double) * size_t(nv) * stride);
+        hsh = hash_bytes_parallel(hsh, A.elems.data(), sizeof(uint32_t) * A.elems.size());
+        hsh = hash_bytes_parallel(hsh, A.adj.data(), sizeof(int32_t) * A.adj.size());
         if(!A.weights.empty()) {
             hsh = hash_bytes(hsh, A.weights.data(), sizeof(double) * A.weights.size());
         }
@@ -245,12 +268,13 @@ namespace GEO {
         A.full = hsh;
         A.quick = q;
         A.valid = true;
+        A.full_checked = true;
         return A;
     }
 
     void RestrictedVoronoiDiagramB200::mesh_modified() {
-        surf_arrays_.valid = false;
-        vol_arrays_.valid = false;
+        surf_arrays_.valid = false; surf_arrays_.full_checked = false;
+        vol_arrays_.valid = false; vol_arrays_.full_checked = false;
     }
 
     b200cvt_handle RestrictedVoronoiDiagramB200::handle(bool full_check) {

@@ -82,7 +82,7 @@ namespace GEO {
             std::vector<double> weights;
             unsigned long long quick = 0, full = 0;
             unsigned version = 0;     /* bumped when the content changed */
-            bool valid = false;
+            bool valid = false, full_checked = false;
         };
         /** the C-ABI handle with the current mesh uploaded. Every call checks a cheap signature of the borrowed mesh (addresses,
          *  counts, a strided sample); full_check also hashes all of it (done once per Lloyd_iterations / Newton_iterations /
