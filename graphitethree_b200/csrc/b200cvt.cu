@@ -149,6 +149,25 @@ __global__ void scatter_results_kernel(const SeedRec<D>* xs, u32 qbegin, u32 qen
     if (cnt_orig) cnt_orig[o] = pair_cnt[s];
 }
 
+// Sharded Newton: the gradient of every evaluated seed goes straight into the L-BFGS slice of the rank that owns the seed
+// (rows of L = ceil(S / nranks) original indices per rank), over NVLink when that is another GPU; locked seeds get zeros
+// (constrain_points, CVT.cpp:309-321). Flags and pair counts stay local.
+template <int D>
+__global__ void scatter_gradient_peer_kernel(const SeedRec<D>* xs, u32 qbegin, u32 qend, const double* out_v, const uint8_t* flags,
+                                             const u32* pair_cnt, const uint8_t* locked, PeerBufs pb, u32 L,
+                                             uint8_t* flags_orig, u32* cnt_orig) {
+    const u32 s = qbegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= qend) return;
+    const u32 o = (u32)xs[s].orig;
+    const u32 owner = o / L;
+    double* dst = pb.g[owner] + (size_t)(o - owner * L) * D;
+    const bool z = locked && locked[o];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dst[c] = z ? 0.0 : out_v[(size_t)s * D + c];
+    flags_orig[o] = flags[s];
+    cnt_orig[o] = pair_cnt[s];
+}
+
 template <int D>
 __global__ void knn_export_kernel(const SeedRec<D>* xs, const u32* nbr, const u32* nbr_n, const double* sqd, const uint8_t* flags,
                                   u32 S, u32 k, u32* idx_out, u32* cnt_out, double* sqd_out, uint8_t* flags_out) {
@@ -266,7 +285,9 @@ template <class T> struct DevBuf {
 };
 
 // shared by the member handles of a single-process group (b200cvt_group_*): one host thread per GPU
+struct b200cvt_ctx;
 struct GroupShared {
+    std::vector<b200cvt_ctx*> members;
     std::mutex mu; std::condition_variable cv;
     int n = 1, waiting = 0; unsigned long long generation = 0;
     int cancel = 0;
@@ -365,6 +386,11 @@ struct b200cvt_ctx {
                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<double> xch_slice, xch_all, g_full;    // exchange buffers owned by the library (communicator mode)
     GroupShared* group = nullptr;                 // member of a single-process group
+    // peer-mapped seed arrays / gradient slices of all ranks (Newton loop); IPC mappings are cached by handle
+    PeerBufs pb; bool pb_valid = false;
+    void* pb_ipc_ptr[2][B200_MAX_RANKS] = {};
+    cudaIpcMemHandle_t pb_ipc_handle[2][B200_MAX_RANKS] = {};
+    bool use_peer_exchange = true;                // B200CVT_PEER_EXCHANGE=0: NCCL reduce-scatter / all-gather instead
     // L-BFGS
     DevBuf<double> lb_g, lb_q, lb_px, lb_pg, lb_wa, lb_s, lb_y, lb_part;
     DevBuf<LbfgsScalars> lb_sc;
@@ -1986,6 +2012,7 @@ static void comm_finish(b200cvt_ctx* h, u32 rank, u32 nranks, PeerBox** peers) {
     for (u32 p = 0; p < nranks; ++p) h->pc.boxes[p] = peers[p];
     h->pc.seq = h->pc_seq.p; h->pc.gtot = h->pc_gtot.p; h->pc.error = h->pc_err.p;
     h->rank = rank; h->nranks = nranks; h->has_comm = true;
+    { const char* e = getenv("B200CVT_PEER_EXCHANGE"); h->use_peer_exchange = !(e && atoi(e) == 0); }
     h->knn_valid = false; h->has_results = false; h->rdt_valid = false; h->rdt_valid_mn = false; h->prev_valid = false;
 }
 
@@ -1993,8 +2020,12 @@ static void comm_release(b200cvt_ctx* h) {
     if (!h->has_comm) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int p = 0; p < B200_MAX_RANKS; ++p)
+    for (int p = 0; p < B200_MAX_RANKS; ++p) {
         if (h->ipc_opened[p]) { cudaIpcCloseMemHandle(h->ipc_opened[p]); h->ipc_opened[p] = nullptr; }
+        for (int b = 0; b < 2; ++b)
+            if (h->pb_ipc_ptr[b][p]) { cudaIpcCloseMemHandle(h->pb_ipc_ptr[b][p]); h->pb_ipc_ptr[b][p] = nullptr; }
+    }
+    h->pb_valid = false;
     if (h->nccl) { nccl_api().CommDestroy(h->nccl); h->nccl = nullptr; }
     h->has_comm = false;
     memset(&h->pc, 0, sizeof(h->pc)); h->pc.nranks = 1;
@@ -2090,6 +2121,7 @@ int b200cvt_group_create(int n_gpus, int dim, int volumetric, b200cvt_group_hand
             if (b200cvt_create(d, dim, volumetric, &m) != B200CVT_OK) throw CudaError(g_last_error);
             m->group = &g->shared;
             g->members.push_back(m);
+            g->shared.members.push_back(m);
         }
         if (n_gpus > 1) {
             std::vector<ncclComm_t> comms(n_gpus);

@@ -117,3 +117,32 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& pc, const double*
     }
     if (lane == 0) *((volatile unsigned long long*)pc.seq) = seq;
 }
+
+// ---------------------------------------------------------------------------------------
+// Bulk exchanges of the sharded Newton loop through peer memory (the NCCL calls remain as the fallback path):
+//   the gradient of a seed is STORED by the rank that evaluated it straight into the L-BFGS slice of the rank that owns it,
+//   the new trial point of a slice is stored by its owner into every rank's seed array,
+// each followed by a mailbox barrier. No staging buffer, no zero fill, no collective launch.
+// ---------------------------------------------------------------------------------------
+struct PeerBufs {
+    double* x[B200_MAX_RANKS];       // every rank's seed array (original order, padded to nranks * L rows)
+    double* g[B200_MAX_RANKS];       // every rank's L-BFGS gradient slice (L rows)
+};
+
+// barrier over the ranks = a mailbox reduction of nothing; everything this GPU stored before it (earlier kernels of the
+// stream included) is visible to a peer once the peer has passed its own barrier
+__global__ void peer_barrier_kernel(PeerComm pc) {
+    __threadfence_system();
+    double z = 0.0, r;
+    peer_allreduce<1>(pc, &z, &r);
+    __threadfence_system();
+}
+
+// this rank's slice of the seed array -> the same rows of every other rank's seed array
+__global__ void peer_push_slice_kernel(PeerBufs pb, int rank, int nranks, size_t off, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = pb.x[rank][off + i];
+        for (int p = 0; p < nranks; ++p)
+            if (p != rank) pb.x[p][off + i] = v;
+    }
+}

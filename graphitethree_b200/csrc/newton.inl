@@ -24,6 +24,16 @@ static void newton_eval_t(b200cvt_ctx* h) {
     h->grid_valid = false; h->knn_valid = false;
     evaluate(h, 1, 1);
     const u32 S = h->S;
+    if (h->has_comm && h->nranks > 1 && h->pb_valid) {
+        // peer-memory path: every gradient row is stored into its owner's slice, then a barrier
+        const u32 nown = h->qend() - h->qbegin();
+        if (nown > 0)
+            LAUNCH(h, scatter_gradient_peer_kernel<D>, div_up(nown, 256), 256, 0, (const SeedRec<D>*)h->xs.p, h->qbegin(), h->qend(),
+                   h->out_v.p, h->flags.p, h->pair_cnt.p, h->locked.p, h->pb, (u32)h->slice_len(), h->flags_orig.p, h->cnt_orig.p);
+        LAUNCH(h, peer_barrier_kernel, 1, 32, 0, h->pc);
+        h->exchanges++;
+        return;
+    }
     if (h->has_comm && h->nranks > 1) {
         const size_t L = h->slice_len();
         const size_t padded = L * h->nranks * D;
@@ -64,8 +74,64 @@ static void newton_pad_seeds(b200cvt_ctx* h) {
     h->x.grow_keep(padded, (size_t)h->S * h->dim, h->stream);
 }
 
+// the seed arrays and gradient slices of all ranks, mapped into this process (collective; called once per Newton call
+// after the buffers have their final size)
+static void newton_map_peer_buffers(b200cvt_ctx* h) {
+    h->pb_valid = false;
+    if (!h->use_peer_exchange) return;
+    const u32 n = h->nranks;
+    memset(&h->pb, 0, sizeof(h->pb));
+    if (h->group) {
+        // one process: peer access is enabled, the pointers are valid on every GPU
+        h->group->barrier();
+        for (u32 p = 0; p < n; ++p) { h->pb.x[p] = h->group->members[p]->x.p; h->pb.g[p] = h->group->members[p]->lb_g.p; }
+        h->group->barrier();
+        h->pb_valid = true;
+        return;
+    }
+    // one process per GPU: CUDA IPC handles of the two allocations travel with one all-gather; a mapping is reused as long as
+    // the peer's handle does not change
+    cudaIpcMemHandle_t mine[2];
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine[0], h->x.p));
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine[1], h->lb_g.p));
+    DevBuf<unsigned char> d_handles;
+    d_handles.ensure(sizeof(mine) * n);
+    CUDA_CHECK(cudaMemcpyAsync(d_handles.p + sizeof(mine) * h->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    NCCL_CHECK(nccl_api().AllGather(d_handles.p + sizeof(mine) * h->rank, d_handles.p, sizeof(mine), ncclUint8, h->nccl, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(2 * (size_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_handles.p, sizeof(mine) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (u32 p = 0; p < n; ++p)
+        for (int b = 0; b < 2; ++b) {
+            double** slot = b == 0 ? &h->pb.x[p] : &h->pb.g[p];
+            if (p == h->rank) { *slot = b == 0 ? h->x.p : h->lb_g.p; continue; }
+            const cudaIpcMemHandle_t& hd = all[2 * (size_t)p + b];
+            if (h->pb_ipc_ptr[b][p] && memcmp(&hd, &h->pb_ipc_handle[b][p], sizeof(hd)) != 0) {
+                cudaIpcCloseMemHandle(h->pb_ipc_ptr[b][p]);
+                h->pb_ipc_ptr[b][p] = nullptr;
+            }
+            if (!h->pb_ipc_ptr[b][p]) {
+                void* ptr = nullptr;
+                CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+                h->pb_ipc_ptr[b][p] = ptr; h->pb_ipc_handle[b][p] = hd;
+            }
+            *slot = (double*)h->pb_ipc_ptr[b][p];
+        }
+    h->pb_valid = true;
+}
+
 static void newton_gather_seeds(b200cvt_ctx* h) {
     const size_t L = h->slice_len();
+    if (h->pb_valid) {
+        // the new trial point of this rank's slice -> every rank's seed array, then a barrier
+        const size_t n = (size_t)lb_local_seeds(h) * h->dim;
+        if (n > 0)
+            LAUNCH(h, peer_push_slice_kernel, std::min<u32>(div_up(n, 256), (u32)h->num_sms * 8u), 256, 0, h->pb, (int)h->rank, (int)h->nranks,
+                   (size_t)h->rank * L * h->dim, n);
+        LAUNCH(h, peer_barrier_kernel, 1, 32, 0, h->pc);
+        h->exchanges++;
+        return;
+    }
     NCCL_CHECK(nccl_api().AllGather(h->x.p + (size_t)h->rank * L * h->dim, h->x.p, L * h->dim, ncclDouble, h->nccl, h->stream));
     h->exchanges++;
 }
@@ -90,6 +156,7 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     h->lb_s.ensure((size_t)std::max(M, 1) * Nalloc); h->lb_y.ensure((size_t)std::max(M, 1) * Nalloc);
     PeerComm pc = h->pc;
     if (!sharded) { memset(&pc, 0, sizeof(pc)); pc.nranks = 1; }
+    if (sharded) newton_map_peer_buffers(h);
     // the direction kernel needs all its blocks resident (grid barriers): one cooperative launch
     if (h->lb_dir_blocks == 0) {
         int per_sm = 0, coop = 0;
@@ -173,6 +240,12 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         if (perr) throw std::runtime_error("a peer GPU did not answer a mailbox reduction (timeout)");
     }
     if (info_out) { info_out[0] = iter; info_out[1] = nfev_total; info_out[2] = (u32)ls_info; info_out[3] = 0; }
+    if (sharded && h->pb_valid) {
+        // nobody may leave (and free or move its buffers) while a peer still stores into them
+        LAUNCH(h, peer_barrier_kernel, 1, 32, 0, h->pc);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->pb_valid = false;
+    }
     h->grid_valid = false; h->knn_valid = false; h->has_results = true;
     if (canceled) throw CanceledError("canceled by the progress callback");
 }
