@@ -342,7 +342,7 @@ struct b200cvt_ctx {
     bool knn_valid = false, planes_valid = false;   // planes_valid: the bisector table matches nbr (written by the kNN kernel)
     DevBuf<u32> cellflag;                   // sharded runs only: one byte per cell, four to a word
     DevBuf<uint8_t> has_planes;
-    DevBuf<float4> facet_ball; DevBuf<u32> facet_cell, facet_list, facet_list_n;
+    DevBuf<float4> facet_ball; DevBuf<float> facet_rad; DevBuf<u32> facet_cell, facet_list, facet_list_n;
     bool facet_cell_valid = false;
     DevBuf<u32> need_list, need_n;   // knn_fb: [0] count, [1..] queries knn_tile_kernel left to knn_kernel
     DevBuf<u32> nbr, nbr_n, nbr_prev;   // nbr_prev: lists of the previous evaluation, original indices, rows by original index
@@ -646,7 +646,7 @@ static void run_pairs_t(b200cvt_ctx* h) {
             }
             CUDA_CHECK(cudaMemsetAsync(h->facet_list_n.p, 0, sizeof(u32), h->stream));
             FacetFilterArgs fl;
-            fl.ball = h->facet_ball.p; fl.facet_cell = h->facet_cell.p; fl.T = h->T; fl.cellflag = (const uint8_t*)h->cellflag.p;
+            fl.ball = h->facet_ball.p; fl.rad = h->facet_rad.p; fl.facet_cell = h->facet_cell.p; fl.T = h->T; fl.cellflag = (const uint8_t*)h->cellflag.p;
             fl.cell_range = h->cell_range.p; fl.facet_guess = h->facet_guess.p; fl.rank_of = h->rank_of.p; fl.xs = h->xs.p;
             fl.g = h->g; fl.list = h->facet_list.p; fl.list_n = h->facet_list_n.p;
             LAUNCH(h, facet_filter_kernel<D>, div_up(h->T, 256 * FFILT_PER_THREAD), 256, 0, fl);
@@ -1565,11 +1565,11 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
         }
         h->facet_guess.ensure(ne);
         LAUNCH(h, fill_u32_kernel, 1024, 256, 0, h->facet_guess.p, (size_t)ne, B200_NONE);
-        h->facet_ball.ensure(ne); h->facet_cell_valid = false;
+        h->facet_ball.ensure(ne); h->facet_rad.ensure(ne); h->facet_cell_valid = false;
         if (ne > 0) {
-            if (h->volumetric) LAUNCH(h, (facet_ball_kernel<3, 4>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
-            else if (D == 3) LAUNCH(h, (facet_ball_kernel<3, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
-            else LAUNCH(h, (facet_ball_kernel<6, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p);
+            if (h->volumetric) LAUNCH(h, (facet_ball_kernel<3, 4>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p, h->facet_rad.p);
+            else if (D == 3) LAUNCH(h, (facet_ball_kernel<3, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p, h->facet_rad.p);
+            else LAUNCH(h, (facet_ball_kernel<6, 3>), div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_ball.p, h->facet_rad.p);
         }
         h->mesh_vmax2 = 0.0;
         if (ne > 0) {

@@ -602,7 +602,7 @@ facet_task_kernel(const __grid_constant__ FacetPairArgs a) {
 // ---------------------------------------------------------------------------------------
 // once per mesh: bounding ball of every facet about its centroid, in float (radius inflated for the rounding)
 template <int D, int NC>
-__global__ void facet_ball_kernel(const double* tri, u32 T, float4* ball) {
+__global__ void facet_ball_kernel(const double* tri, u32 T, float4* ball, float* rad) {
     const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= T) return;
     const double* t = tri + (size_t)f * NC * D;
@@ -626,6 +626,7 @@ __global__ void facet_ball_kernel(const double* tri, u32 T, float4* ball) {
     double rho = sqrt(rho2);
     rho = rho * (1.0 + 1e-6) + 4e-7 * gmax + 1e-30;
     ball[f] = make_float4((float)gc[0], (float)gc[1], (float)gc[2], __double2float_ru(rho));
+    rad[f] = __double2float_ru(rho);
 }
 
 // once per grid: the grid cell of every facet centroid
@@ -646,7 +647,7 @@ __global__ void facet_cell_kernel(const double* tri, u32 T, GridParams g, u32* f
 }
 
 struct FacetFilterArgs {
-    const float4* ball; const u32* facet_cell; u32 T;
+    const float4* ball; const float* rad; const u32* facet_cell; u32 T;   // rad[f] = ball[f].w (the early exit reads 9 bytes per facet)
     const uint8_t* cellflag;      // [ncells] CELLF_* bits: an owned seed within 1 / 2 / 3 cells, cell occupied
     const uint2* cell_range;
     const u32* facet_guess; const u32* rank_of; const void* xs;
@@ -667,12 +668,12 @@ facet_filter_kernel(FacetFilterArgs a) {
     const int lane = threadIdx.x & 31;
     const u32 base_f = blockIdx.x * (256u * FFILT_PER_THREAD) + threadIdx.x;
     u32 cid[FFILT_PER_THREAD], fl[FFILT_PER_THREAD];
-    float4 b[FFILT_PER_THREAD];
+    float rw[FFILT_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < FFILT_PER_THREAD; ++k) {
         const u32 f = base_f + 256u * k;
         cid[k] = f < a.T ? a.facet_cell[f] : 0u;
-        b[k] = f < a.T ? a.ball[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rw[k] = f < a.T ? a.rad[f] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < FFILT_PER_THREAD; ++k) fl[k] = a.cellflag[cid[k]];
@@ -686,17 +687,18 @@ facet_filter_kernel(FacetFilterArgs a) {
             // (D > 3: the grid only sees the first three coordinates and the float ball only stores those, so neither
             // bound on delta holds in the facet's own space: every facet stays relevant)
             if (D > 3) rel = true;
-            else if (!(fl[k] & CELLF_WITHIN3) && (double)b[k].w <= 0.6 * h && (fl[k] & CELLF_OCCUPIED)) rel = false;
+            else if (!(fl[k] & CELLF_WITHIN3) && (double)rw[k] <= 0.6 * h && (fl[k] & CELLF_OCCUPIED)) rel = false;
             else if (fl[k] & CELLF_WITHIN1) rel = true;      // an owned seed next to the facet: relevant whatever R is
             else {
                 rel = true;
                 const u32 guess = a.facet_guess[f];
                 if (guess != B200_NONE) {
+                    const float4 bb = a.ball[f];
                     const SeedRec<D>* xs = (const SeedRec<D>*)a.xs;
                     const SeedRec<D>* r = xs + a.rank_of[guess];
-                    const double qx = r->p[0] - (double)b[k].x, qy = r->p[1] - (double)b[k].y, qz = r->p[2] - (double)b[k].z;
+                    const double qx = r->p[0] - (double)bb.x, qy = r->p[1] - (double)bb.y, qz = r->p[2] - (double)bb.z;
                     const double d2 = qx * qx + qy * qy + qz * qz;
-                    const double R = (2.0 * (double)b[k].w + sqrt(d2)) * (1.0 + 1e-6);
+                    const double R = (2.0 * (double)bb.w + sqrt(d2)) * (1.0 + 1e-6);
                     if (R <= h) rel = (fl[k] & CELLF_WITHIN1) != 0;
                     else if (R <= 2.0 * h) rel = (fl[k] & CELLF_WITHIN2) != 0;
                     else if (R <= 3.0 * h) rel = (fl[k] & CELLF_WITHIN3) != 0;
