@@ -223,6 +223,9 @@ class Handle:
         d["clip_planes"] = int(st[8])
         d["knn_queries"] = int(st[11])                            # seeds served by the last kNN launch (owned + halo when sharded)
         d["subdivision"] = dict(pieces=int(st[9]), pieces_uncertified=int(st[10]), seeds_collected=int(st[12]))
+        # volumetric handles reuse the three slots: cells integrated by the cell-first path, cells sent to the (tet, seed) path,
+        # bisectors applied to whole cells (vcell.cuh)
+        d["volumetric_cells"] = dict(direct=int(st[9]), tet_path=int(st[10]), bisectors=int(st[12]))
         d["facets_skipped_far_from_owned_seeds"] = int(st[13])    # sharded runs
         d["facets_uncertified"] = int(st[14])                     # home list ended inside the distance bound
         d["facets_subdivided"] = int(st[15] & 0xffffffff)         # ... of which covered by small pieces
@@ -299,7 +302,7 @@ class Handle:
         ms = np.zeros(6)
         n = C.c_uint64(0)
         _check(lib().b200cvt_get_cumulative(self._h, ms.ctypes.data_as(_dp), C.byref(n), int(reset)))
-        return dict(sort=ms[0], knn=ms[1], pairs=ms[2], clip=ms[3], clip_kernel=ms[4], evals=int(n.value))
+        return dict(sort=ms[0], knn=ms[1], pairs=ms[2], clip=ms[3], clip_kernel=ms[4], cells=ms[5], evals=int(n.value))
 
     def launch_count(self):
         return int(lib().b200cvt_launch_count(self._h))

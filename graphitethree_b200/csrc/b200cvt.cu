@@ -15,6 +15,7 @@
 #include "clip_flat.cuh"
 #include "facet_pairs.cuh"
 #include "clip_tet.cuh"
+#include "vcell.cuh"
 #include "comm.cuh"
 #include "lbfgs.cuh"
 #include "rdt.cuh"
@@ -310,6 +311,13 @@ struct b200cvt_ctx {
     bool has_mesh = false, weighted = false;
     DevBuf<double> tri, triw;
     DevBuf<uint8_t> tet_inner;         // volumetric: bit lf = face opposite to corner lf is shared with another tet
+    // volumetric cell-first path (vcell.cuh): inside / boundary grid of the mesh, lists of the cells that need the tet path
+    DevBuf<u32> vgrid_cells, vgrid_need, facet_list2; DevBuf<uint2> tet_gbox; VGrid vg; bool vgrid_valid = false; u32 vgrid_R = 0;
+    size_t vgrid_ncell = 0; bool vneed_active = false;   // the facet walk is restricted to the tets near the cells of the tet path
+    DevBuf<u32> vc_bnd, vc_redo_a, vc_redo_b, vc_n;
+    bool use_vcell = true;
+    cudaEvent_t evc[2] = {nullptr, nullptr};   // around the cell stage
+    bool evc_used = false;
     DevBuf<u32> facet_guess;
     // surface meshes: host copies kept for the facet adjacency the RDT extraction needs (built on first use)
     std::vector<u32> host_elems, host_perm;
@@ -401,7 +409,7 @@ struct b200cvt_ctx {
     bool ev_valid = false;
     u64 host_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool ev_pending = false;          // phase events recorded but not yet accumulated
-    double cum_ms[6] = {0, 0, 0, 0, 0, 0};  // sort+grid, kNN+bisectors, pairs, clip phase (+redo), clip kernel alone, -
+    double cum_ms[6] = {0, 0, 0, 0, 0, 0};  // sort+grid, kNN+bisectors, pairs, clip phase (+redo), clip kernel alone, volumetric cell stage
     u64 cum_evals = 0;
 
     u32 slice_len() const { return (S + nranks - 1) / nranks; }
@@ -450,6 +458,13 @@ static void sync_stream(b200cvt_ctx* h) {
         }
         float tk = 0.f;
         if (h->evk[0] && cudaEventElapsedTime(&tk, h->evk[0], h->evk[1]) == cudaSuccess) h->cum_ms[4] += tk;
+        if (h->evc_used) {
+            // volumetric: the cell stage runs between the kNN and the facet walk (its output restricts the walk); it is
+            // accounted to the clip phase
+            float tc = 0.f;
+            if (cudaEventElapsedTime(&tc, h->evc[0], h->evc[1]) == cudaSuccess) { h->cum_ms[5] += tc; h->cum_ms[2] -= tc; h->cum_ms[3] += tc; }
+            h->evc_used = false;
+        }
         h->cum_evals++;
         h->ev_pending = false;
     }
@@ -652,6 +667,14 @@ static void run_pairs_t(b200cvt_ctx* h) {
             LAUNCH(h, facet_filter_kernel<D>, div_up(h->T, 256 * FFILT_PER_THREAD), 256, 0, fl);
             a.facet_list = h->facet_list.p; a.facet_list_n = h->facet_list_n.p;
         }
+        if (NC == 4 && h->T > 0 && h->vneed_active) {
+            // volumetric: only the tets near a cell that goes through the (tet, seed) path (need bits of vcell_kernel)
+            h->facet_list2.ensure((size_t)h->T + 1);
+            u32* n2 = h->facet_list2.p + h->T;
+            CUDA_CHECK(cudaMemsetAsync(n2, 0, sizeof(u32), h->stream));
+            LAUNCH(h, vtet_filter_kernel, div_up(h->T, 256), 256, 0, h->tet_gbox.p, a.facet_list, a.facet_list_n, h->T, h->vg, h->facet_list2.p, n2);
+            a.facet_list = h->facet_list2.p; a.facet_list_n = n2;
+        }
         if (h->T > 0) {
             LAUNCH(h, (facet_home_kernel<D, NC>), div_up(h->T, 128), 128, 0, a);
             if (NC == 3) {
@@ -703,20 +726,136 @@ static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
     LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
 }
 
+// inside / boundary grid of the tet mesh (vcell.cuh), about one grid cell per seed spacing; rebuilt when the seed count
+// changes by more than a quarter
+static void ensure_vgrid(b200cvt_ctx* h) {
+    double maxext = 0.0;
+    for (int a = 0; a < 3; ++a) maxext = std::max(maxext, h->bb_hi[a] - h->bb_lo[a]);
+    if (!(maxext > 0.0)) maxext = 1.0;
+    u32 R = (u32)std::ceil(1.25 * std::cbrt((double)std::max<u32>(h->S, 1)));
+    R = std::max<u32>(8, std::min<u32>(R, 160));
+    if (h->vgrid_valid && 4 * R >= 3 * h->vgrid_R && 4 * R <= 5 * h->vgrid_R) return;
+    VGrid& g = h->vg;
+    const double margin = 1e-3 * maxext;
+    g.h = (maxext + 2.0 * margin) / (double)R;
+    g.inv_h = 1.0 / g.h;
+    size_t ncell = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.lo[a] = h->bb_lo[a] - margin;
+        g.res[a] = std::max(1, (int)std::ceil((h->bb_hi[a] - h->bb_lo[a] + 2.0 * margin) * g.inv_h));
+        ncell *= (size_t)g.res[a];
+    }
+    h->vgrid_cells.ensure(ncell / 4 + 1);
+    h->vgrid_need.ensure(ncell / 32 + 2);
+    h->tet_gbox.ensure(std::max<size_t>(h->T, 1));
+    h->vgrid_ncell = ncell;
+    g.cells = h->vgrid_cells.p;
+    g.need = h->vgrid_need.p; g.need_all = h->vgrid_need.p + (ncell / 32 + 1);
+    CUDA_CHECK(cudaMemsetAsync(g.cells, 0, sizeof(u32) * (ncell / 4 + 1), h->stream));
+    if (h->T > 0) {
+        const int nslab = std::max(1, std::min(g.res[2], 8));
+        dim3 grid(div_up(h->T, 128), (unsigned)nslab);
+        vgrid_mark_kernel<<<grid, 128, 0, h->stream>>>(h->tri.p, h->tet_inner.p, h->T, g, nslab, h->tet_gbox.p);
+        h->launches++;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    h->vgrid_valid = true; h->vgrid_R = R;
+}
+
+static void launch_vcell(b200cvt_ctx* h, VCellArgs& a) {
+    if (a.nseeds == 0 && !a.nseeds_dev) return;
+    const u32 blocks = a.nseeds_dev ? (u32)h->num_sms * 8u : std::min<u32>(div_up(a.nseeds, VC_WARPS), (u32)h->num_sms * 8u);
+    LAUNCH(h, vcell_kernel, blocks, VC_WARPS * 32, 0, a);
+}
+
+// kNN with kbig neighbours for the seeds of a list (rows by list slot)
+static void knn_for_list(b200cvt_ctx* h, const u32* list, u32 n, u32 kbig) {
+    h->nbr_big.ensure((size_t)n * kbig);
+    h->nbr_big_n.ensure(n);
+    KnnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+    a.query_list = list; a.ksize = nullptr; a.out_by_slot = 1;
+    a.k = kbig; a.kstride = kbig; a.S = h->S; a.qbegin = 0; a.qend = n;
+    a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+    launch_knn<3>(h, a, n);
+}
+
 static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
     const u32 S = h->S;
-    run_pairs_t<3, 4>(h);
-    CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+    const u32 nown = h->qend() - h->qbegin();
     h->out_s.ensure(S); h->out_v.ensure((size_t)S * 3);
     h->redo_a.ensure(S); h->redo_b.ensure(S); h->redo_n.ensure(4);
     CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
-    const u32 nown = h->qend() - h->qbegin();
+    const u32 kmax = std::min<u32>(B200CVT_KMAX, S > 0 ? S - 1 : 0);
+    const bool vcell = h->use_vcell && nown > 0 && mode != 2;
+    if (vcell) {
+        // cell stage: every owned seed builds its Voronoi cell once; cells inside the domain are integrated on the spot
+        NvtxRange r("b200cvt:cells");
+        if (!h->evc[0]) for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&h->evc[i]));
+        ensure_vgrid(h);
+        h->vc_bnd.ensure(S); h->vc_redo_a.ensure(S); h->vc_redo_b.ensure(S); h->vc_n.ensure(4);
+        CUDA_CHECK(cudaMemsetAsync(h->vc_n.p, 0, 4 * sizeof(u32), h->stream));
+        CUDA_CHECK(cudaEventRecord(h->evc[0], h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->vgrid_need.p, 0, sizeof(u32) * (h->vgrid_ncell / 32 + 2), h->stream));
+        VCellArgs v;
+        memset(&v, 0, sizeof(v));
+        v.xs = h->xs.p; v.nbr = h->nbr.p; v.nbr_n = h->nbr_n.p; v.kstride = h->kstride; v.nbr_by_slot = 0;
+        v.seed_list = nullptr; v.nseeds = nown; v.qbegin = h->qbegin();
+        v.mode = mode; v.check_SR = check_SR; v.S = S;
+        double maxext = 0.0;
+        for (int a = 0; a < 3; ++a) maxext = std::max(maxext, h->bb_hi[a] - h->bb_lo[a]);
+        if (!(maxext > 0.0)) maxext = 1.0;
+        for (int a = 0; a < 3; ++a) { v.box_lo[a] = h->bb_lo[a] - 0.5 * maxext; v.box_hi[a] = h->bb_hi[a] + 0.5 * maxext; }
+        v.vg = h->vg;
+        v.out_s = h->out_s.p; v.out_v = h->out_v.p; v.flags = h->flags.p;
+        v.redo_list = check_SR ? h->vc_redo_a.p : nullptr; v.redo_n = h->vc_n.p;
+        v.bnd_list = h->vc_bnd.p; v.bnd_n = h->vc_n.p + 2;
+        v.stats = h->want_stats ? h->stats.p : nullptr;
+        launch_vcell(h, v);
+        if (check_SR) {
+            // enlarge_neighborhood loop (generic_RVD.h:2330-2346) on whole cells, batched over the seeds that need it
+            u32 kbig = 40;
+            u32* cur_list = h->vc_redo_a.p; u32* nxt_list = h->vc_redo_b.p;
+            int cur_slot = 0;
+            for (;;) {
+                u32 nredo = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&nredo, h->vc_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                if (nredo == 0) break;
+                h->host_stats[4] += nredo;
+                kbig = std::min<u32>(kbig, kmax);
+                knn_for_list(h, cur_list, nredo, kbig);
+                const int nslot = cur_slot ^ 1;
+                CUDA_CHECK(cudaMemsetAsync(h->vc_n.p + nslot, 0, sizeof(u32), h->stream));
+                VCellArgs r2 = v;
+                r2.nbr = h->nbr_big.p; r2.nbr_n = h->nbr_big_n.p; r2.kstride = kbig; r2.nbr_by_slot = 1;
+                r2.seed_list = cur_list; r2.nseeds = nredo;
+                r2.redo_list = kbig >= kmax ? nullptr : nxt_list; r2.redo_n = h->vc_n.p + nslot;
+                launch_vcell(h, r2);
+                std::swap(cur_list, nxt_list);
+                cur_slot = nslot;
+                if (kbig >= kmax) break;
+                kbig *= 2;
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(h->evc[1], h->stream));
+        h->evc_used = true;
+    }
+    // (tet, seed) stage for the rest: candidate rows from the facet walk with 4 corners, one warp per seed
+    h->vneed_active = vcell;
+    { NvtxRange r("b200cvt:facet walk (pairs)"); run_pairs_t<3, 4>(h); }
+    h->vneed_active = false;
+    CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+    if (mode == 2) { CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream)); return; }
+    NvtxRange nvtx_clip("b200cvt:clip+integrate (tets)");
     TetClipArgs c;
     memset(&c, 0, sizeof(c));
     c.xs = h->xs.p; c.nbr = h->nbr.p; c.nbr_n = h->nbr_n.p; c.kstride = h->kstride; c.nbr_by_slot = 0;
     c.tet = h->tri.p; c.tet_inner = h->tet_inner.p;
     c.pair_cnt = h->pair_cnt.p; c.pair_facet = h->pair_facet.p; c.cap = h->pair_cap;
     c.seed_list = nullptr; c.nseeds = nown; c.qbegin = h->qbegin();
+    if (vcell) { c.seed_list = h->vc_bnd.p; c.nseeds = 0; c.nseeds_dev = h->vc_n.p + 2; }
     c.mode = mode; c.check_SR = check_SR; c.S = S;
     c.out_s = h->out_s.p; c.out_v = h->out_v.p; c.flags = h->flags.p;
     c.redo_list = check_SR ? h->redo_a.p : nullptr; c.redo_n = h->redo_n.p;
@@ -735,27 +874,18 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
             if (nredo == 0) break;
             h->host_stats[4] += nredo;
-            kbig = std::min<u32>(kbig, B200CVT_KMAX);
-            kbig = std::min<u32>(kbig, S - 1);
-            h->nbr_big.ensure((size_t)nredo * kbig);
-            h->nbr_big_n.ensure(nredo);
-            KnnArgs a;
-            memset(&a, 0, sizeof(a));
-            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
-            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
-            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
-            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
-            launch_knn<3>(h, a, nredo);
+            kbig = std::min<u32>(kbig, kmax);
+            knn_for_list(h, cur_list, nredo, kbig);
             int nslot = cur_slot ^ 1;
             CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
             TetClipArgs r = c;
             r.nbr = h->nbr_big.p; r.nbr_n = h->nbr_big_n.p; r.kstride = kbig; r.nbr_by_slot = 1;
-            r.seed_list = cur_list; r.nseeds = nredo;
+            r.seed_list = cur_list; r.nseeds = nredo; r.nseeds_dev = nullptr;
             r.redo_list = nxt_list; r.redo_n = h->redo_n.p + nslot;
             launch_clip_tet(h, r);
             std::swap(cur_list, nxt_list);
             cur_slot = nslot;
-            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) break;
+            if (kbig >= kmax) break;
             kbig *= 2;
         }
     }
@@ -1424,6 +1554,7 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
         CUDA_CHECK(cudaSetDevice(device));
         std::unique_ptr<b200cvt_ctx> h(new b200cvt_ctx);
         h->device = device; h->dim = dim; h->volumetric = volumetric;
+        { const char* e = getenv("B200CVT_VCELL"); h->use_vcell = !(e && atoi(e) == 0); }
         CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
@@ -1440,6 +1571,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     comm_release(h);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
+    for (int i = 0; i < 2; ++i) if (h->evc[i]) cudaEventDestroy(h->evc[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;                         // DevBuf members release their device memory
 }
@@ -1588,7 +1720,7 @@ int b200cvt_set_mesh(b200cvt_handle h, const double* vertices, uint32_t nv, uint
             else LAUNCH(h, facet_area_kernel<6>, div_up(ne, 256), 256, 0, h->tri.p, ne, h->facet_area.p);
         }
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        h->has_mesh = true; h->grid_valid = false; h->knn_valid = false; h->has_results = false; h->pair_cap = 0;
+        h->has_mesh = true; h->grid_valid = false; h->knn_valid = false; h->has_results = false; h->pair_cap = 0; h->vgrid_valid = false;
     });
 }
 

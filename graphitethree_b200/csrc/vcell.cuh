@@ -1,0 +1,545 @@
+// vcell.cuh — volumetric mode, cell-first path: the Voronoi cell of a seed is built ONCE, cooperatively by a warp, and
+// integrated directly when it provably lies inside the tetrahedralised domain; only the cells that may touch the domain
+// boundary go through the (tetrahedron, seed) clipping of clip_tet.cuh.
+//
+// What the reference computes for a seed i in volumetric mode (generic_RVD.h:1464-1597, RVD.cpp:428-527, 791-910) is a
+// sum over the tets t that meet its cell of integrals over  t ∩ cell(i):  the mass and first moment (Lloyd), or, from the
+// faces of t ∩ cell(i) that are NOT shared with another tet, pyramids with apex p_i (CVT energy and gradient). The tets
+// partition the domain, the faces between two tets are skipped by the reference itself (visit_inner_tets = false) or cancel
+// (volumes add), so for a cell that does not reach the domain boundary the sum is the integral over the cell and the
+// tets are irrelevant: ~35 (tet, seed) clips of 8-20 planes each collapse into one cell of ~15 faces. The bisectors are
+// applied in the reference's order (increasing distance) with the reference's security-radius rule (4.1 R^2,
+// generic_RVD.h:2295-2328), now on the whole cell, every new vertex is the reference's interpolation on a cell edge
+// (Vertex::intersect_geom, generic_RVD_vertex.h:976-1030), the conflict zone is the reference's flood fill from the
+// furthest vertex (ConvexCell::clip_by_plane, generic_RVD_cell.h:886-1160). Sums differ from the reference's by the order
+// of the additions only (1e-14 relative; the parity tolerance is 1e-9).
+//
+// Cell = dual form, as the reference: a cell vertex is a triangle of three plane ids with three adjacent cell vertices and a
+// point; 64 slots per warp in shared memory. A clip is data-parallel over the cell: every lane tests its vertices (two
+// slots per lane), ballots give the conflict zone, every zone edge that leads to a kept vertex creates one new vertex in a
+// free slot (prefix sum over the lanes), and the ring of new vertices is closed through a table indexed by plane id
+// (a new vertex (P, v1, v2) is followed by the one whose v1 is its v2). No sequential walk anywhere.
+//
+// "Provably inside": a static grid over the mesh (vgrid_mark_kernel, per mesh) flags the grid cells a boundary face may
+// touch and the grid cells whose centre lies in a tet; a Voronoi cell all of whose overlapped grid cells are inside and
+// untouched is inside the domain. Everything else (hull cells, cells near the boundary, seeds outside the domain, cells
+// that overflow the slots) is appended to a list for clip_tet_kernel.
+#pragma once
+#include "common.cuh"
+#include "clip.cuh"
+
+#define VC_WARPS 8
+#define VC_SLOTS 64
+#define VG_BND 1u      // a boundary face of the tet mesh may touch the grid cell
+#define VG_IN 2u       // the centre of the grid cell lies in a tet
+#define VG_MAXCHECK 1728u
+
+struct VGrid {
+    double lo[3];
+    double h, inv_h;
+    int res[3];
+    u32* cells;        // one byte per grid cell, four per word
+    u32* need;         // per evaluation: one bit per grid cell, set where a cell of the tet path may lie (need[0] bit 31 of the
+                       // last word is not special; need_all[0] != 0 means "everywhere")
+    u32* need_all;
+};
+
+__device__ __forceinline__ u32 vg_byte(const VGrid& g, int cx, int cy, int cz) {
+    const u32 idx = ((u32)cz * (u32)g.res[1] + (u32)cy) * (u32)g.res[0] + (u32)cx;
+    return (__ldg(g.cells + (idx >> 2)) >> ((idx & 3u) * 8u)) & 0xffu;
+}
+__device__ __forceinline__ void vg_or(const VGrid& g, int cx, int cy, int cz, u32 bit) {
+    const u32 idx = ((u32)cz * (u32)g.res[1] + (u32)cy) * (u32)g.res[0] + (u32)cx;
+    const u32 m = bit << ((idx & 3u) * 8u);
+    if ((g.cells[idx >> 2] & m) != m) atomicOr(g.cells + (idx >> 2), m);
+}
+
+// per mesh: thread per (tet, z-slab of its bounding box)
+__global__ void vgrid_mark_kernel(const double* __restrict__ tet, const uint8_t* __restrict__ inner, u32 T, VGrid g, int nslab, uint2* __restrict__ tet_gbox) {
+    const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= T) return;
+    const int slab = blockIdx.y;
+    double p[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[k][c] = tet[(size_t)f * 12 + k * 3 + c];
+    const u32 in = inner[f];
+    // boundary faces: every grid cell their bounding box touches
+    for (int lf = 0; lf < 4; ++lf) {
+        if ((in >> lf) & 1u) continue;
+        int c0[3], c1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double mn = 1e300, mx = -1e300;
+            for (int k = 0; k < 4; ++k) if (k != lf) { mn = fmin(mn, p[k][c]); mx = fmax(mx, p[k][c]); }
+            c0[c] = max(0, (int)floor((mn - g.lo[c]) * g.inv_h - 1e-6));
+            c1[c] = min(g.res[c] - 1, (int)floor((mx - g.lo[c]) * g.inv_h + 1e-6));
+        }
+        for (int z = c0[2] + slab; z <= c1[2]; z += nslab)
+            for (int y = c0[1]; y <= c1[1]; ++y)
+                for (int x = c0[0]; x <= c1[0]; ++x) vg_or(g, x, y, z, VG_BND);
+    }
+    // grid cell centres inside the tet (closed: a centre on a face shared by two tets is marked by both)
+    double U[3], V[3], W[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { U[c] = p[1][c] - p[0][c]; V[c] = p[2][c] - p[0][c]; W[c] = p[3][c] - p[0][c]; }
+    const double det = U[0] * (V[1] * W[2] - V[2] * W[1]) - U[1] * (V[0] * W[2] - V[2] * W[0]) + U[2] * (V[0] * W[1] - V[1] * W[0]);
+    int c0[3], c1[3];
+    u32 b0[3], b1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double mn = fmin(fmin(p[0][c], p[1][c]), fmin(p[2][c], p[3][c]));
+        const double mx = fmax(fmax(p[0][c], p[1][c]), fmax(p[2][c], p[3][c]));
+        c0[c] = max(0, (int)ceil((mn - g.lo[c]) * g.inv_h - 0.5 - 1e-9));
+        c1[c] = min(g.res[c] - 1, (int)floor((mx - g.lo[c]) * g.inv_h - 0.5 + 1e-9));
+        b0[c] = (u32)max(0, min(g.res[c] - 1, (int)floor((mn - g.lo[c]) * g.inv_h - 1e-6)));
+        b1[c] = (u32)max(0, min(g.res[c] - 1, (int)floor((mx - g.lo[c]) * g.inv_h + 1e-6)));
+    }
+    // the grid cells the tet's bounding box touches (8 bits per bound: the grid has at most 160 cells per axis)
+    if (slab == 0) tet_gbox[f] = make_uint2(b0[0] | (b0[1] << 8) | (b0[2] << 16), b1[0] | (b1[1] << 8) | (b1[2] << 16));
+    if (det == 0.0) return;
+    const double tol = 1e-9 * fabs(det);
+    const double sg = det > 0.0 ? 1.0 : -1.0;
+    for (int z = c0[2] + slab; z <= c1[2]; z += nslab)
+        for (int y = c0[1]; y <= c1[1]; ++y)
+            for (int x = c0[0]; x <= c1[0]; ++x) {
+                double q[3] = {g.lo[0] + (x + 0.5) * g.h - p[0][0], g.lo[1] + (y + 0.5) * g.h - p[0][1], g.lo[2] + (z + 0.5) * g.h - p[0][2]};
+                // barycentric coordinates times det (Cramer)
+                const double b1 = q[0] * (V[1] * W[2] - V[2] * W[1]) - q[1] * (V[0] * W[2] - V[2] * W[0]) + q[2] * (V[0] * W[1] - V[1] * W[0]);
+                const double b2 = U[0] * (q[1] * W[2] - q[2] * W[1]) - U[1] * (q[0] * W[2] - q[2] * W[0]) + U[2] * (q[0] * W[1] - q[1] * W[0]);
+                const double b3 = U[0] * (V[1] * q[2] - V[2] * q[1]) - U[1] * (V[0] * q[2] - V[2] * q[0]) + U[2] * (V[0] * q[1] - V[1] * q[0]);
+                const double s1 = b1 * sg, s2 = b2 * sg, s3 = b3 * sg, s0 = fabs(det) - s1 - s2 - s3;
+                if (s0 >= -tol && s1 >= -tol && s2 >= -tol && s3 >= -tol) vg_or(g, x, y, z, VG_IN);
+            }
+}
+
+// the tets whose bounding box touches a grid cell where a cell of the tet path may lie (need bits set by vcell_kernel)
+__global__ void __launch_bounds__(256)
+vtet_filter_kernel(const uint2* __restrict__ tet_gbox, const u32* __restrict__ in_list, const u32* __restrict__ in_n, u32 T, VGrid g,
+                   u32* __restrict__ list, u32* __restrict__ list_n) {
+    const int lane = threadIdx.x & 31;
+    const u32 n = in_list ? *in_n : T;
+    const u32 e = blockIdx.x * 256u + threadIdx.x;
+    bool rel = false;
+    u32 f = 0;
+    if (e < n) {
+        f = in_list ? in_list[e] : e;
+        if (*g.need_all) rel = true;
+        else {
+            const uint2 b = tet_gbox[f];
+            const u32 x0 = b.x & 255u, y0 = (b.x >> 8) & 255u, z0 = (b.x >> 16) & 255u;
+            const u32 x1 = b.y & 255u, y1 = (b.y >> 8) & 255u, z1 = (b.y >> 16) & 255u;
+            for (u32 z = z0; z <= z1 && !rel; ++z)
+                for (u32 y = y0; y <= y1 && !rel; ++y) {
+                    const u32 row = (z * (u32)g.res[1] + y) * (u32)g.res[0];
+                    for (u32 x = x0; x <= x1; ++x) {
+                        const u32 idx = row + x;
+                        if ((__ldg(g.need + (idx >> 5)) >> (idx & 31u)) & 1u) { rel = true; break; }
+                    }
+                }
+        }
+    }
+    __shared__ u32 s_cnt[8], s_base;
+    const int w = threadIdx.x >> 5;
+    const u32 bal = __ballot_sync(B200_FULL, rel);
+    if (lane == 0) s_cnt[w] = (u32)__popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int i = 0; i < 8; ++i) { const u32 c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+        s_base = tot ? atomicAdd(list_n, tot) : 0u;
+    }
+    __syncthreads();
+    if (rel) list[s_base + s_cnt[w] + (u32)__popc(bal & ((1u << lane) - 1u))] = f;
+}
+
+struct VCellArgs {
+    const void* xs;
+    const u32* nbr; const u32* nbr_n; u32 kstride;
+    int nbr_by_slot;
+    const u32* seed_list; u32 nseeds; const u32* nseeds_dev; u32 qbegin;
+    int mode, check_SR;
+    u32 S;
+    double box_lo[3], box_hi[3];
+    VGrid vg;
+    double* out_s; double* out_v; uint8_t* flags;
+    u32* redo_list; u32* redo_n;     // inside the domain, neighbour list used up before the radius test passed (check_SR)
+    u32* bnd_list; u32* bnd_n;       // not provably inside the domain: (tet, seed) path
+    unsigned long long* stats;       // volumetric handles: [9] cells integrated here, [10] cells sent to the tet path, [12] bisectors applied
+};
+
+__device__ __forceinline__ bool vc_in(u32 lo, u32 hi, u32 t) { return ((((t & 32u) ? hi : lo) >> (t & 31u)) & 1u) != 0u; }
+
+__device__ __forceinline__ u32 vc_kth_free(u32 free_lo, u32 free_hi, u32 nfl, u32 k) {
+    return k < nfl ? __fns(free_lo, 0, (int)k + 1) : 32u + __fns(free_hi, 0, (int)(k - nfl) + 1);
+}
+
+__device__ __forceinline__ double vc_warp_max_nonneg(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const u32 hi = (u32)(b >> 32), lo = (u32)b;
+    const u32 mh = __reduce_max_sync(B200_FULL, hi);
+    const u32 ml = __reduce_max_sync(B200_FULL, hi == mh ? lo : 0u);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+
+struct VcState {
+    u32 used_lo, used_hi, np;
+    bool overflow;
+};
+
+// max squared distance of the cell's vertices to the seed
+__device__ __forceinline__ double vc_radius2(const double (*P)[VC_SLOTS], const VcState& st, double pix, double piy, double piz, int lane) {
+    double r = 0.0;
+    if ((st.used_lo >> lane) & 1u) {
+        const double dx = P[0][lane] - pix, dy = P[1][lane] - piy, dz = P[2][lane] - piz;
+        double d = dx * dx; d += dy * dy; d += dz * dz;
+        r = d;
+    }
+    if ((st.used_hi >> lane) & 1u) {
+        const double dx = P[0][lane + 32] - pix, dy = P[1][lane + 32] - piy, dz = P[2][lane + 32] - piz;
+        double d = dx * dx; d += dy * dy; d += dz * dz;
+        r = fmax(r, d);
+    }
+    return vc_warp_max_nonneg(r);
+}
+
+// ConvexCell::clip_by_plane with the bisector of (pi, pj), the whole warp on one cell. Returns true if the plane cut.
+__device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, VcState& st,
+                                        double pix, double piy, double piz, double pjx, double pjy, double pjz, int lane) {
+    const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
+    double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0, rA = 0.0, rB = 0.0;
+    if (uA) {
+        ax = P[0][lane]; ay = P[1][lane]; az = P[2][lane];
+        rA += (pjx - ax) * (pjx - ax); rA -= (pix - ax) * (pix - ax);
+        rA += (pjy - ay) * (pjy - ay); rA -= (piy - ay) * (piy - ay);
+        rA += (pjz - az) * (pjz - az); rA -= (piz - az) * (piz - az);
+    }
+    if (uB) {
+        bx = P[0][lane + 32]; by = P[1][lane + 32]; bz = P[2][lane + 32];
+        rB += (pjx - bx) * (pjx - bx); rB -= (pix - bx) * (pix - bx);
+        rB += (pjy - by) * (pjy - by); rB -= (piy - by) * (piy - by);
+        rB += (pjz - bz) * (pjz - bz); rB -= (piz - bz) * (piz - bz);
+    }
+    const bool cA = uA && rA < 0.0, cB = uB && rB < 0.0;
+    const u32 c0lo = __ballot_sync(B200_FULL, cA);
+    const u32 c0hi = st.used_hi ? __ballot_sync(B200_FULL, cB) : 0u;
+    if ((c0lo | c0hi) == 0u) return false;
+    if (st.np >= 255u) { st.overflow = true; return false; }
+    const uchar4 tA = uA ? T[lane] : make_uchar4(0, 0, 0, 0);
+    const uchar4 tB = uB ? T[lane + 32] : make_uchar4(0, 0, 0, 0);
+    // conflict zone = the connected part of the negative vertices that holds the furthest one (flood fill)
+    u32 klo = c0lo, khi = c0hi;
+    if (__popc(c0lo) + __popc(c0hi) > 1) {
+        if (c0lo) { klo = c0lo & (0u - c0lo); khi = 0u; } else { klo = 0u; khi = c0hi & (0u - c0hi); }
+        for (int pass = 0; pass < 2; ++pass) {
+            for (;;) {
+                const bool jA = cA && (((klo >> lane) & 1u) || vc_in(klo, khi, tA.x) || vc_in(klo, khi, tA.y) || vc_in(klo, khi, tA.z));
+                const bool jB = cB && (((khi >> lane) & 1u) || vc_in(klo, khi, tB.x) || vc_in(klo, khi, tB.y) || vc_in(klo, khi, tB.z));
+                const u32 nlo = __ballot_sync(B200_FULL, jA);
+                const u32 nhi = c0hi ? __ballot_sync(B200_FULL, jB) : 0u;
+                if (nlo == klo && nhi == khi) break;
+                klo = nlo; khi = nhi;
+            }
+            if ((klo == c0lo && khi == c0hi) || pass == 1) break;
+            // the negative vertices are not connected (rounding): restart from the furthest one, as the reference does
+            double best = cA ? rA : 0.0; u32 bslot = cA ? (u32)lane : 0xffu;
+            if (cB && (!(cA) || rB < best)) { best = rB; bslot = (u32)lane + 32u; }
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const double ob = __shfl_xor_sync(B200_FULL, best, m);
+                const u32 os = __shfl_xor_sync(B200_FULL, bslot, m);
+                if (os != 0xffu && (bslot == 0xffu || ob < best || (ob == best && os < bslot))) { best = ob; bslot = os; }
+            }
+            klo = bslot < 32u ? (1u << bslot) : 0u;
+            khi = bslot < 32u ? 0u : (1u << (bslot - 32u));
+        }
+    }
+    const u32 new_v = st.np++;
+    const bool zA = (klo >> lane) & 1u, zB = (khi >> lane) & 1u;
+    u32 eA = 0u, eB = 0u;       // bit e: edge e of the zone vertex leads to a kept vertex
+    if (zA) eA = (vc_in(klo, khi, tA.x) ? 0u : 1u) | (vc_in(klo, khi, tA.y) ? 0u : 2u) | (vc_in(klo, khi, tA.z) ? 0u : 4u);
+    if (zB) eB = (vc_in(klo, khi, tB.x) ? 0u : 1u) | (vc_in(klo, khi, tB.y) ? 0u : 2u) | (vc_in(klo, khi, tB.z) ? 0u : 4u);
+    const u32 cnt = __popc(eA) + __popc(eB);
+    const u32 lt = (1u << lane) - 1u;
+    const u32 q0 = __ballot_sync(B200_FULL, cnt & 1u), q1 = __ballot_sync(B200_FULL, cnt & 2u), q2 = __ballot_sync(B200_FULL, cnt & 4u);
+    u32 k = __popc(q0 & lt) + 2u * __popc(q1 & lt) + 4u * __popc(q2 & lt);
+    const u32 total = __popc(q0) + 2u * __popc(q1) + 4u * __popc(q2);
+    const u32 free_lo = ~st.used_lo, free_hi = ~st.used_hi;
+    const u32 nfl = __popc(free_lo);
+    if (total > nfl + __popc(free_hi)) { st.overflow = true; return true; }
+    if (total == 0u) { st.used_lo = 0u; st.used_hi = 0u; return true; }     // everything removed
+    // bisector (ConvexCell::clip_by_plane / intersect_geom): n = pi - pj, d = -(n . (pi + pj)) / 2
+    const double nx = pix - pjx, ny = piy - pjy, nz = piz - pjz;
+    double dd = 0.0;
+    dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
+    dd = 0.5 * dd;
+    uint8_t* Tb = (uint8_t*)T;
+    u32 newN[6], newV2[6];
+    u32 my_lo = 0u, my_hi = 0u;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const u32 em = half ? eB : eA;
+        const u32 t = half ? (u32)lane + 32u : (u32)lane;
+        const uchar4 tt = half ? tB : tA;
+        const double tx = half ? bx : ax, ty = half ? by : ay, tz = half ? bz : az;
+        uchar4 vt = make_uchar4(0, 0, 0, 0);
+        if (em) vt = V[t];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            newN[half * 3 + e] = 0xffu; newV2[half * 3 + e] = 0u;
+            if (!((em >> e) & 1u)) continue;
+            const u32 nb = e == 0 ? tt.x : (e == 1 ? tt.y : tt.z);
+            const u32 v1 = e == 0 ? vt.y : (e == 1 ? vt.z : vt.x);
+            const u32 v2 = e == 0 ? vt.z : (e == 1 ? vt.x : vt.y);
+            const u32 N = vc_kth_free(free_lo, free_hi, nfl, k);
+            ++k;
+            const double kx = P[0][nb], ky = P[1][nb], kz = P[2][nb];
+            double l1 = 0.0, l2 = 0.0;
+            l1 += kx * nx; l1 += ky * ny; l1 += kz * nz;
+            l2 += tx * nx; l2 += ty * ny; l2 += tz * nz;
+            l1 = fabs(l1 + dd); l2 = fabs(l2 + dd);
+            const double l12 = l1 + l2;
+            if (l12 > 1e-30) { l1 /= l12; l2 /= l12; } else { l1 = 0.5; l2 = 0.5; }
+            P[0][N] = l1 * tx + l2 * kx; P[1][N] = l1 * ty + l2 * ky; P[2][N] = l1 * tz + l2 * kz;
+            V[N] = make_uchar4((unsigned char)new_v, (unsigned char)v1, (unsigned char)v2, 0);
+            Tb[N * 4 + 0] = (unsigned char)nb;
+            // the kept vertex now sees the new one where it saw the zone vertex
+            const uchar4 tn = T[nb];
+            const u32 idx = (tn.y == t ? 1u : 0u) | (tn.z == t ? 2u : 0u);
+            Tb[nb * 4 + idx] = (unsigned char)N;
+            B[v1] = N;
+            newN[half * 3 + e] = N; newV2[half * 3 + e] = v2;
+            if (N < 32u) my_lo |= 1u << N; else my_hi |= 1u << (N - 32u);
+        }
+    }
+    __syncwarp();
+    // close the ring: the new vertex (P, v1, v2) is followed by the new vertex whose v1 is v2
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (newN[i] == 0xffu) continue;
+        const u32 nxn = B[newV2[i]];
+        Tb[newN[i] * 4 + 1] = (unsigned char)nxn;
+        Tb[nxn * 4 + 2] = (unsigned char)newN[i];
+    }
+    const u32 add_lo = __reduce_or_sync(B200_FULL, my_lo), add_hi = __reduce_or_sync(B200_FULL, my_hi);
+    st.used_lo = (st.used_lo & ~klo) | add_lo;
+    st.used_hi = (st.used_hi & ~khi) | add_hi;
+    __syncwarp();
+    return true;
+}
+
+// Geom::tetra_volume<3> (geometry.h:483-524)
+__device__ __forceinline__ double vc_tet_volume(double ax, double ay, double az, double bx, double by, double bz,
+                                                double cx, double cy, double cz, double dx, double dy, double dz) {
+    const double U0 = bx - ax, U1 = by - ay, U2 = bz - az;
+    const double V0 = cx - ax, V1 = cy - ay, V2 = cz - az;
+    const double W0 = dx - ax, W1 = dy - ay, W2 = dz - az;
+    const double x = V1 * W2 - V2 * W1;
+    const double y = V2 * W0 - V0 * W2;
+    const double z = V0 * W1 - V1 * W0;
+    return fabs((U0 * x + U1 * y + U2 * z) / 6.0);
+}
+
+__global__ void __launch_bounds__(VC_WARPS * 32) vcell_kernel(VCellArgs a) {
+    __shared__ double sP[VC_WARPS][3][VC_SLOTS];
+    __shared__ uchar4 sV[VC_WARPS][VC_SLOTS];
+    __shared__ uchar4 sT[VC_WARPS][VC_SLOTS];
+    __shared__ u32 sB[VC_WARPS][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double (*P)[VC_SLOTS] = sP[w];
+    uchar4* V = sV[w];
+    uchar4* T = sT[w];
+    u32* B = sB[w];
+    const SeedRec<3>* xs = (const SeedRec<3>*)a.xs;
+    const u32 nseeds = a.nseeds_dev ? *a.nseeds_dev : a.nseeds;
+    unsigned long long st_cells = 0, st_bnd = 0, st_clips = 0;
+    for (u32 si = blockIdx.x * VC_WARPS + w; si < nseeds; si += gridDim.x * VC_WARPS) {
+        const u32 s = a.seed_list ? a.seed_list[si] : a.qbegin + si;
+        const double pix = xs[s].p[0], piy = xs[s].p[1], piz = xs[s].p[2];
+        const size_t nrow = a.nbr_by_slot ? (size_t)si : (size_t)s;
+        const u32 nn = min(a.nbr_n[nrow], a.kstride);
+        const u32* nrowp = a.nbr + nrow * a.kstride;
+        __syncwarp();
+        if (lane < 8) {
+            const int b0 = lane & 1, b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1;
+            P[0][lane] = b0 ? a.box_hi[0] : a.box_lo[0];
+            P[1][lane] = b1 ? a.box_hi[1] : a.box_lo[1];
+            P[2][lane] = b2 ? a.box_hi[2] : a.box_lo[2];
+            uchar4 v = make_uchar4((unsigned char)b0, (unsigned char)(2 + b1), (unsigned char)(4 + b2), 0);
+            uchar4 t = make_uchar4((unsigned char)(lane ^ 1), (unsigned char)(lane ^ 2), (unsigned char)(lane ^ 4), 0);
+            if ((b0 + b1 + b2) & 1) {
+                unsigned char x = v.y; v.y = v.z; v.z = x;
+                x = t.y; t.y = t.z; t.z = x;
+            }
+            V[lane] = v; T[lane] = t;
+        }
+        __syncwarp();
+        VcState st;
+        st.used_lo = 0xffu; st.used_hi = 0u; st.np = 6u; st.overflow = false;
+        double R2 = vc_radius2(P, st, pix, piy, piz, lane);
+        bool sr_ok = false, done = false;
+        for (u32 base = 0; base < nn && !done; base += 32) {
+            double qx = 0.0, qy = 0.0, qz = 0.0, qd = 0.0;
+            if (base + lane < nn) {
+                const SeedRec<3>* r = xs + nrowp[base + lane];
+                qx = r->p[0]; qy = r->p[1]; qz = r->p[2];
+                const double dx = qx - pix, dy = qy - piy, dz = qz - piz;
+                qd = dx * dx; qd += dy * dy; qd += dz * dz;
+            }
+            const u32 cnt = min(32u, nn - base);
+            for (u32 l = 0; l < cnt; ++l) {
+                const double dj = shfl_d(qd, (int)l);
+                if (dj > 4.1 * R2) { sr_ok = true; done = true; break; }
+                ++st_clips;
+                const bool cut = vc_clip(P, V, T, B, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), lane);
+                if (st.overflow || (st.used_lo | st.used_hi) == 0u) { done = true; break; }
+                if (cut) R2 = vc_radius2(P, st, pix, piy, piz, lane);
+            }
+        }
+        const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
+        double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+        if (uA) { ax = P[0][lane]; ay = P[1][lane]; az = P[2][lane]; }
+        if (uB) { bx = P[0][lane + 32]; by = P[1][lane + 32]; bz = P[2][lane + 32]; }
+        // inside the domain?  every grid cell the cell's bounding box overlaps must be inside and free of boundary faces
+        const bool nonempty = (st.used_lo | st.used_hi) != 0u;
+        bool interior = !st.overflow && nonempty;
+        int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+        if (nonempty) {
+            const double big = 1e9;
+            if (uA) {
+                const double g0 = fmin(fmax((ax - a.vg.lo[0]) * a.vg.inv_h, -big), big), g1 = fmin(fmax((ay - a.vg.lo[1]) * a.vg.inv_h, -big), big),
+                             g2 = fmin(fmax((az - a.vg.lo[2]) * a.vg.inv_h, -big), big);
+                mn[0] = (int)floor(g0 - 1e-6); mx[0] = (int)floor(g0 + 1e-6);
+                mn[1] = (int)floor(g1 - 1e-6); mx[1] = (int)floor(g1 + 1e-6);
+                mn[2] = (int)floor(g2 - 1e-6); mx[2] = (int)floor(g2 + 1e-6);
+            }
+            if (uB) {
+                const double g0 = fmin(fmax((bx - a.vg.lo[0]) * a.vg.inv_h, -big), big), g1 = fmin(fmax((by - a.vg.lo[1]) * a.vg.inv_h, -big), big),
+                             g2 = fmin(fmax((bz - a.vg.lo[2]) * a.vg.inv_h, -big), big);
+                mn[0] = min(mn[0], (int)floor(g0 - 1e-6)); mx[0] = max(mx[0], (int)floor(g0 + 1e-6));
+                mn[1] = min(mn[1], (int)floor(g1 - 1e-6)); mx[1] = max(mx[1], (int)floor(g1 + 1e-6));
+                mn[2] = min(mn[2], (int)floor(g2 - 1e-6)); mx[2] = max(mx[2], (int)floor(g2 + 1e-6));
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { mn[c] = __reduce_min_sync(B200_FULL, mn[c]); mx[c] = __reduce_max_sync(B200_FULL, mx[c]); }
+        }
+        if (interior) {
+            if (mn[0] < 0 || mn[1] < 0 || mn[2] < 0 || mx[0] >= a.vg.res[0] || mx[1] >= a.vg.res[1] || mx[2] >= a.vg.res[2]) interior = false;
+            else {
+                const u32 ex = (u32)(mx[0] - mn[0] + 1), ey = (u32)(mx[1] - mn[1] + 1), ez = (u32)(mx[2] - mn[2] + 1);
+                const u32 nc = ex * ey * ez;
+                if (nc > VG_MAXCHECK) interior = false;
+                else {
+                    bool ok = true;
+                    for (u32 i = lane; i < nc; i += 32) {
+                        const u32 x = i % ex, y = (i / ex) % ey, z = i / (ex * ey);
+                        ok = ok && ((vg_byte(a.vg, mn[0] + (int)x, mn[1] + (int)y, mn[2] + (int)z) & (VG_BND | VG_IN)) == VG_IN);
+                    }
+                    interior = __all_sync(B200_FULL, ok);
+                }
+            }
+        }
+        const bool exhausted = !sr_ok && nn > 0;
+        if (!interior) {
+            if (lane == 0) { const u32 pos = atomicAdd(a.bnd_n, 1u); a.bnd_list[pos] = s; }
+            ++st_bnd;
+            // the tets this cell can meet lie in the grid cells its bounding box touches (a cell only shrinks from here on)
+            if (nonempty && a.vg.need) {
+                const int x0 = max(mn[0], 0), y0 = max(mn[1], 0), z0 = max(mn[2], 0);
+                const int x1 = min(mx[0], a.vg.res[0] - 1), y1 = min(mx[1], a.vg.res[1] - 1), z1 = min(mx[2], a.vg.res[2] - 1);
+                if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+                    const u32 ex = (u32)(x1 - x0 + 1), ey = (u32)(y1 - y0 + 1), ez = (u32)(z1 - z0 + 1);
+                    const u32 nc = ex * ey * ez;
+                    if (nc > 32768u) { if (lane == 0) *a.vg.need_all = 1u; }
+                    else
+                        for (u32 i = lane; i < nc; i += 32) {
+                            const u32 x = i % ex, y = (i / ex) % ey, z = i / (ex * ey);
+                            const u32 idx = (((u32)z0 + z) * (u32)a.vg.res[1] + (u32)y0 + y) * (u32)a.vg.res[0] + (u32)x0 + x;
+                            const u32 m = 1u << (idx & 31u);
+                            if (!(a.vg.need[idx >> 5] & m)) atomicOr(a.vg.need + (idx >> 5), m);
+                        }
+                }
+            }
+            continue;
+        }
+        if (exhausted && a.check_SR && nn + 1 < a.S && nn < B200CVT_KMAX_DEV && a.redo_list) {
+            if (lane == 0) { const u32 pos = atomicAdd(a.redo_n, 1u); a.redo_list[pos] = s; }
+            continue;
+        }
+        ++st_cells;
+        // integrate. Every face (plane id) is fanned from its lowest-numbered vertex; one fan triangle per (vertex, face) corner.
+        uchar4 vA = make_uchar4(0, 0, 0, 0), vB = vA, tA = vA, tB = vA;
+        if (uA) { vA = V[lane]; tA = T[lane]; B[vA.x] = 0xffffffffu; B[vA.y] = 0xffffffffu; B[vA.z] = 0xffffffffu; }
+        if (uB) { vB = V[lane + 32]; tB = T[lane + 32]; B[vB.x] = 0xffffffffu; B[vB.y] = 0xffffffffu; B[vB.z] = 0xffffffffu; }
+        __syncwarp();
+        if (uA) { atomicMin(&B[vA.x], (u32)lane); atomicMin(&B[vA.y], (u32)lane); atomicMin(&B[vA.z], (u32)lane); }
+        if (uB) { atomicMin(&B[vB.x], (u32)lane + 32u); atomicMin(&B[vB.y], (u32)lane + 32u); atomicMin(&B[vB.z], (u32)lane + 32u); }
+        __syncwarp();
+        const u32 t0 = st.used_lo ? (u32)__ffs((int)st.used_lo) - 1u : 32u + (u32)__ffs((int)st.used_hi) - 1u;
+        const double q0x = P[0][t0], q0y = P[1][t0], q0z = P[2][t0];
+        double acc_s = 0.0, acc_x = 0.0, acc_y = 0.0, acc_z = 0.0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (!(half ? uB : uA)) continue;
+            const u32 t = half ? (u32)lane + 32u : (u32)lane;
+            const uchar4 vt = half ? vB : vA, tt = half ? tB : tA;
+            const double px = half ? bx : ax, py = half ? by : ay, pz = half ? bz : az;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const u32 cv = i == 0 ? vt.x : (i == 1 ? vt.y : vt.z);
+                const u32 nx = i == 0 ? tt.y : (i == 1 ? tt.z : tt.x);       // next vertex around the face (move_to_next_around_vertex)
+                const u32 A = B[cv];
+                if (t == A || nx == A) continue;
+                const double Ax = P[0][A], Ay = P[1][A], Az = P[2][A];
+                const double Nx = P[0][nx], Ny = P[1][nx], Nz = P[2][nx];
+                if (a.mode == 0) {
+                    // ComputeCentroidsVolumetric over TetrahedronAction (generic_RVD.h:901-978, RVD.cpp:428-497): tets from the cell's first vertex
+                    if (A == t0) continue;
+                    const double m = vc_tet_volume(q0x, q0y, q0z, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
+                    const double sc = m / 4.0;
+                    acc_s += m;
+                    acc_x += sc * (q0x + Ax + px + Nx); acc_y += sc * (q0y + Ay + py + Ny); acc_z += sc * (q0z + Az + pz + Nz);
+                } else {
+                    // ComputeCVTFuncGradVolumetric (RVD.cpp:791-876): pyramid of the face triangle with apex p_i
+                    const double mi = vc_tet_volume(pix, piy, piz, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
+                    double fi = 0.0;
+                    {
+                        const double Uc = Ax - pix, Vc = px - pix, Wc = Nx - pix;
+                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                    }
+                    {
+                        const double Uc = Ay - piy, Vc = py - piy, Wc = Ny - piy;
+                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                    }
+                    {
+                        const double Uc = Az - piz, Vc = pz - piz, Wc = Nz - piz;
+                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                    }
+                    fi *= (mi / 10.0);
+                    acc_s += fi;
+                    acc_x += 2.0 * mi * (0.75 * pix - 0.25 * Ax - 0.25 * px - 0.25 * Nx);
+                    acc_y += 2.0 * mi * (0.75 * piy - 0.25 * Ay - 0.25 * py - 0.25 * Ny);
+                    acc_z += 2.0 * mi * (0.75 * piz - 0.25 * Az - 0.25 * pz - 0.25 * Nz);
+                }
+            }
+        }
+        acc_s = warp_sum(acc_s); acc_x = warp_sum(acc_x); acc_y = warp_sum(acc_y); acc_z = warp_sum(acc_z);
+        if (lane == 0) {
+            a.out_s[s] = acc_s;
+            a.out_v[(size_t)s * 3 + 0] = acc_x; a.out_v[(size_t)s * 3 + 1] = acc_y; a.out_v[(size_t)s * 3 + 2] = acc_z;
+            uint8_t f8 = (uint8_t)(a.flags[s] & ~(uint8_t)(1 | 4 | 8));
+            if (exhausted) {
+                if (!a.check_SR) f8 |= 1;
+                else if (nn + 1 >= a.S) { }
+                else if (nn >= B200CVT_KMAX_DEV) f8 |= 8;
+            }
+            a.flags[s] = f8;
+        }
+    }
+    if (a.stats && lane == 0) {
+        if (st_cells) atomicAdd(&a.stats[9], st_cells);
+        if (st_bnd) atomicAdd(&a.stats[10], st_bnd);
+        if (st_clips) atomicAdd(&a.stats[12], st_clips);
+    }
+}

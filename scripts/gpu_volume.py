@@ -23,7 +23,7 @@ def run(n, ref_too=False):
     out = {"n": n, "tets": int(T.shape[0]), "seeds": int(S), "set_mesh_s": round(t_mesh, 2),
            "lloyd_ms_per_iter_e2e": round(t_l * 1e3, 2), "seed_iterations_per_s_lloyd": S / t_l,
            "funcgrad_ms_e2e": round(t_f * 1e3, 2),
-           "phase_ms": {k: round(c[k] / c["evals"], 3) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")},
+           "phase_ms": {k: round(c[k] / c["evals"], 3) for k in ("sort", "knn", "pairs", "clip", "clip_kernel", "cells")},
            "sum_m_minus_1": float(m.sum() - 1.0), "g_identity": float(np.abs(g - 2.0 * (m[:, None] * x - mg)).max()),
            "flags": int((h.flags() & (capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum())}
     h.close()
