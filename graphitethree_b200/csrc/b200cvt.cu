@@ -726,14 +726,17 @@ static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
     LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
 }
 
+#ifndef VGRID_FACTOR
+#define VGRID_FACTOR 2.0
+#endif
 // inside / boundary grid of the tet mesh (vcell.cuh), about one grid cell per seed spacing; rebuilt when the seed count
 // changes by more than a quarter
 static void ensure_vgrid(b200cvt_ctx* h) {
     double maxext = 0.0;
     for (int a = 0; a < 3; ++a) maxext = std::max(maxext, h->bb_hi[a] - h->bb_lo[a]);
     if (!(maxext > 0.0)) maxext = 1.0;
-    u32 R = (u32)std::ceil(1.25 * std::cbrt((double)std::max<u32>(h->S, 1)));
-    R = std::max<u32>(8, std::min<u32>(R, 160));
+    u32 R = (u32)std::ceil(VGRID_FACTOR * std::cbrt((double)std::max<u32>(h->S, 1)));
+    R = std::max<u32>(8, std::min<u32>(R, 250));
     if (h->vgrid_valid && 4 * R >= 3 * h->vgrid_R && 4 * R <= 5 * h->vgrid_R) return;
     VGrid& g = h->vg;
     const double margin = 1e-3 * maxext;

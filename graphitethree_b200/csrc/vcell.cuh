@@ -96,7 +96,7 @@ __global__ void vgrid_mark_kernel(const double* __restrict__ tet, const uint8_t*
         b0[c] = (u32)max(0, min(g.res[c] - 1, (int)floor((mn - g.lo[c]) * g.inv_h - 1e-6)));
         b1[c] = (u32)max(0, min(g.res[c] - 1, (int)floor((mx - g.lo[c]) * g.inv_h + 1e-6)));
     }
-    // the grid cells the tet's bounding box touches (8 bits per bound: the grid has at most 160 cells per axis)
+    // the grid cells the tet's bounding box touches (8 bits per bound: the grid has at most 250 cells per axis)
     if (slab == 0) tet_gbox[f] = make_uint2(b0[0] | (b0[1] << 8) | (b0[2] << 16), b1[0] | (b1[1] << 8) | (b1[2] << 16));
     if (det == 0.0) return;
     const double tol = 1e-9 * fabs(det);
@@ -171,10 +171,6 @@ struct VCellArgs {
 
 __device__ __forceinline__ bool vc_in(u32 lo, u32 hi, u32 t) { return ((((t & 32u) ? hi : lo) >> (t & 31u)) & 1u) != 0u; }
 
-__device__ __forceinline__ u32 vc_kth_free(u32 free_lo, u32 free_hi, u32 nfl, u32 k) {
-    return k < nfl ? __fns(free_lo, 0, (int)k + 1) : 32u + __fns(free_hi, 0, (int)(k - nfl) + 1);
-}
-
 __device__ __forceinline__ double vc_warp_max_nonneg(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     const u32 hi = (u32)(b >> 32), lo = (u32)b;
@@ -205,7 +201,7 @@ __device__ __forceinline__ double vc_radius2(const double (*P)[VC_SLOTS], const 
 }
 
 // ConvexCell::clip_by_plane with the bisector of (pi, pj), the whole warp on one cell. Returns true if the plane cut.
-__device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, VcState& st,
+__device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, unsigned short* IT, unsigned char* FS, VcState& st,
                                         double pix, double piy, double piz, double pjx, double pjy, double pjz, int lane) {
     const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
     double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0, rA = 0.0, rB = 0.0;
@@ -267,62 +263,70 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
     const u32 total = __popc(q0) + 2u * __popc(q1) + 4u * __popc(q2);
     const u32 free_lo = ~st.used_lo, free_hi = ~st.used_hi;
     const u32 nfl = __popc(free_lo);
-    if (total > nfl + __popc(free_hi)) { st.overflow = true; return true; }
+    if (total > 32u || total > nfl + __popc(free_hi)) { st.overflow = true; return true; }
     if (total == 0u) { st.used_lo = 0u; st.used_hi = 0u; return true; }     // everything removed
-    // bisector (ConvexCell::clip_by_plane / intersect_geom): n = pi - pj, d = -(n . (pi + pj)) / 2
-    const double nx = pix - pjx, ny = piy - pjy, nz = piz - pjz;
-    double dd = 0.0;
-    dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
-    dd = 0.5 * dd;
-    uint8_t* Tb = (uint8_t*)T;
-    u32 newN[6], newV2[6];
-    u32 my_lo = 0u, my_hi = 0u;
+    // The zone edges are found by the few lanes of the zone; the work per edge (a new vertex) is spread over the warp:
+    // the zone lanes publish (slot, edge) items, every lane publishes the free slot of its rank, lane i builds item i.
+    if (eA | eB) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const u32 em = half ? eB : eA;
-        const u32 t = half ? (u32)lane + 32u : (u32)lane;
-        const uchar4 tt = half ? tB : tA;
-        const double tx = half ? bx : ax, ty = half ? by : ay, tz = half ? bz : az;
-        uchar4 vt = make_uchar4(0, 0, 0, 0);
-        if (em) vt = V[t];
+        for (int e = 0; e < 3; ++e) if ((eA >> e) & 1u) IT[k++] = (unsigned short)((u32)lane | ((u32)e << 8));
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            newN[half * 3 + e] = 0xffu; newV2[half * 3 + e] = 0u;
-            if (!((em >> e) & 1u)) continue;
-            const u32 nb = e == 0 ? tt.x : (e == 1 ? tt.y : tt.z);
-            const u32 v1 = e == 0 ? vt.y : (e == 1 ? vt.z : vt.x);
-            const u32 v2 = e == 0 ? vt.z : (e == 1 ? vt.x : vt.y);
-            const u32 N = vc_kth_free(free_lo, free_hi, nfl, k);
-            ++k;
-            const double kx = P[0][nb], ky = P[1][nb], kz = P[2][nb];
-            double l1 = 0.0, l2 = 0.0;
-            l1 += kx * nx; l1 += ky * ny; l1 += kz * nz;
-            l2 += tx * nx; l2 += ty * ny; l2 += tz * nz;
-            l1 = fabs(l1 + dd); l2 = fabs(l2 + dd);
-            const double l12 = l1 + l2;
-            if (l12 > 1e-30) { l1 /= l12; l2 /= l12; } else { l1 = 0.5; l2 = 0.5; }
-            P[0][N] = l1 * tx + l2 * kx; P[1][N] = l1 * ty + l2 * ky; P[2][N] = l1 * tz + l2 * kz;
-            V[N] = make_uchar4((unsigned char)new_v, (unsigned char)v1, (unsigned char)v2, 0);
-            Tb[N * 4 + 0] = (unsigned char)nb;
-            // the kept vertex now sees the new one where it saw the zone vertex
-            const uchar4 tn = T[nb];
-            const u32 idx = (tn.y == t ? 1u : 0u) | (tn.z == t ? 2u : 0u);
-            Tb[nb * 4 + idx] = (unsigned char)N;
-            B[v1] = N;
-            newN[half * 3 + e] = N; newV2[half * 3 + e] = v2;
-            if (N < 32u) my_lo |= 1u << N; else my_hi |= 1u << (N - 32u);
-        }
+        for (int e = 0; e < 3; ++e) if ((eB >> e) & 1u) IT[k++] = (unsigned short)(((u32)lane + 32u) | ((u32)e << 8));
+    }
+    const bool fA = (free_lo >> lane) & 1u;
+    const u32 rkA = __popc(free_lo & lt);
+    if (fA) FS[rkA] = (unsigned char)lane;
+    const bool takeA = fA && rkA < total;
+    bool takeB = false;
+    if (total > nfl) {
+        const bool fB = (free_hi >> lane) & 1u;
+        const u32 rkB = nfl + __popc(free_hi & lt);
+        if (fB) FS[rkB] = (unsigned char)(lane + 32);
+        takeB = fB && rkB < total;
+    }
+    __syncwarp();
+    u32 N = 0u, v2 = 0u;
+    if ((u32)lane < total) {
+        // bisector (ConvexCell::clip_by_plane / intersect_geom): n = pi - pj, d = -(n . (pi + pj)) / 2
+        const double nx = pix - pjx, ny = piy - pjy, nz = piz - pjz;
+        double dd = 0.0;
+        dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
+        dd = 0.5 * dd;
+        uint8_t* Tb = (uint8_t*)T;
+        const u32 it = IT[lane];
+        const u32 t = it & 0xffu, e = it >> 8;
+        N = FS[lane];
+        const uchar4 tt = T[t], vt = V[t];
+        const u32 nb = e == 0 ? tt.x : (e == 1 ? tt.y : tt.z);
+        const u32 v1 = e == 0 ? vt.y : (e == 1 ? vt.z : vt.x);
+        v2 = e == 0 ? vt.z : (e == 1 ? vt.x : vt.y);
+        const double tx = P[0][t], ty = P[1][t], tz = P[2][t];
+        const double kx = P[0][nb], ky = P[1][nb], kz = P[2][nb];
+        double l1 = 0.0, l2 = 0.0;
+        l1 += kx * nx; l1 += ky * ny; l1 += kz * nz;
+        l2 += tx * nx; l2 += ty * ny; l2 += tz * nz;
+        l1 = fabs(l1 + dd); l2 = fabs(l2 + dd);
+        const double l12 = l1 + l2;
+        if (l12 > 1e-30) { l1 /= l12; l2 /= l12; } else { l1 = 0.5; l2 = 0.5; }
+        P[0][N] = l1 * tx + l2 * kx; P[1][N] = l1 * ty + l2 * ky; P[2][N] = l1 * tz + l2 * kz;
+        V[N] = make_uchar4((unsigned char)new_v, (unsigned char)v1, (unsigned char)v2, 0);
+        Tb[N * 4 + 0] = (unsigned char)nb;
+        // the kept vertex now sees the new one where it saw the zone vertex
+        const uchar4 tn = T[nb];
+        const u32 idx = (tn.y == t ? 1u : 0u) | (tn.z == t ? 2u : 0u);
+        Tb[nb * 4 + idx] = (unsigned char)N;
+        B[v1] = N;
     }
     __syncwarp();
     // close the ring: the new vertex (P, v1, v2) is followed by the new vertex whose v1 is v2
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        if (newN[i] == 0xffu) continue;
-        const u32 nxn = B[newV2[i]];
-        Tb[newN[i] * 4 + 1] = (unsigned char)nxn;
-        Tb[nxn * 4 + 2] = (unsigned char)newN[i];
+    if ((u32)lane < total) {
+        uint8_t* Tb = (uint8_t*)T;
+        const u32 nxn = B[v2];
+        Tb[N * 4 + 1] = (unsigned char)nxn;
+        Tb[nxn * 4 + 2] = (unsigned char)N;
     }
-    const u32 add_lo = __reduce_or_sync(B200_FULL, my_lo), add_hi = __reduce_or_sync(B200_FULL, my_hi);
+    const u32 add_lo = __ballot_sync(B200_FULL, takeA);
+    const u32 add_hi = total > nfl ? __ballot_sync(B200_FULL, takeB) : 0u;
     st.used_lo = (st.used_lo & ~klo) | add_lo;
     st.used_hi = (st.used_hi & ~khi) | add_hi;
     __syncwarp();
@@ -341,16 +345,23 @@ __device__ __forceinline__ double vc_tet_volume(double ax, double ay, double az,
     return fabs((U0 * x + U1 * y + U2 * z) / 6.0);
 }
 
-__global__ void __launch_bounds__(VC_WARPS * 32) vcell_kernel(VCellArgs a) {
+#ifndef VC_MINBLK
+#define VC_MINBLK 3
+#endif
+__global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellArgs a) {
     __shared__ double sP[VC_WARPS][3][VC_SLOTS];
     __shared__ uchar4 sV[VC_WARPS][VC_SLOTS];
     __shared__ uchar4 sT[VC_WARPS][VC_SLOTS];
     __shared__ u32 sB[VC_WARPS][256];
+    __shared__ unsigned short sIT[VC_WARPS][32];
+    __shared__ unsigned char sFS[VC_WARPS][VC_SLOTS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double (*P)[VC_SLOTS] = sP[w];
     uchar4* V = sV[w];
     uchar4* T = sT[w];
     u32* B = sB[w];
+    unsigned short* IT = sIT[w];
+    unsigned char* FS = sFS[w];
     const SeedRec<3>* xs = (const SeedRec<3>*)a.xs;
     const u32 nseeds = a.nseeds_dev ? *a.nseeds_dev : a.nseeds;
     unsigned long long st_cells = 0, st_bnd = 0, st_clips = 0;
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(VC_WARPS * 32) vcell_kernel(VCellArgs a) {
                 const double dj = shfl_d(qd, (int)l);
                 if (dj > 4.1 * R2) { sr_ok = true; done = true; break; }
                 ++st_clips;
-                const bool cut = vc_clip(P, V, T, B, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), lane);
+                const bool cut = vc_clip(P, V, T, B, IT, FS, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), lane);
                 if (st.overflow || (st.used_lo | st.used_hi) == 0u) { done = true; break; }
                 if (cut) R2 = vc_radius2(P, st, pix, piy, piz, lane);
             }

@@ -10,7 +10,11 @@ V, T = shapes.kuhn_cube(%(n)d); S = T.shape[0] // 10
 X = 0.01 + 0.98 * np.random.default_rng(5).random((S, 3))
 h = capi.Handle(3, volumetric=True); h.set_mesh(V, T)
 x = h.lloyd(X, 3); h.cumulative(reset=True); x = h.lloyd(x, 3); c = h.cumulative(reset=True)
-print("%(name)s", " ".join("%%s=%%.3f" %% (k, c[k] / c["evals"]) for k in ("knn", "pairs", "clip")))
+import time
+h.set_seeds(x); h.funcgrad(True); h.cumulative(reset=True); h.stats(); h.set_seeds(x); t0 = time.time(); h.funcgrad(True); tf = time.time() - t0
+cf = h.cumulative(reset=True); st = h.stats()
+print("  funcgrad phases", " ".join("%%s=%%.3f" %% (k, cf[k]) for k in ("sort", "knn", "pairs", "clip", "clip_kernel", "cells")), "redo_total", st["redo_seeds"], st["volumetric_cells"])
+print("%(name)s", " ".join("%%s=%%.3f" %% (k, c[k] / c["evals"]) for k in ("knn", "pairs", "clip", "clip_kernel", "cells")), "funcgrad_ms=%%.2f" %% (tf * 1e3))
 '''
 n = int(sys.argv[1])
 for name in sys.argv[2:]:

@@ -576,6 +576,51 @@ def test_rdt_against_oracle_trefoil(built):
     h.close()
 
 
+def test_volume_cell_first_path_equals_tet_path(built, monkeypatch):
+    """vcell.cuh builds the Voronoi cell of a seed once (one warp, cooperative) and integrates it directly when the
+    inside / boundary grid proves it inside the domain; everything else takes the (tet, seed) path (B200CVT_VCELL=0 forces it
+    for all seeds). Same per-seed results on a convex and on a concave domain with seeds outside of it."""
+    V, T = shapes.kuhn_cube(20)                                  # 48 000 tets
+    cen = V[T].mean(axis=1)
+    T_L = np.ascontiguousarray(T[~((cen[:, 0] > 0.5) & (cen[:, 1] > 0.5) & (cen[:, 2] > 0.5))])   # cube minus an octant
+    rng = np.random.default_rng(33)
+    for Tm, vol in ((T, 1.0), (T_L, 0.875)):
+        X = 0.01 + 0.98 * rng.random((Tm.shape[0] // 10, 3))     # on the concave domain some seeds lie outside
+        monkeypatch.setenv("B200CVT_VCELL", "0")
+        ht = volume_handle(V, Tm)
+        monkeypatch.setenv("B200CVT_VCELL", "1")
+        hc = volume_handle(V, Tm)
+        x = ht.lloyd(X, 2)
+        res = {}
+        for name, h in (("tet", ht), ("cell", hc)):
+            h.stats()
+            h.set_seeds(x); mg, m = h.centroids(True); fl = h.flags().copy(); st = h.stats()
+            h.set_seeds(x); f, g = h.funcgrad(True); fs = h.seed_energy().copy()
+            h.set_seeds(x); mgL, mL = h.centroids(False); flL = h.flags().copy()
+            res[name] = (m, mg, f, g, fl, st, mL, mgL, flL, fs)
+        a, b = res["tet"], res["cell"]
+        S = x.shape[0]
+        assert b[5]["volumetric_cells"]["direct"] > 0.4 * S and b[5]["volumetric_cells"]["tet_path"] > 0
+        assert a[5]["volumetric_cells"]["direct"] == 0
+        assert ((a[4] | b[4]) & (capi.FLAG_EXHAUSTED | capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+        assert abs(b[0].sum() - vol) <= 1e-12
+        assert np.abs(a[0] - b[0]).max() <= 1e-12 * a[0].max()
+        assert np.abs(a[1] - b[1]).max() <= 1e-12 * np.abs(a[1]).max()
+        assert abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+        assert np.abs(a[3] - b[3]).max() <= 1e-12 * np.abs(a[3]).max()
+        assert np.abs(a[9] - b[9]).max() <= 1e-12 * np.abs(a[9]).max()
+        # Lloyd mode (20 stored neighbours): wherever neither path used up a list the cell is exact in both
+        ok = ((a[8] | b[8]) & capi.FLAG_EXHAUSTED) == 0
+        assert ok.sum() > 0
+        assert np.abs(a[6] - b[6])[ok].max() <= 1e-12 * a[6].max()
+        assert np.abs(a[7] - b[7])[ok].max() <= 1e-12 * np.abs(a[7]).max()
+        # trajectories: exact cells, so the two paths walk the same Newton iterates
+        xa, ia = ht.newton(x, 5, 7)
+        xb, ib = hc.newton(x, 5, 7)
+        assert ia == ib and np.abs(xa - xb).max() <= 1e-9
+        ht.close(); hc.close()
+
+
 def test_sharded_volumetric_two_partitions_one_gpu(built):
     """Volumetric mode through the partition + exchange path: two handles on one GPU stand in for two ranks."""
     import torch
