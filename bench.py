@@ -348,6 +348,13 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax.item())
+    # per-rank phase sums (load balance of the Morton ranges): rank 0 reports min / max over the ranks
+    by_rank = None
+    if world > 1:
+        mine = torch.tensor([cum[k] for k in ("sort", "knn", "pairs", "clip")] + [dev_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = torch.stack(allr).cpu().numpy()
     n_eval = evals["n"]
     value = S * n_eval * args.steps / (ms_total * 1e-3)
     x_final = h.get_seeds()
@@ -457,6 +464,12 @@ def main():
                                     "units_per_launch": int(knn_queries),
                                     "note": "issue-bound (64-bit key compare-exchanges), not HBM; time = the kNN phase of bench.py's timers"}
             line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
+            if by_rank is not None:
+                line["phase_ms_per_evaluation_over_ranks"] = {
+                    k: {"min": float(by_rank[:, i].min() / n_launch), "max": float(by_rank[:, i].max() / n_launch)}
+                    for i, k in enumerate(("sort", "knn", "pairs", "clip"))}
+                tot = by_rank[:, :4].sum(axis=1) / n_launch
+                line["phase_ms_per_evaluation_over_ranks"]["all_phases"] = {"min": float(tot.min()), "max": float(tot.max())}
         except Exception as ex_:   # the bench value stands even if the roofline leg fails
             line["roofline"] = {"error": str(ex_)}
         # CPU baseline on the host cores, bounded sample of the same workload: rank 0 at N = 1 only

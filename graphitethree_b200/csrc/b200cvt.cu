@@ -726,6 +726,9 @@ static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
     LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
 }
 
+#ifndef VC_NEWTON_K0
+#define VC_NEWTON_K0 32
+#endif
 #ifndef VGRID_FACTOR
 #define VGRID_FACTOR 2.0
 #endif
@@ -815,10 +818,27 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
         v.redo_list = check_SR ? h->vc_redo_a.p : nullptr; v.redo_n = h->vc_n.p;
         v.bnd_list = h->vc_bnd.p; v.bnd_n = h->vc_n.p + 2;
         v.stats = h->want_stats ? h->stats.p : nullptr;
-        launch_vcell(h, v);
+        u32 kbig0 = 40;
+        if (check_SR && VC_NEWTON_K0 > 20 && kmax > 20) {
+            // exact cells: whole cells need more than the 20 stored neighbours for most seeds (the radius test compares against
+            // the farthest vertex of the whole cell), so the first pass already runs on longer lists
+            const u32 k0 = std::min<u32>(VC_NEWTON_K0, kmax);
+            h->iota.ensure(S);
+            if (h->iota_filled < h->iota.cap) {
+                LAUNCH(h, iota_u32_kernel, 1024, 256, 0, h->iota.p, h->iota.cap);
+                h->iota_filled = h->iota.cap;
+            }
+            knn_for_list(h, h->iota.p + h->qbegin(), nown, k0);
+            VCellArgs v0 = v;
+            v0.nbr = h->nbr_big.p; v0.nbr_n = h->nbr_big_n.p; v0.kstride = k0; v0.nbr_by_slot = 1;
+            v0.seed_list = h->iota.p + h->qbegin(); v0.nseeds = nown;
+            if (k0 >= kmax) v0.redo_list = nullptr;
+            launch_vcell(h, v0);
+            kbig0 = 2 * k0;
+        } else launch_vcell(h, v);
         if (check_SR) {
             // enlarge_neighborhood loop (generic_RVD.h:2330-2346) on whole cells, batched over the seeds that need it
-            u32 kbig = 40;
+            u32 kbig = kbig0;
             u32* cur_list = h->vc_redo_a.p; u32* nxt_list = h->vc_redo_b.p;
             int cur_slot = 0;
             for (;;) {
