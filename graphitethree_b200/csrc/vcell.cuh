@@ -285,20 +285,22 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
         takeB = fB && rkB < total;
     }
     __syncwarp();
-    u32 N = 0u, v2 = 0u;
-    if ((u32)lane < total) {
+    // phase A: lane i reads what new vertex i needs (nothing is written yet)
+    u32 N = 0u, v1 = 0u, v2 = 0u, nb = 0u, idx = 0u;
+    double nx_ = 0.0, ny_ = 0.0, nz_ = 0.0;
+    const bool mine = (u32)lane < total;
+    if (mine) {
         // bisector (ConvexCell::clip_by_plane / intersect_geom): n = pi - pj, d = -(n . (pi + pj)) / 2
         const double nx = pix - pjx, ny = piy - pjy, nz = piz - pjz;
         double dd = 0.0;
         dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
         dd = 0.5 * dd;
-        uint8_t* Tb = (uint8_t*)T;
         const u32 it = IT[lane];
         const u32 t = it & 0xffu, e = it >> 8;
         N = FS[lane];
         const uchar4 tt = T[t], vt = V[t];
-        const u32 nb = e == 0 ? tt.x : (e == 1 ? tt.y : tt.z);
-        const u32 v1 = e == 0 ? vt.y : (e == 1 ? vt.z : vt.x);
+        nb = e == 0 ? tt.x : (e == 1 ? tt.y : tt.z);
+        v1 = e == 0 ? vt.y : (e == 1 ? vt.z : vt.x);
         v2 = e == 0 ? vt.z : (e == 1 ? vt.x : vt.y);
         const double tx = P[0][t], ty = P[1][t], tz = P[2][t];
         const double kx = P[0][nb], ky = P[1][nb], kz = P[2][nb];
@@ -308,23 +310,27 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
         l1 = fabs(l1 + dd); l2 = fabs(l2 + dd);
         const double l12 = l1 + l2;
         if (l12 > 1e-30) { l1 /= l12; l2 /= l12; } else { l1 = 0.5; l2 = 0.5; }
-        P[0][N] = l1 * tx + l2 * kx; P[1][N] = l1 * ty + l2 * ky; P[2][N] = l1 * tz + l2 * kz;
+        nx_ = l1 * tx + l2 * kx; ny_ = l1 * ty + l2 * ky; nz_ = l1 * tz + l2 * kz;
+        // the kept vertex will see the new one where it saw the zone vertex
+        const uchar4 tn = T[nb];
+        idx = (tn.y == t ? 1u : 0u) | (tn.z == t ? 2u : 0u);
+    }
+    __syncwarp();
+    // phase B: the new vertices (free slots), the links of the kept vertices (one byte each, all distinct), the ring table
+    uint8_t* Tb = (uint8_t*)T;
+    if (mine) {
+        P[0][N] = nx_; P[1][N] = ny_; P[2][N] = nz_;
         V[N] = make_uchar4((unsigned char)new_v, (unsigned char)v1, (unsigned char)v2, 0);
         Tb[N * 4 + 0] = (unsigned char)nb;
-        // the kept vertex now sees the new one where it saw the zone vertex
-        const uchar4 tn = T[nb];
-        const u32 idx = (tn.y == t ? 1u : 0u) | (tn.z == t ? 2u : 0u);
         Tb[nb * 4 + idx] = (unsigned char)N;
         B[v1] = N;
     }
     __syncwarp();
-    // close the ring: the new vertex (P, v1, v2) is followed by the new vertex whose v1 is v2
-    if ((u32)lane < total) {
-        uint8_t* Tb = (uint8_t*)T;
-        const u32 nxn = B[v2];
-        Tb[N * 4 + 1] = (unsigned char)nxn;
-        Tb[nxn * 4 + 2] = (unsigned char)N;
-    }
+    // phase C: close the ring: the new vertex (P, v1, v2) is followed by the new vertex whose v1 is v2
+    u32 nxn = 0u;
+    if (mine) { nxn = B[v2]; Tb[N * 4 + 1] = (unsigned char)nxn; }
+    __syncwarp();
+    if (mine) Tb[nxn * 4 + 2] = (unsigned char)N;
     const u32 add_lo = __ballot_sync(B200_FULL, takeA);
     const u32 add_hi = total > nfl ? __ballot_sync(B200_FULL, takeB) : 0u;
     st.used_lo = (st.used_lo & ~klo) | add_lo;
@@ -481,8 +487,9 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
         ++st_cells;
         // integrate. Every face (plane id) is fanned from its lowest-numbered vertex; one fan triangle per (vertex, face) corner.
         uchar4 vA = make_uchar4(0, 0, 0, 0), vB = vA, tA = vA, tB = vA;
-        if (uA) { vA = V[lane]; tA = T[lane]; B[vA.x] = 0xffffffffu; B[vA.y] = 0xffffffffu; B[vA.z] = 0xffffffffu; }
-        if (uB) { vB = V[lane + 32]; tB = T[lane + 32]; B[vB.x] = 0xffffffffu; B[vB.y] = 0xffffffffu; B[vB.z] = 0xffffffffu; }
+        if (uA) { vA = V[lane]; tA = T[lane]; }
+        if (uB) { vB = V[lane + 32]; tB = T[lane + 32]; }
+        for (u32 i = lane; i < st.np; i += 32) B[i] = 0xffffffffu;
         __syncwarp();
         if (uA) { atomicMin(&B[vA.x], (u32)lane); atomicMin(&B[vA.y], (u32)lane); atomicMin(&B[vA.z], (u32)lane); }
         if (uB) { atomicMin(&B[vB.x], (u32)lane + 32u); atomicMin(&B[vB.y], (u32)lane + 32u); atomicMin(&B[vB.z], (u32)lane + 32u); }
