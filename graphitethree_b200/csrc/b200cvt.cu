@@ -726,6 +726,9 @@ static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
     LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
 }
 
+#ifndef COMPACT_BLOCKS_PER_SM
+#define COMPACT_BLOCKS_PER_SM 8u
+#endif
 #ifndef VC_NEWTON_K0
 #define VC_NEWTON_K0 32
 #endif
@@ -1008,7 +1011,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         ca.pair_cnt = h->pair_cnt.p; ca.pair_facet = h->pair_facet.p; ca.pair_mask = h->pair_mask.p; ca.cap = h->pair_cap;
         ca.pair_off = h->pair_off.p; ca.qbegin = h->qbegin(); ca.nown = nown;
         ca.flat_seed = h->flat_seed.p; ca.flat_facet = h->flat_facet.p; ca.flat_mask = h->flat_mask.p;
-        LAUNCH(h, compact_pairs_kernel, div_up(nown, 8), 256, 0, ca);
+        LAUNCH(h, compact_pairs_kernel, std::min<u32>(div_up(nown, 8), (u32)h->num_sms * COMPACT_BLOCKS_PER_SM), 256, 0, ca);
     }
     if (np > 0) {
         ClipFlatArgs fa;
@@ -1055,7 +1058,7 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
         ra.out_s = h->out_s.p; ra.out_v = h->out_v.p; ra.flags = h->flags.p;
         ra.slow_list = h->slow_list.p; ra.slow_n = h->redo_n.p + 2;
         ra.redo_list = h->redo_a.p; ra.redo_n = h->redo_n.p;
-        LAUNCH(h, reduce_pairs_kernel<D>, div_up(nown, 8), 256, 0, ra);
+        LAUNCH(h, reduce_pairs_kernel<D>, div_up(nown, 32), 256, 0, ra);
         // seeds with a pair the in-place fast path gave up on: warp-per-seed kernel, same neighbour table
         ClipArgs sl = c;
         sl.seed_list = h->slow_list.p; sl.nseeds = 0; sl.nseeds_dev = h->redo_n.p + 2;

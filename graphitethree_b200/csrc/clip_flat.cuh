@@ -56,15 +56,24 @@ compact_pairs_kernel(CompactArgs a) {
     const int lane = threadIdx.x & 31;
     const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    // persistent warps; the row of the next seed is requested before the current one is sorted (the kernel is latency-bound)
+    u32 n = 0, off = 0;
+    u64 v = ~0ull;
+    auto fetch = [&](u32 i, u32& n_, u32& off_, u64& v_) {
+        n_ = 0; off_ = 0; v_ = ~0ull;
+        if (i < a.nown) {
+            const u32 s = a.qbegin + i;
+            n_ = min(a.pair_cnt[s], a.cap);
+            off_ = a.pair_off[i];
+            if ((u32)lane < n_ && n_ <= 32) v_ = ((u64)a.pair_facet[(size_t)s * a.cap + lane] << 32) | a.pair_mask[(size_t)s * a.cap + lane];
+        }
+    };
+    fetch(wid, n, off, v);
     for (u32 i = wid; i < a.nown; i += nwarps) {
+        u32 n2, off2; u64 v2;
+        fetch(i + nwarps, n2, off2, v2);
         const u32 s = a.qbegin + i;
-        const u32 n = min(a.pair_cnt[s], a.cap);
-        if (n == 0) continue;
-        const u32 off = a.pair_off[i];
-        const u32* row = a.pair_facet + (size_t)s * a.cap;
-        const u32* mrow = a.pair_mask + (size_t)s * a.cap;
-        if (n <= 32) {
-            u64 v = lane < n ? (((u64)row[lane] << 32) | mrow[lane]) : ~0ull;
+        if (n > 0 && n <= 32) {
 #pragma unroll
             for (int k = 2; k <= 32; k <<= 1)
 #pragma unroll
@@ -73,19 +82,22 @@ compact_pairs_kernel(CompactArgs a) {
                     bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
                     v = (lower == up) ? min(v, o) : max(v, o);
                 }
-            if (lane < n) {
+            if ((u32)lane < n) {
                 const u32 m = (u32)v;
                 a.flat_facet[off + lane] = (u32)(v >> 32); a.flat_seed[off + lane] = s; a.flat_mask[off + lane] = m;
             }
-        } else {
+        } else if (n > 32) {
             // rank by counting (facet ids of one seed are distinct)
+            const u32* row = a.pair_facet + (size_t)s * a.cap;
+            const u32* mrow = a.pair_mask + (size_t)s * a.cap;
             for (u32 t = lane; t < n; t += 32) {
-                const u32 v = row[t], m = mrow[t];
+                const u32 fv = row[t], m = mrow[t];
                 u32 r = 0;
-                for (u32 u = 0; u < n; ++u) r += (row[u] < v) ? 1u : 0u;
-                a.flat_facet[off + r] = v; a.flat_seed[off + r] = s; a.flat_mask[off + r] = m;
+                for (u32 u = 0; u < n; ++u) r += (row[u] < fv) ? 1u : 0u;
+                a.flat_facet[off + r] = fv; a.flat_seed[off + r] = s; a.flat_mask[off + r] = m;
             }
         }
+        n = n2; off = off2; v = v2;
     }
 }
 
@@ -717,31 +729,57 @@ struct ReduceArgs {
     u32* redo_list; u32* redo_n;     // seeds whose neighbour list must grow (check_SR)
 };
 
-// one warp per seed: lanes take the seed's pairs round-robin (in facet order), then a fixed xor tree
+// Eight lanes per seed, four seeds per warp (the loads of four seeds are in flight together: the kernel is latency-bound).
+// The sum is the one of the former warp-per-seed layout, bit for bit: position q = 0..31 takes the pairs q, q + 32, ... in
+// facet order, then the xor tree 16, 8, 4, 2, 1; lane g of a group holds the positions g, g + 8, g + 16, g + 24, so the first
+// two levels of the tree are local.
 template <int D>
 __global__ void __launch_bounds__(256)
 reduce_pairs_kernel(ReduceArgs a) {
-    const int lane = threadIdx.x & 31;
-    const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= a.nown) return;
+    const int lane = threadIdx.x & 31, g = lane & 7;
+    const u32 i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4u + (u32)(lane >> 3);
+    const bool valid = i < a.nown;
     const u32 s = a.qbegin + i;
-    const u32 b = a.pair_off[i], e = a.pair_off[i + 1];
-    double acc_s = 0.0, acc_v[D];
+    u32 b = 0, e = 0;
+    if (valid) { b = a.pair_off[i]; e = a.pair_off[i + 1]; }
+    double acc[4][D + 1];
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc_v[c] = 0.0;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c <= D; ++c) acc[j][c] = 0.0;
     u32 ps = 0;
-    for (u32 t = b + lane; t < e; t += 32) {
-        acc_s += a.contrib[t];
+    for (u32 base = b; base < e; base += 32) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc_v[c] += a.contrib[(size_t)(c + 1) * a.cstride + t];
-        ps |= a.pstat[t];
+        for (int j = 0; j < 4; ++j) {
+            const u32 t = base + (u32)g + 8u * j;
+            if (t < e) {
+                acc[j][0] += a.contrib[t];
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[j][c + 1] += a.contrib[(size_t)(c + 1) * a.cstride + t];
+                ps |= a.pstat[t];
+            }
+        }
     }
-    acc_s = warp_sum(acc_s);
+    double acc_s, acc_v[D];
+    {
+        double r[D + 1];
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc_v[c] = warp_sum(acc_v[c]);
+        for (int c = 0; c <= D; ++c) {
+            const double lo = acc[0][c] + acc[2][c];      // level 16: q and q + 16
+            const double hi = acc[1][c] + acc[3][c];
+            double v = lo + hi;                           // level 8
+            v += __shfl_xor_sync(B200_FULL, v, 4);
+            v += __shfl_xor_sync(B200_FULL, v, 2);
+            v += __shfl_xor_sync(B200_FULL, v, 1);
+            r[c] = v;
+        }
+        acc_s = r[0];
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) ps |= __shfl_xor_sync(B200_FULL, ps, m);
-    if (lane != 0) return;
+        for (int c = 0; c < D; ++c) acc_v[c] = r[c + 1];
+    }
+#pragma unroll
+    for (int m = 4; m > 0; m >>= 1) ps |= __shfl_xor_sync(B200_FULL, ps, m);
+    if (g != 0 || !valid) return;
     a.out_s[s] = acc_s;
 #pragma unroll
     for (int c = 0; c < D; ++c) a.out_v[(size_t)s * D + c] = acc_v[c];

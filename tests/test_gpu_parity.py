@@ -845,6 +845,38 @@ def test_c5_volumetric_62k_per_seed_against_reference(built):
     per_seed_vs_reference(V, T, x, volumetric=True)
 
 
+def test_sticky_list_sizes_only_matter_where_flagged(built):
+    """The reference keeps the size a neighbour list was enlarged to (Delaunay::update_neighbors stores array_size(v)
+    neighbours, delaunay.cpp:260-268, delaunay_nn.cpp:73-86): a Lloyd-mode evaluation AFTER a Newton evaluation clips some cells
+    by more than 20 neighbours. The library restarts every evaluation from 20 and enlarges on demand. Provoked
+    here on a raw sampling: the oracle run with the sticky sizes differs from the oracle run with fresh sizes on some seeds (it
+    computes their exact cells); every such seed lies in the flagged set of the library's result (truncated cells and the cells
+    that share a facet with one), and all other seeds agree with the sticky run at 1e-9."""
+    V, F = shapes.icosphere(12)
+    X = shapes.sample_surface(V, F, 700, 5)
+    ks = np.full(X.shape[0], 20, dtype=np.uint32)
+    port.surface_eval(V, F, X, 1, True, ksize=ks)                 # a Newton-mode evaluation: ks now holds the enlarged sizes
+    assert (ks > 20).sum() > 0
+    x2 = X + 1e-4 * np.random.default_rng(1).standard_normal(X.shape)
+    e_sticky = port.surface_eval(V, F, x2, 0, False, ksize=ks.copy(), kcap=int(ks.max()))
+    e_fresh = port.surface_eval(V, F, x2, 0, False)
+    differs = np.abs(e_sticky.m - e_fresh.m) > 1e-12 * e_fresh.m.max()
+    assert differs.sum() > 0                                       # the case is provoked (measured: 25 of 700 seeds)
+    h = handle_for(V, F)
+    h.set_seeds(X); h.funcgrad(True)
+    h.set_seeds(x2)
+    mg, m = h.centroids(False)
+    fl = h.flags()
+    h.close()
+    t, _ = tainted(V, F, x2, gpu_flags=fl)
+    assert np.all(t[differs])                                      # sticky sizes change nothing outside the flagged configurations
+    assert np.all(((fl & capi.FLAG_EXHAUSTED) != 0)[(e_fresh.flags & port.FLAG_EXHAUSTED) != 0])
+    ok = ~t
+    assert ok.sum() > 0.3 * len(ok)
+    assert_close(m, e_sticky.m, ok, "mass against the sticky-size run")
+    assert_close(mg, e_sticky.mg, ok, "mass*centroid against the sticky-size run")
+
+
 def test_neighbour_cap_is_flagged(built):
     # Seeds on a line next to a facet much longer than their spacing: every cell is a strip whose security radius reaches all
     # the other seeds, so check_SR asks for all S - 1 neighbours (the reference grows the list without bound,
