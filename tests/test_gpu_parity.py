@@ -621,6 +621,38 @@ def test_volume_cell_first_path_equals_tet_path(built, monkeypatch):
         ht.close(); hc.close()
 
 
+def test_volume_cell_with_more_vertices_than_slots_takes_the_tet_path(built, monkeypatch):
+    """A seed surrounded by 160 seeds on a sphere: its exact cell has ~160 faces and ~300 vertices, more than the 64 slots of
+    vcell_kernel; the kernel gives up on it (and only on it) and the (tet, seed) path integrates it. Same result as the run
+    that sends every seed through the tet path, and the cells still tile the cube."""
+    V, T = shapes.kuhn_cube(10)
+    rng = np.random.default_rng(12)
+    u = rng.standard_normal((160, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    ring = 0.5 + 0.3 * u * (1.0 + 1e-3 * rng.random((160, 1)))
+    outer = rng.random((4000, 3))
+    outer = outer[np.linalg.norm(outer - 0.5, axis=1) > 0.34][:500]
+    X = np.concatenate([[[0.5, 0.5, 0.5]], ring, outer])
+    res = []
+    for env in ("0", "1"):
+        monkeypatch.setenv("B200CVT_VCELL", env)
+        h = volume_handle(V, T)
+        h.stats()
+        h.set_seeds(X); mg, m = h.centroids(True); st = h.stats(); fl = h.flags().copy()
+        h.set_seeds(X); f, g = h.funcgrad(True)
+        h.close()
+        res.append((m, mg, f, g, fl, st))
+    a, b = res
+    assert ((a[4] | b[4]) & (capi.FLAG_EXHAUSTED | capi.FLAG_POLY_OVERFLOW | capi.FLAG_KMAX)).sum() == 0
+    assert b[5]["volumetric_cells"]["direct"] > 0 and b[5]["volumetric_cells"]["tet_path"] > 0
+    assert abs(b[0].sum() - 1.0) <= 1e-12
+    assert b[0][0] > 0.05                                  # the big cell: roughly a ball of radius 0.15
+    assert np.abs(a[0] - b[0]).max() <= 1e-12 * a[0].max()
+    assert np.abs(a[1] - b[1]).max() <= 1e-12 * np.abs(a[1]).max()
+    assert abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+    assert np.abs(a[3] - b[3]).max() <= 1e-12 * np.abs(a[3]).max()
+
+
 def test_sharded_volumetric_two_partitions_one_gpu(built):
     """Volumetric mode through the partition + exchange path: two handles on one GPU stand in for two ranks."""
     import torch
