@@ -116,6 +116,7 @@ class Handle:
     def __init__(self, dim=3, volumetric=False, device=-1):
         self._h = C.c_void_p()
         self.dim = dim
+        self.volumetric = bool(volumetric)
         self.S = 0
         _check(lib().b200cvt_create(device, dim, int(volumetric), C.byref(self._h)))
 
@@ -184,10 +185,11 @@ class Handle:
         return f.value, g
 
     def rdt(self):
-        """compute_RDT, simple mode (RVD.cpp:2353-2370): (n, 3) original seed indices, rows sorted."""
+        """compute_RDT, simple mode (RVD.cpp:2353-2370): (n, 3) original seed indices, rows sorted; volumetric handles:
+        (n, 4) Delaunay tets whose Voronoi vertex lies inside the domain (RVD.cpp:2308-2335)."""
         n = C.c_uint64(0)
         _check(lib().b200cvt_rdt(self._h, None, 0, C.byref(n)))
-        tri = np.empty((int(n.value), 3), dtype=np.uint32)
+        tri = np.empty((int(n.value), 4 if self.volumetric else 3), dtype=np.uint32)
         if n.value:
             _check(lib().b200cvt_rdt(self._h, tri.ctypes.data_as(_up), n.value, C.byref(n)))
         return tri

@@ -316,6 +316,7 @@ struct b200cvt_ctx {
     size_t vgrid_ncell = 0; bool vneed_active = false;   // the facet walk is restricted to the tets near the cells of the tet path
     DevBuf<u32> vc_bnd, vc_redo_a, vc_redo_b, vc_n;
     bool use_vcell = true;
+    DevBuf<uint4> rdtv; DevBuf<unsigned long long> rdtv_n;   // volumetric RDT rows (mode 3)
     cudaEvent_t evc[2] = {nullptr, nullptr};   // around the cell stage
     bool evc_used = false;
     DevBuf<u32> facet_guess;
@@ -821,6 +822,7 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
         v.redo_list = check_SR ? h->vc_redo_a.p : nullptr; v.redo_n = h->vc_n.p;
         v.bnd_list = h->vc_bnd.p; v.bnd_n = h->vc_n.p + 2;
         v.stats = h->want_stats ? h->stats.p : nullptr;
+        v.tets = h->rdtv.p; v.tet_n = h->rdtv_n.p; v.tet_cap = h->rdtv.cap;
         u32 kbig0 = 40;
         if (check_SR && VC_NEWTON_K0 > 20 && kmax > 20) {
             // exact cells: whole cells need more than the 20 stored neighbours for most seeds (the radius test compares against
@@ -886,6 +888,7 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
     c.out_s = h->out_s.p; c.out_v = h->out_v.p; c.flags = h->flags.p;
     c.redo_list = check_SR ? h->redo_a.p : nullptr; c.redo_n = h->redo_n.p;
     c.stats = h->want_stats ? h->stats.p : nullptr;
+    c.tets = h->rdtv.p; c.tet_n = h->rdtv_n.p; c.tet_cap = h->rdtv.cap;
     CUDA_CHECK(cudaEventRecord(h->evk[0], h->stream));
     launch_clip_tet(h, c);
     CUDA_CHECK(cudaEventRecord(h->evk[1], h->stream));
@@ -916,7 +919,7 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
         }
     }
     CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
-    h->has_results = true;
+    h->has_results = (mode != 3);
     h->has_energy = (mode == 1);
     h->ev_valid = true;
     h->ev_pending = true;
@@ -1295,6 +1298,99 @@ static void launch_rdt(b200cvt_ctx* h, RdtArgs& a) {
 // RestrictedVoronoiDiagram::compute_RDT(simplices, embedding, RDTMode(0)) for the owned seeds (RVD.cpp:2353-2370):
 // check_SR = true as CentroidalVoronoiTesselation::compute_surface sets it (CVT.cpp:194). Result in h->rdt_host,
 // rows sorted lexicographically.
+// ---------------------------------------------------------------------------------------
+// volumetric RDT: RestrictedVoronoiDiagram::compute_RDT with set_volumetric(true) (RVD.cpp:2308-2335)
+// ---------------------------------------------------------------------------------------
+namespace {
+inline void two_sum(double a, double b, double& s, double& e) { s = a + b; const double bb = s - a; e = (a - (s - bb)) + (b - bb); }
+inline void two_prod(double a, double b, double& p, double& e) { p = a * b; e = std::fma(a, b, -p); }
+// exact sum of doubles as a non-overlapping expansion (Shewchuk's Grow-Expansion), components by increasing magnitude
+inline void grow(std::vector<double>& ex, double b) {
+    double q = b;
+    size_t w = 0;
+    for (size_t i = 0; i < ex.size(); ++i) { double sum, r; two_sum(q, ex[i], sum, r); if (r != 0.0) ex[w++] = r; q = sum; }
+    ex.resize(w);
+    ex.push_back(q);
+}
+// sign of det(p1 - p0, p2 - p0, p3 - p0) = PCK::orient_3d (numerics/predicates/orient3d.h:4-24; exact fallback as the reference)
+int orient3d_sign(const double* p0, const double* p1, const double* p2, const double* p3) {
+    double a[3][3];
+    for (int c = 0; c < 3; ++c) { a[0][c] = p1[c] - p0[c]; a[1][c] = p2[c] - p0[c]; a[2][c] = p3[c] - p0[c]; }
+    const double m0 = a[1][1] * a[2][2] - a[1][2] * a[2][1], m1 = a[0][1] * a[2][2] - a[0][2] * a[2][1], m2 = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+    const double det = a[0][0] * m0 - a[1][0] * m1 + a[2][0] * m2;
+    const double perm = std::fabs(a[0][0]) * (std::fabs(a[1][1] * a[2][2]) + std::fabs(a[1][2] * a[2][1])) +
+                        std::fabs(a[1][0]) * (std::fabs(a[0][1] * a[2][2]) + std::fabs(a[0][2] * a[2][1])) +
+                        std::fabs(a[2][0]) * (std::fabs(a[0][1] * a[1][2]) + std::fabs(a[0][2] * a[1][1]));
+    if (std::fabs(det) > 1e-13 * perm) return det > 0.0 ? 1 : -1;
+    // exact: every difference as a two-term expansion, every triple product expanded, one exact sum
+    double hi[3][3], lo[3][3];
+    const double* P[3] = {p1, p2, p3};
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) two_sum(P[r][c], -p0[c], hi[r][c], lo[r][c]);
+    std::vector<double> ex;
+    static const int perms[6][4] = {{0, 1, 2, 1}, {1, 2, 0, 1}, {2, 0, 1, 1}, {0, 2, 1, -1}, {1, 0, 2, -1}, {2, 1, 0, -1}};
+    for (int q = 0; q < 6; ++q) {
+        const int c0 = perms[q][0], c1 = perms[q][1], c2 = perms[q][2];
+        const double sg = (double)perms[q][3];
+        for (int m = 0; m < 8; ++m) {
+            const double x = (m & 1) ? lo[0][c0] : hi[0][c0], y = (m & 2) ? lo[1][c1] : hi[1][c1], z = (m & 4) ? lo[2][c2] : hi[2][c2];
+            if (x == 0.0 || y == 0.0 || z == 0.0) continue;
+            double p, e;
+            two_prod(x, y, p, e);
+            double t0, t1, t2, t3;
+            two_prod(p, z, t0, t1);
+            two_prod(e, z, t2, t3);
+            grow(ex, sg * t3); grow(ex, sg * t1); grow(ex, sg * t2); grow(ex, sg * t0);
+        }
+    }
+    for (size_t i = ex.size(); i-- > 0;) if (ex[i] != 0.0) return ex[i] > 0.0 ? 1 : -1;
+    return 0;
+}
+}
+
+// The Delaunay tets whose Voronoi vertex lies inside the tetrahedralised domain, each once: rows of four original seed indices,
+// ascending within a row except for the first two (swapped where orient_3d asks for it, as the reference does), rows sorted.
+// Interior cells emit from vcell_kernel, the cells near the boundary from clip_tet_kernel (one row per piece vertex on three
+// bisectors); check_SR = true as CentroidalVoronoiTesselation::compute_volume sets it (CVT.cpp:245).
+static void compute_rdt_volume(b200cvt_ctx* h) {
+    if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
+    if (!h->has_seeds) throw StateError("no seeds: call b200cvt_set_seeds first");
+    if (h->nranks > 1) throw ArgError("compute_RDT on a partitioned handle: gather the seeds on one handle first");
+    const u32 S = h->S;
+    h->rdtv_n.ensure(1);
+    size_t cap = std::max<size_t>(h->rdtv.cap, (size_t)8 * S + 1024);
+    unsigned long long n = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        h->rdtv.ensure(cap);
+        CUDA_CHECK(cudaMemsetAsync(h->rdtv_n.p, 0, sizeof(unsigned long long), h->stream));
+        evaluate_t<3>(h, 3, 1);
+        CUDA_CHECK(cudaMemcpyAsync(&n, h->rdtv_n.p, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+        sync_stream(h);
+        if (n <= h->rdtv.cap) break;
+        cap = (size_t)n + n / 8 + 1024;
+        if (attempt == 3) throw CapacityError("restricted Delaunay tets keep overflowing their buffer");
+    }
+    std::vector<uint4> rows((size_t)n);
+    if (n > 0) CUDA_CHECK(cudaMemcpy(rows.data(), h->rdtv.p, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<double> xh((size_t)S * 3);
+    CUDA_CHECK(cudaMemcpy(xh.data(), h->x.p, sizeof(double) * (size_t)S * 3, cudaMemcpyDeviceToHost));
+    struct T4 { u32 v[4]; };
+    std::vector<T4> t((size_t)n);
+    for (size_t i = 0; i < (size_t)n; ++i) {
+        u32 q[4] = {rows[i].x, rows[i].y, rows[i].z, rows[i].w};
+        std::sort(q, q + 4);
+        memcpy(t[i].v, q, sizeof(q));
+    }
+    auto less4 = [](const T4& a, const T4& b) { return std::lexicographical_compare(a.v, a.v + 4, b.v, b.v + 4); };
+    std::sort(t.begin(), t.end(), less4);
+    // a piece that passed its radius test in one pass and was computed again with a longer list emits its rows twice
+    t.erase(std::unique(t.begin(), t.end(), [](const T4& a, const T4& b) { return memcmp(a.v, b.v, sizeof(a.v)) == 0; }), t.end());
+    for (T4& r : t)
+        if (orient3d_sign(&xh[(size_t)r.v[0] * 3], &xh[(size_t)r.v[1] * 3], &xh[(size_t)r.v[2] * 3], &xh[(size_t)r.v[3] * 3]) < 0) std::swap(r.v[0], r.v[1]);
+    h->rdt_host.resize(t.size() * 4);
+    if (!t.empty()) memcpy(h->rdt_host.data(), t.data(), sizeof(T4) * t.size());
+    h->rdt_valid = true;
+}
+
 template <int D>
 static void compute_rdt_t(b200cvt_ctx* h) {
     if (h->volumetric) throw ArgError("compute_RDT of a volumetric diagram stays on the reference implementation");
@@ -1754,11 +1850,12 @@ int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uin
     return guarded([&] {
         if (!h || !n_out) throw ArgError("null argument");
         CUDA_CHECK(cudaSetDevice(h->device));
-        if (!h->rdt_valid) { if (h->dim == 3) compute_rdt_t<3>(h); else compute_rdt_t<6>(h); }
-        const uint64_t n = h->rdt_host.size() / 3;
+        if (!h->rdt_valid) { if (h->volumetric) compute_rdt_volume(h); else if (h->dim == 3) compute_rdt_t<3>(h); else compute_rdt_t<6>(h); }
+        const size_t per = h->volumetric ? 4 : 3;
+        const uint64_t n = h->rdt_host.size() / per;
         *n_out = n;
         if (tri_out && cap_triangles > 0)
-            memcpy(tri_out, h->rdt_host.data(), sizeof(u32) * 3 * (size_t)std::min<uint64_t>(n, cap_triangles));
+            memcpy(tri_out, h->rdt_host.data(), sizeof(u32) * per * (size_t)std::min<uint64_t>(n, cap_triangles));
     });
 }
 

@@ -30,6 +30,7 @@ struct TetCell {
     uint8_t t[TETC_MAXT][3];     // adjacent triangles
     uint8_t next[TETC_MAXT];
     uint8_t status[TETC_MAXT];   // 0 used, 1 conflict, 2 free
+    uint8_t pn[TETC_MAXP];       // plane -> position of the neighbour in the seed's list (planes 0..3: the tet's faces)
     uint8_t nt;                  // slots in use (max_t)
     uint8_t np;                  // planes
     uint8_t first_free;
@@ -57,7 +58,7 @@ __device__ __forceinline__ int tetc_find_vertex(const TetCell& C, int t, int v) 
 }
 
 // ConvexCell::clip_by_plane<3>, fast predicates. Returns false if the bisector did not touch the cell.
-__device__ __noinline__ bool tetc_clip(TetCell& C, const double* pi, const double* pj, unsigned long long& st_pv) {
+__device__ __noinline__ bool tetc_clip(TetCell& C, const double* pi, const double* pj, u32 jj, unsigned long long& st_pv) {
     // Phase I: furthest point on pj's side, then flood fill of the conflict zone (side_fast)
     int furthest = -1;
     double fd = 0.0;
@@ -76,6 +77,7 @@ __device__ __noinline__ bool tetc_clip(TetCell& C, const double* pi, const doubl
     if (!(fd < 0.0)) return false;
     if (C.np >= TETC_MAXP) { C.overflow = true; return false; }
     const int new_v = C.np++;
+    C.pn[new_v] = (uint8_t)jj;
     int cbegin = TETC_NONE, cend = TETC_NONE;
     uint8_t stack[TETC_MAXT];
     int sn = 0;
@@ -186,6 +188,8 @@ struct TetClipArgs {
     double* out_s; double* out_v; uint8_t* flags;
     u32* redo_list; u32* redo_n;
     unsigned long long* stats;
+    // mode 3: restricted Delaunay tets (PrimalTetrahedronAction, generic_RVD.h:1036-1058), rows of four ORIGINAL seed indices
+    uint4* tets; unsigned long long* tet_n; unsigned long long tet_cap;
 };
 
 #ifndef TETC_MINBLK
@@ -274,7 +278,7 @@ clip_tet_kernel(TetClipArgs a) {
                     if (C.status[k] == 0) R2 = fmax(R2, dist2<3>(pi, C.p[k]));
                 if (nb_d[jj] > 4.1 * R2) { sr_ok = true; break; }
                 ++st_planes;
-                tetc_clip(C, pi, nb_p + jj * 3, st_pv);
+                tetc_clip(C, pi, nb_p + jj * 3, jj, st_pv);
                 if (C.overflow) break;
             }
             if (C.overflow) { lflags |= 4; continue; }
@@ -283,6 +287,25 @@ clip_tet_kernel(TetClipArgs a) {
             if (t0 < 0) continue;                       // empty cell
             if (!sr_ok && nn > 0) lexh = true;          // list used up before the radius test passed
             ++st_ne;
+            if (a.mode == 3) {
+                // a vertex of the piece on three bisectors is a Voronoi vertex inside this tet: its Delaunay tet, once
+                // (a cell whose list was used up is run again with a longer one: its rows come from the final pass only)
+                if (sr_ok || nn == 0 || nn + 1 >= a.S || nn >= B200CVT_KMAX_DEV) {
+                    const u32 me = (u32)xs[s].orig;
+                    for (int k = 0; k < C.nt; ++k) {
+                        if (C.status[k] != 0) continue;
+                        if (C.v[k][0] < 4 || C.v[k][1] < 4 || C.v[k][2] < 4) continue;
+                        const u32 n1 = (u32)xs[a.nbr[nrow * a.kstride + C.pn[C.v[k][0]]]].orig;
+                        const u32 n2 = (u32)xs[a.nbr[nrow * a.kstride + C.pn[C.v[k][1]]]].orig;
+                        const u32 n3 = (u32)xs[a.nbr[nrow * a.kstride + C.pn[C.v[k][2]]]].orig;
+                        if (me < n1 && me < n2 && me < n3) {
+                            const unsigned long long r = atomicAdd(a.tet_n, 1ull);
+                            if (r < a.tet_cap) a.tets[r] = make_uint4(me, n1, n2, n3);
+                        }
+                    }
+                }
+                continue;
+            }
             // v_to_t (init_v_to_t, generic_RVD_cell.h:640-652): the last used triangle incident to each plane
             uint8_t vt[TETC_MAXP];
             for (int v = 0; v < C.np; ++v) vt[v] = TETC_NONE;

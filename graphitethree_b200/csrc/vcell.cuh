@@ -167,6 +167,8 @@ struct VCellArgs {
     u32* redo_list; u32* redo_n;     // inside the domain, neighbour list used up before the radius test passed (check_SR)
     u32* bnd_list; u32* bnd_n;       // not provably inside the domain: (tet, seed) path
     unsigned long long* stats;       // volumetric handles: [9] cells integrated here, [10] cells sent to the tet path, [12] bisectors applied
+    // mode 3 (restricted Delaunay tets, PrimalTetrahedronAction generic_RVD.h:1036-1058): rows of four ORIGINAL seed indices
+    uint4* tets; unsigned long long* tet_n; unsigned long long tet_cap;
 };
 
 __device__ __forceinline__ bool vc_in(u32 lo, u32 hi, u32 t) { return ((((t & 32u) ? hi : lo) >> (t & 31u)) & 1u) != 0u; }
@@ -201,8 +203,8 @@ __device__ __forceinline__ double vc_radius2(const double (*P)[VC_SLOTS], const 
 }
 
 // ConvexCell::clip_by_plane with the bisector of (pi, pj), the whole warp on one cell. Returns true if the plane cut.
-__device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, unsigned short* IT, unsigned char* FS, VcState& st,
-                                        double pix, double piy, double piz, double pjx, double pjy, double pjz, int lane) {
+__device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, unsigned short* IT, unsigned char* FS, unsigned char* PLN, VcState& st,
+                                        double pix, double piy, double piz, double pjx, double pjy, double pjz, u32 jj, int lane) {
     const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
     double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0, rA = 0.0, rB = 0.0;
     if (uA) {
@@ -252,6 +254,7 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
         }
     }
     const u32 new_v = st.np++;
+    if (lane == 0) PLN[new_v] = (unsigned char)jj;      // which neighbour of the list the plane is the bisector of
     const bool zA = (klo >> lane) & 1u, zB = (khi >> lane) & 1u;
     u32 eA = 0u, eB = 0u;       // bit e: edge e of the zone vertex leads to a kept vertex
     if (zA) eA = (vc_in(klo, khi, tA.x) ? 0u : 1u) | (vc_in(klo, khi, tA.y) ? 0u : 2u) | (vc_in(klo, khi, tA.z) ? 0u : 4u);
@@ -361,6 +364,7 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
     __shared__ u32 sB[VC_WARPS][256];
     __shared__ unsigned short sIT[VC_WARPS][32];
     __shared__ unsigned char sFS[VC_WARPS][VC_SLOTS];
+    __shared__ unsigned char sPLN[VC_WARPS][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double (*P)[VC_SLOTS] = sP[w];
     uchar4* V = sV[w];
@@ -368,6 +372,7 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
     u32* B = sB[w];
     unsigned short* IT = sIT[w];
     unsigned char* FS = sFS[w];
+    unsigned char* PLN = sPLN[w];
     const SeedRec<3>* xs = (const SeedRec<3>*)a.xs;
     const u32 nseeds = a.nseeds_dev ? *a.nseeds_dev : a.nseeds;
     unsigned long long st_cells = 0, st_bnd = 0, st_clips = 0;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
                 const double dj = shfl_d(qd, (int)l);
                 if (dj > 4.1 * R2) { sr_ok = true; done = true; break; }
                 ++st_clips;
-                const bool cut = vc_clip(P, V, T, B, IT, FS, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), lane);
+                const bool cut = vc_clip(P, V, T, B, IT, FS, PLN, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), base + l, lane);
                 if (st.overflow || (st.used_lo | st.used_hi) == 0u) { done = true; break; }
                 if (cut) R2 = vc_radius2(P, st, pix, piy, piz, lane);
             }
@@ -485,6 +490,36 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
             continue;
         }
         ++st_cells;
+        if (a.mode == 3) {
+            // every vertex of the cell on three bisectors is a Voronoi vertex inside the domain: its Delaunay tet, once (smallest seed)
+            __syncwarp();
+            const u32 me = (u32)xs[s].orig;
+            uint4 rowA = make_uint4(0, 0, 0, 0), rowB = rowA;
+            bool eA = false, eB = false;
+            if (uA) {
+                const uchar4 v = V[lane];
+                if (v.x >= 6 && v.y >= 6 && v.z >= 6) {
+                    rowA = make_uint4(me, (u32)xs[nrowp[PLN[v.x]]].orig, (u32)xs[nrowp[PLN[v.y]]].orig, (u32)xs[nrowp[PLN[v.z]]].orig);
+                    eA = me < rowA.y && me < rowA.z && me < rowA.w;
+                }
+            }
+            if (uB) {
+                const uchar4 v = V[lane + 32];
+                if (v.x >= 6 && v.y >= 6 && v.z >= 6) {
+                    rowB = make_uint4(me, (u32)xs[nrowp[PLN[v.x]]].orig, (u32)xs[nrowp[PLN[v.y]]].orig, (u32)xs[nrowp[PLN[v.z]]].orig);
+                    eB = me < rowB.y && me < rowB.z && me < rowB.w;
+                }
+            }
+            const u32 mA = __ballot_sync(B200_FULL, eA), mB = __ballot_sync(B200_FULL, eB);
+            const u32 tot = (u32)__popc(mA) + (u32)__popc(mB);
+            unsigned long long base_row = 0;
+            if (lane == 0 && tot) base_row = atomicAdd(a.tet_n, (unsigned long long)tot);
+            base_row = __shfl_sync(B200_FULL, base_row, 0);
+            const u32 ltm = (1u << lane) - 1u;
+            if (eA) { const unsigned long long r = base_row + __popc(mA & ltm); if (r < a.tet_cap) a.tets[r] = rowA; }
+            if (eB) { const unsigned long long r = base_row + __popc(mA) + __popc(mB & ltm); if (r < a.tet_cap) a.tets[r] = rowB; }
+            continue;
+        }
         // integrate. Every face (plane id) is fanned from its lowest-numbered vertex; one fan triangle per (vertex, face) corner.
         uchar4 vA = make_uchar4(0, 0, 0, 0), vB = vA, tA = vA, tB = vA;
         if (uA) { vA = V[lane]; tA = T[lane]; }

@@ -116,7 +116,12 @@ int b200cvt_funcgrad(b200cvt_handle h, int check_SR, double* f_accum, double* g_
  * lexicographically (the reference's order is its traversal order); duplicates are kept as the reference keeps them.
  * The embedding the reference returns with the triangles is the seed array itself. Call with tri_out = NULL to get the
  * count, then with a buffer of cap_triangles rows. Partitioned handles return the triangles of their own seeds.
- * Needs the facet adjacency: the one given to b200cvt_set_mesh, else it is rebuilt from shared edges. */
+ * Needs the facet adjacency: the one given to b200cvt_set_mesh, else it is rebuilt from shared edges.
+ * Volumetric handles (RVD.cpp:2308-2335, for_each_primal_tetrahedron, G/voronoi/generic_RVD.h:1017-1058, check_SR = true as
+ * CentroidalVoronoiTesselation::compute_volume sets it, CVT.cpp:245): rows of FOUR original seed indices, one per Voronoi
+ * vertex that lies inside the tetrahedralised domain (the Delaunay tet of its four seeds), indices ascending within a row
+ * except that the first two are swapped where PCK::orient_3d of the four seeds is negative (the reference's reorientation;
+ * exact arithmetic where the floating-point determinant is not conclusive), rows sorted and unique. */
 int b200cvt_rdt(b200cvt_handle h, uint32_t* tri_out, uint64_t cap_triangles, uint64_t* n_out);
 
 /* Replaces: RestrictedVoronoiDiagram::compute_RDT with RDT_MULTINERVE (| RDT_RVC_CENTROIDS | RDT_PREFER_SEEDS), the mode

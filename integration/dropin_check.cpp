@@ -21,6 +21,7 @@
 #include <geogram/mesh/mesh_distance.h>
 #include <geogram/mesh/mesh_geometry.h>
 #include <geogram/mesh/mesh_repair.h>
+#include <geogram/numerics/predicates.h>
 
 #include <algorithm>
 #include <array>
@@ -118,6 +119,7 @@ namespace {
         vector<index_t> rdt;
         double t_lloyd = 0.0, t_newton = 0.0;
         bool on_gpu = false;
+        index_t nb_volume_tets = 0;
     };
 
     template <class CVT_T>
@@ -140,7 +142,17 @@ namespace {
             out.on_gpu = cvt.last_call_on_gpu();
         }
         if(g_volumetric) {
-            return;        /* compute_volume / the tetrahedral RDT stay on the reference implementation */
+            /* CentroidalVoronoiTesselation::compute_volume (CVT.cpp:234-270): set_vertices, check_SR = true, compute_RDT —
+             * the Delaunay tets whose Voronoi vertex lies inside the domain */
+            cvt.RVD()->delete_threads();
+            cvt.compute_volume(&out.surface);
+            out.nb_volume_tets = out.surface.cells.nb();
+            vector<double> emb;
+            cvt.RVD()->compute_RDT(out.rdt, emb, RestrictedVoronoiDiagram::RDTMode(0));
+            if constexpr (std::is_same<CVT_T, CentroidalVoronoiTesselationB200>::value) {
+                out.on_gpu = cvt.last_call_on_gpu();
+            }
+            return;
         }
         cvt.RVD()->delete_threads();
         cvt.set_use_RVC_centroids(false);   /* vertices of the remesh = the seeds, so that the triangle sets are comparable */
@@ -243,8 +255,30 @@ int main(int argc, char** argv) {
         }
     }
 
-    std::set<Tri> ta = triangle_set(ref.rdt), tb = triangle_set(b200.rdt);
-    size_t only_ref = 0, only_b200 = 0;
+    std::set<Tri> ta, tb;
+    size_t only_ref = 0, only_b200 = 0, vol_tets_ref = 0, vol_tets_b200 = 0, vol_bad_orientation = 0;
+    if(g_volumetric) {
+        /* tets as sorted quadruples; every row of both sides positively oriented (RVD.cpp:2318-2329) */
+        typedef std::array<index_t, 4> Tet;
+        auto tet_set = [&](const vector<index_t>& rows, const std::vector<double>& x) {
+            std::set<Tet> out;
+            for(index_t f = 0; f + 3 < rows.size(); f += 4) {
+                Tet t = {{rows[f], rows[f + 1], rows[f + 2], rows[f + 3]}};
+                if(PCK::orient_3d(&x[size_t(t[0]) * 3], &x[size_t(t[1]) * 3], &x[size_t(t[2]) * 3], &x[size_t(t[3]) * 3]) <= 0) {
+                    ++vol_bad_orientation;
+                }
+                std::sort(t.begin(), t.end());
+                out.insert(t);
+            }
+            return out;
+        };
+        std::set<Tet> va = tet_set(ref.rdt, ref.x_final), vb = tet_set(b200.rdt, ref.x_final);
+        vol_tets_ref = va.size(); vol_tets_b200 = vb.size();
+        for(const Tet& t : va) { if(vb.find(t) == vb.end()) { ++only_ref; } }
+        for(const Tet& t : vb) { if(va.find(t) == va.end()) { ++only_b200; } }
+    } else {
+        ta = triangle_set(ref.rdt); tb = triangle_set(b200.rdt);
+    }
     for(const Tri& t : ta) {
         if(tb.find(t) == tb.end()) {
             ++only_ref;
@@ -347,6 +381,7 @@ int main(int argc, char** argv) {
         "{\"volumetric\": %s, \"seeds\": %u, \"dim\": %u, \"pre_lloyd\": %u, \"lloyd\": %u, \"newton\": %u, \"on_gpu\": %s, "
         "\"max_abs_dx_lloyd\": %.3e, \"max_abs_dx_final\": %.3e, "
         "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
+        "\"volume_tets_ref\": %zu, \"volume_tets_b200\": %zu, \"volume_bad_orientation\": %zu, \"compute_volume_cells_ref\": %u, \"compute_volume_cells_b200\": %u, "
         "\"ref_vertices\": %u, \"b200_vertices\": %u, "
         "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"hausdorff_ref_to_ref_sorted\": %.3e, \"bbox_diagonal\": %.6e, "
         "\"hausdorff_raw_rdt_ref_to_b200\": %.3e, \"hausdorff_raw_rdt_b200_to_ref\": %.3e, \"nonmanifold_edges\": %zu, \"isolated_seeds_ref\": %u, \"isolated_seeds_b200\": %u, "
@@ -357,6 +392,7 @@ int main(int argc, char** argv) {
         g_volumetric ? "true" : "false", S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
         max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
         ta.size(), tb.size(), only_ref, only_b200,
+        vol_tets_ref, vol_tets_b200, vol_bad_orientation, unsigned(ref.nb_volume_tets), unsigned(b200.nb_volume_tets),
         ref.surface.vertices.nb(), b200.surface.vertices.nb(),
         h_ab, h_ba, h_ctrl, diag,
         h_raw_ab, h_raw_ba, nonmanifold_edges, isolated_ref, isolated_b200,

@@ -475,6 +475,22 @@ namespace GEO {
          * tree of the input surface: reference implementation. */
         const bool multinerve = (mode & RDT_MULTINERVE) != 0;
         const bool needs_aabb = (mode & (RDT_SELECT_NEAREST | RDT_PROJECT_ON_SURFACE)) != 0;
+        if(volumetric_ && gpu_eligible() && check_SR_) {
+            /* volumes: "only simple mode is supported" (RVD.cpp:2309), whatever the mode bits: the Delaunay tets whose Voronoi
+             * vertex lies inside the domain, reoriented, with the seeds as embedding (RVD.cpp:2308-2335) */
+            b200cvt_handle hv = handle(true);
+            upload_seeds();
+            uint64_t n = 0;
+            check(b200cvt_rdt(hv, nullptr, 0, &n), "b200cvt_rdt");
+            std::vector<uint32_t> tets(size_t(n) * 4);
+            check(b200cvt_rdt(hv, tets.data(), n, &n), "b200cvt_rdt");
+            simplices.assign(tets.begin(), tets.end());
+            const index_t nb = delaunay_->nb_vertices();
+            embedding.assign(delaunay_->vertex_ptr(0), delaunay_->vertex_ptr(0) + size_t(nb) * dimension_);
+            report_flags(hv, nb);
+            ++nb_gpu_calls_;
+            return;
+        }
         if(volumetric_ || !gpu_eligible() || !check_SR_ || needs_aabb || (!multinerve && mode != RDTMode(0))) {
             ref_->compute_RDT(simplices, embedding, mode, seed_is_locked, AABB);
             return;

@@ -937,6 +937,8 @@ static int integrate_cell(orc_rvd* R, orc_accum* A, u32 v, orc_cell* C) {
     return 1;
 }
 
+static struct { int on; u32* tet; u64 cap; u64 n; } orc_rdt_vol_sink = {0, 0, 0, 0};
+
 /* compute_volumetric_with_seeds_priority — G/voronoi/generic_RVD.h:1464-1597. R->T holds 4 vertex ids per tet,
  * R->adj 4 adjacent tets per tet (-1: border; adj[4t+lf] is across the face opposite to local vertex lf). */
 static void volumetric_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 pairs_cap, u64* npairs_out) {
@@ -966,6 +968,29 @@ static void volumetric_traversal(orc_rvd* R, orc_accum* A, u32* pairs_out, u64 p
                 cell_init_from_tet(&C, R->V, R->T, R->adj, ct);
                 cell_clip_by_cell_SR(R, seed, &C, &fstack, &fstack_cap);
                 R->cn.pairs++;
+                if (orc_rdt_vol_sink.on) {
+                    /* PrimalTetrahedronAction — G/voronoi/generic_RVD.h:1036-1058: every vertex of the piece that lies on three
+                     * bisectors is a Voronoi vertex inside the tet; its Delaunay tet is emitted by its smallest seed */
+                    for (u32 it = 0; it < C.nt; ++it) {
+                        if (C.tri[it].status != CTRI_USED) continue;
+                        int64_t i0 = C.vert[C.tri[it].v[0]].id, i1 = C.vert[C.tri[it].v[1]].id, i2 = C.vert[C.tri[it].v[2]].id;
+                        if (i0 > 0 && i1 > 0 && i2 > 0) {
+                            u32 v1 = (u32)(i0 - 1), v2 = (u32)(i1 - 1), v3 = (u32)(i2 - 1);
+                            /* SymbolicVertex keeps its bisectors sorted (GenericVoronoiDiagram::SymbolicVertex, a sorted
+                             * small set): bisector(0) > bisector(1) > bisector(2) in the rows the reference emits */
+                            if (v1 < v2) { u32 q = v1; v1 = v2; v2 = q; }
+                            if (v2 < v3) { u32 q = v2; v2 = v3; v3 = q; }
+                            if (v1 < v2) { u32 q = v1; v1 = v2; v2 = q; }
+                            if (seed < v1 && seed < v2 && seed < v3) {
+                                if (orc_rdt_vol_sink.n < orc_rdt_vol_sink.cap) {
+                                    u32* o = orc_rdt_vol_sink.tet + 4 * orc_rdt_vol_sink.n;
+                                    o[0] = seed; o[1] = v1; o[2] = v2; o[3] = v3;
+                                }
+                                orc_rdt_vol_sink.n++;
+                            }
+                        }
+                    }
+                }
                 if (integrate_cell(R, A, seed, &C)) {
                     R->cn.nonempty_pairs++;
                     if (pairs_out && npairs < pairs_cap) { pairs_out[2 * npairs] = seed; pairs_out[2 * npairs + 1] = ct; }
@@ -1140,6 +1165,48 @@ int orc_rdt(int dim, u32 nv, const double* V, u32 nt, const u32* T, const int32_
     orc_symbolic = 0;
     if (n_out) *n_out = orc_rdt_sink.n;
     orc_rdt_sink.tri = NULL; orc_rdt_sink.cap = 0;
+    rvd_free(&R, NULL);
+    free(m); free(mg); free(fl);
+    return 0;
+}
+
+/* RestrictedVoronoiDiagram::compute_RDT in volumetric mode — G/voronoi/RVD.cpp:2308-2335: for_each_primal_tetrahedron
+ * (GetPrimalTetrahedra), check_SR = true as CentroidalVoronoiTesselation::compute_volume sets it (CVT.cpp:245), then every
+ * tet is reoriented with orient_3d (swap of the first two vertices). tet_out: rows (seed, v1, v2, v3) in traversal order;
+ * *n_out may exceed cap. The orientation uses a long double determinant (the reference: the exact predicate PCK::orient_3d);
+ * *n_uncertain counts the rows whose determinant is below the rounding bound. */
+int orc_rdt_volume(u32 nv, const double* V, u32 nt, const u32* T, const int32_t* adj, u32 S, const double* x,
+                   u32 k, u32 kcap, u32* tet_out, u64 cap, u64* n_out, u64* n_uncertain) {
+    if (!orc_volumetric_mode) return 1;
+    orc_rvd R;
+    uint8_t* fl = (uint8_t*)calloc(S ? S : 1, 1);
+    rvd_init(&R, 3, nv, V, nt, T, adj, NULL, S, x, k, kcap, NULL, 1, fl);
+    double* m = (double*)calloc(S ? S : 1, sizeof(double));
+    double* mg = (double*)calloc((size_t)(S ? S : 1) * 3, sizeof(double));
+    orc_accum A;
+    A.mode = 0; A.m = m; A.mg = mg; A.g = NULL; A.f_seed = NULL; A.f = 0.0;
+    orc_rdt_vol_sink.on = 1; orc_rdt_vol_sink.tet = tet_out; orc_rdt_vol_sink.cap = cap; orc_rdt_vol_sink.n = 0;
+    volumetric_traversal(&R, &A, NULL, 0, NULL);
+    orc_rdt_vol_sink.on = 0;
+    u64 n = orc_rdt_vol_sink.n, unc = 0;
+    for (u64 t = 0; t < n && t < cap; ++t) {
+        u32* o = tet_out + 4 * t;
+        const double* p1 = x + 3 * (size_t)o[0]; const double* p2 = x + 3 * (size_t)o[1];
+        const double* p3 = x + 3 * (size_t)o[2]; const double* p4 = x + 3 * (size_t)o[3];
+        long double a[3], b[3], c[3], mag = 0.0L;
+        for (int i = 0; i < 3; ++i) {
+            a[i] = (long double)p2[i] - p1[i]; b[i] = (long double)p3[i] - p1[i]; c[i] = (long double)p4[i] - p1[i];
+        }
+        long double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+        mag = fabsl(a[0]) * (fabsl(b[1] * c[2]) + fabsl(b[2] * c[1])) + fabsl(a[1]) * (fabsl(b[0] * c[2]) + fabsl(b[2] * c[0])) +
+              fabsl(a[2]) * (fabsl(b[0] * c[1]) + fabsl(b[1] * c[0]));
+        if (fabsl(det) <= 1e-17L * mag) unc++;
+        /* PCK::orient_3d(p1, p2, p3, p4) = sign det(p2 - p1, p3 - p1, p4 - p1) (numerics/predicates/orient3d.h:4-24) */
+        if (det < 0) { u32 tmp = o[0]; o[0] = o[1]; o[1] = tmp; }
+    }
+    if (n_out) *n_out = n;
+    if (n_uncertain) *n_uncertain = unc;
+    orc_rdt_vol_sink.tet = NULL; orc_rdt_vol_sink.cap = 0;
     rvd_free(&R, NULL);
     free(m); free(mg); free(fl);
     return 0;

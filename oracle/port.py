@@ -157,6 +157,25 @@ def rdt(V, T, x, k=20, kcap=256, adj=None):
     return tri[:n.value].copy()
 
 
+def rdt_volume(V, T, x, k=20, kcap=256, adj=None):
+    """compute_RDT in volumetric mode (RVD.cpp:2308-2335): (n, 4) rows (seed, v1, v2, v3) in the reference's traversal order,
+    reoriented as the reference does; second value: rows whose orientation determinant is below the rounding bound."""
+    V, x = _f64(V), _f64(x)
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    if adj is None:
+        adj = tet_adjacency(T)
+    S = x.shape[0]
+    cap = 10 * S + 64
+    tet = np.zeros((cap, 4), dtype=np.uint32)
+    n, unc = C.c_uint64(0), C.c_uint64(0)
+    with _Volumetric(T):
+        rc = _lib().orc_rdt_volume(C.c_uint32(V.shape[0]), _p(V, _dp), C.c_uint32(T.shape[0]), _p(T, _up), _p(adj, _ip),
+                                   C.c_uint32(S), _p(x, _dp), C.c_uint32(k), C.c_uint32(min(kcap, max(S - 1, 1))), _p(tet, _up),
+                                   C.c_uint64(cap), C.byref(n), C.byref(unc))
+    assert rc == 0 and n.value <= cap
+    return tet[:n.value].copy(), int(unc.value)
+
+
 def rdt_multinerve(V, T, x, use_centroids=True, prefer_seeds=True, locked=None, k=20, kcap=256, adj=None):
     """compute_RDT with RDT_MULTINERVE (| RDT_RVC_CENTROIDS | RDT_PREFER_SEEDS), RVD.cpp:1901-2264, in the reference's own
     order: (triangles [n, 3] of component indices as emitted, vertices [nc, dim], seed of every vertex [nc])."""

@@ -128,6 +128,22 @@ def volume_case(V, T, X, lloyd_iters=4, newton_iters=3):
     return out
 
 
+def rdt_volume_case(V, T, X, lloyd_iters=3):
+    """compute_RDT in volumetric mode (CentroidalVoronoiTesselation::compute_volume): tets of seed indices, on the raw
+    sampling and after Lloyd iterations."""
+    out = dict(V=V, F=T, X=X, volumetric=np.int32(1))
+    r = RefCVT(V, T, volumetric=True, multithread=False)
+    r.set_points(X); r.update_delaunay()
+    out["rdt_tets_raw"], _ = r.rdt(0)
+    r.lloyd(lloyd_iters)
+    out["x_lloyd"] = r.points()
+    r.update_delaunay()
+    out["rdt_tets_lloyd"], emb = r.rdt(0)
+    assert np.array_equal(emb, out["x_lloyd"])
+    r.close()
+    return out
+
+
 def main():
     V, F = shapes.icosphere(6)
     np.savez_compressed(os.path.join(HERE, "sphere_s150.npz"), **case(V, F, shapes.sample_surface(V, F, 150, 3)))
@@ -145,6 +161,8 @@ def main():
     V, T = shapes.kuhn_cube(6)
     X = np.random.default_rng(13).random((130, 3))
     np.savez_compressed(os.path.join(HERE, "volume_cube_s130.npz"), **volume_case(V, T, X))
+    V, T = shapes.kuhn_cube(6)
+    np.savez_compressed(os.path.join(HERE, "rdtvol_cube_s160.npz"), **rdt_volume_case(V, T, 0.02 + 0.96 * np.random.default_rng(17).random((160, 3))))
     for n in sorted(os.listdir(HERE)):
         if n.endswith(".npz"):
             print(n, os.path.getsize(os.path.join(HERE, n)))

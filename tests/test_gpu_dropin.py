@@ -84,6 +84,11 @@ def test_dropin_volumetric_lloyd_newton(tmp_path):
     r = run_check(tmp_path, V, T, X, 0, 5, pre=3, volumetric=True)
     assert r["volumetric"] and r["on_gpu"]
     assert r["max_abs_dx_final"] <= 1e-7
+    # CentroidalVoronoiTesselation::compute_volume: the adapter's compute_RDT in volumetric mode (b200cvt_rdt on tets) gives
+    # the same Delaunay tets as the stock class, all positively oriented, and compute_volume builds the same number of cells
+    assert r["volume_tets_ref"] == r["volume_tets_b200"] > 0 and r["only_ref"] == 0 and r["only_b200"] == 0
+    assert r["volume_bad_orientation"] == 0
+    assert r["compute_volume_cells_ref"] == r["compute_volume_cells_b200"] > 0
 
 
 def test_dropin_c2_full_size(tmp_path):

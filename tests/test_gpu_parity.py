@@ -23,7 +23,7 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling"))]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling", "rdtvol"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -276,8 +276,10 @@ def test_error_behaviour(built):
     hv.set_mesh(Vt, T)
     hv.set_seeds(X)
     with pytest.raises(capi.B200CVTError) as ei:
-        hv.rdt()                                    # tetrahedral RDT stays on the reference implementation
+        hv.rdt_multinerve()                         # the reference has no multinerve mode for volumes either (RVD.cpp:2309)
     assert ei.value.code == 1
+    tets = hv.rdt()                                 # seeds on a sphere, most of them outside the unit cube: still a valid call
+    assert tets.shape[1] == 4
     hv.close()
 
 
@@ -651,6 +653,67 @@ def test_volume_cell_with_more_vertices_than_slots_takes_the_tet_path(built, mon
     assert np.abs(a[1] - b[1]).max() <= 1e-12 * np.abs(a[1]).max()
     assert abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
     assert np.abs(a[3] - b[3]).max() <= 1e-12 * np.abs(a[3]).max()
+
+
+RDTVOL = os.path.join(os.path.dirname(ALL_GOLDEN[0]), "rdtvol_cube_s160.npz")
+
+
+def lex_rows(a):
+    return a[np.lexsort(a.T[::-1])] if len(a) else a
+
+
+def assert_same_tets(gpu, ref_rows, x):
+    """same Delaunay tets (as sets of four seeds), every GPU row positively oriented like the reference's (orient_3d > 0)"""
+    assert np.array_equal(lex_rows(np.sort(gpu, axis=1)), lex_rows(np.sort(ref_rows, axis=1)))
+    P = x[gpu.astype(np.int64)]
+    det = np.linalg.det(np.stack([P[:, 1] - P[:, 0], P[:, 2] - P[:, 0], P[:, 3] - P[:, 0]], axis=1))
+    assert (det > 0).all()
+    # canonical form: ascending except for the swap of the first two, rows sorted and unique
+    srt = np.sort(gpu, axis=1)
+    assert np.array_equal(srt, lex_rows(srt)) and len(np.unique(srt, axis=0)) == len(srt)
+
+
+def test_volume_rdt_against_reference_golden(built, monkeypatch):
+    """compute_RDT of a volumetric diagram (CentroidalVoronoiTesselation::compute_volume, RVD.cpp:2308-2335): the Delaunay tets
+    whose Voronoi vertex lies inside the domain, from the cell-first path and from the (tet, seed) path alone."""
+    G = load(RDTVOL)
+    V, T = G["V"], G["F"]
+    for env in ("1", "0"):
+        monkeypatch.setenv("B200CVT_VCELL", env)
+        h = volume_handle(V, T)
+        for x, key in ((G["X"], "rdt_tets_raw"), (G["x_lloyd"], "rdt_tets_lloyd")):
+            h.set_seeds(x)
+            assert_same_tets(h.rdt(), G[key], x)
+        # the cache follows the seeds
+        x = h.lloyd(G["X"], 3)
+        assert np.abs(x - G["x_lloyd"]).max() <= 1e-9
+        assert_same_tets(h.rdt(), G["rdt_tets_lloyd"], x)
+        h.close()
+
+
+def test_volume_rdt_against_oracle_and_delaunay(built):
+    """larger case: against the oracle's restatement (pinned to the reference row by row on the CPU) and against the Delaunay
+    triangulation of the seeds (scipy / Qhull): the tets whose circumcentre lies in the unit cube"""
+    V, T = shapes.kuhn_cube(16)
+    X = 0.01 + 0.98 * np.random.default_rng(41).random((3000, 3))
+    h = volume_handle(V, T)
+    x = h.lloyd(X, 3)
+    h.set_seeds(x)
+    tets = h.rdt()
+    h.close()
+    ot, unc = port.rdt_volume(V, T, x)
+    assert unc == 0
+    assert_same_tets(tets, ot, x)
+    from scipy.spatial import Delaunay
+    D = Delaunay(x)
+    P = x[D.simplices]
+    cc = np.linalg.solve(2 * (P[:, 1:] - P[:, :1]), ((P[:, 1:] ** 2).sum(2) - (P[:, :1] ** 2).sum(2))[..., None])[..., 0]
+    margin = 1e-9
+    surely_in = ((cc > margin) & (cc < 1 - margin)).all(1)
+    maybe_in = ((cc > -margin) & (cc < 1 + margin)).all(1)
+    mine = set(map(tuple, np.sort(tets, axis=1).tolist()))
+    assert set(map(tuple, np.sort(D.simplices[surely_in], axis=1).tolist())) <= mine
+    assert mine <= set(map(tuple, np.sort(D.simplices[maybe_in], axis=1).tolist()))
 
 
 def test_sharded_volumetric_two_partitions_one_gpu(built):

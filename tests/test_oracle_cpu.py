@@ -11,7 +11,7 @@ from graphitethree_b200 import shapes
 from oracle import port, ref
 
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling"))]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("volume_", "thinbox_multinerve", "sampling", "rdtvol"))]
 GOLDEN_VOLUME = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("volume_")]
 
 
@@ -151,6 +151,52 @@ def test_volume_oracle_matches_live_reference():
         assert f == e.f and np.array_equal(g, e.g)
     finally:
         r.close()
+
+
+RDTVOL = os.path.join(os.path.dirname(ALL_GOLDEN[0]), "rdtvol_cube_s160.npz")
+
+
+def exact_orient3d(p):
+    """sign of det(p1 - p0, p2 - p0, p3 - p0) in rational arithmetic (the reference: PCK::orient_3d)"""
+    from fractions import Fraction
+    q = [[Fraction(float(c)) for c in row] for row in p]
+    a, b, c = ([q[i][k] - q[0][k] for k in range(3)] for i in (1, 2, 3))
+    d = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0])
+    return (d > 0) - (d < 0)
+
+
+def test_volume_rdt_oracle_matches_reference_golden():
+    """compute_RDT in volumetric mode (RVD.cpp:2308-2335): the oracle returns the reference's rows in the reference's order."""
+    G = load(RDTVOL)
+    V, T = G["V"], G["F"]
+    for x, key in ((G["X"], "rdt_tets_raw"), (G["x_lloyd"], "rdt_tets_lloyd")):
+        tet, unc = port.rdt_volume(V, T, x)
+        assert unc == 0 and np.array_equal(tet, G[key])
+        assert all(exact_orient3d(x[row]) > 0 for row in tet[::7])
+        # independent check: the Delaunay tets whose circumcentre lies in the cube
+        from scipy.spatial import Delaunay
+        D = Delaunay(x)
+        P = x[D.simplices]
+        cc = np.linalg.solve(2 * (P[:, 1:] - P[:, :1]), ((P[:, 1:] ** 2).sum(2) - (P[:, :1] ** 2).sum(2))[..., None])[..., 0]
+        inside = ((cc > 0) & (cc < 1)).all(1)
+        lex = lambda a: a[np.lexsort(a.T[::-1])]
+        assert np.array_equal(lex(np.sort(D.simplices[inside], axis=1).astype(np.uint32)), lex(np.sort(tet, axis=1)))
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_volume_rdt_oracle_matches_live_reference():
+    V, T = shapes.kuhn_cube(8)
+    X = 0.02 + 0.96 * np.random.default_rng(23).random((400, 3))
+    x, _ = port.lloyd(V, T, X, 2)
+    r = ref.RefCVT(V, T, volumetric=True, multithread=False)
+    try:
+        r.set_points(x)
+        r.update_delaunay()
+        rt, emb = r.rdt(0)
+    finally:
+        r.close()
+    tet, unc = port.rdt_volume(V, T, x)
+    assert np.array_equal(tet, rt) and np.array_equal(emb, x)
 
 
 def test_volume_analytic_identities_exact_cells():
