@@ -464,6 +464,8 @@ def main():
                                     "units_per_launch": int(knn_queries),
                                     "note": "issue-bound (64-bit key compare-exchanges), not HBM; time = the kNN phase of bench.py's timers"}
             line["phase_ms_per_evaluation"] = {k: cum[k] / n_launch for k in ("sort", "knn", "pairs", "clip", "clip_kernel")}
+            # outside the phases: the L-BFGS direction kernel (+ the push of the trial point to the peers), once per Newton iteration
+            line["lbfgs_direction_ms_per_iteration"] = cum["cells"] / max(args.steps * evals["newton"]["iters"], 1)
             if by_rank is not None:
                 line["phase_ms_per_evaluation_over_ranks"] = {
                     k: {"min": float(by_rank[:, i].min() / n_launch), "max": float(by_rank[:, i].max() / n_launch)}

@@ -316,8 +316,11 @@ struct b200cvt_ctx {
     size_t vgrid_ncell = 0; bool vneed_active = false;   // the facet walk is restricted to the tets near the cells of the tet path
     DevBuf<u32> vc_bnd, vc_redo_a, vc_redo_b, vc_n;
     bool use_vcell = true;
+    bool use_lbfgs_gram = true;                    // B200CVT_LBFGS_GRAM=0: the level-by-level direction kernel
     DevBuf<uint4> rdtv; DevBuf<unsigned long long> rdtv_n;   // volumetric RDT rows (mode 3)
     cudaEvent_t evc[2] = {nullptr, nullptr};   // around the cell stage
+    cudaEvent_t evl[2] = {nullptr, nullptr};   // around the L-BFGS direction kernel (+ the push of the trial point)
+    bool evl_used = false;
     bool evc_used = false;
     DevBuf<u32> facet_guess;
     // surface meshes: host copies kept for the facet adjacency the RDT extraction needs (built on first use)
@@ -459,6 +462,11 @@ static void sync_stream(b200cvt_ctx* h) {
         }
         float tk = 0.f;
         if (h->evk[0] && cudaEventElapsedTime(&tk, h->evk[0], h->evk[1]) == cudaSuccess) h->cum_ms[4] += tk;
+        if (h->evl_used) {
+            float tl = 0.f;
+            if (cudaEventElapsedTime(&tl, h->evl[0], h->evl[1]) == cudaSuccess) h->cum_ms[5] += tl;
+            h->evl_used = false;
+        }
         if (h->evc_used) {
             // volumetric: the cell stage runs between the kNN and the facet walk (its output restricts the walk); it is
             // accounted to the clip phase
@@ -1677,6 +1685,7 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
         std::unique_ptr<b200cvt_ctx> h(new b200cvt_ctx);
         h->device = device; h->dim = dim; h->volumetric = volumetric;
         { const char* e = getenv("B200CVT_VCELL"); h->use_vcell = !(e && atoi(e) == 0); }
+        { const char* e = getenv("B200CVT_LBFGS_GRAM"); h->use_lbfgs_gram = !(e && atoi(e) == 0); }
         CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
@@ -1694,6 +1703,7 @@ void b200cvt_destroy(b200cvt_handle h) {
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     for (int i = 0; i < 2; ++i) if (h->evc[i]) cudaEventDestroy(h->evc[i]);
+    for (int i = 0; i < 2; ++i) if (h->evl[i]) cudaEventDestroy(h->evl[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;                         // DevBuf members release their device memory
 }

@@ -58,9 +58,10 @@ static NcclApi& nccl_api() {
                                      __FILE__ + ":" + std::to_string(__LINE__));                          \
     } while (0)
 
-// One mailbox entry: written by exactly one peer (its rank selects the entry), read by the owner. 64 bytes.
-struct __align__(64) PeerBox {
-    double v[6];
+// One mailbox entry: written by exactly one peer (its rank selects the entry), read by the owner. 384 bytes.
+#define B200_BOX_DOUBLES 46
+struct __align__(128) PeerBox {
+    double v[B200_BOX_DOUBLES];
     unsigned long long seq;
     unsigned long long pad;
 };
@@ -80,7 +81,7 @@ struct PeerComm {
 // of its slowest peer (it needs that peer's entry to finish the current one).
 template <int K>
 __device__ __forceinline__ void peer_allreduce(const PeerComm& pc, const double* vals, double* result) {
-    static_assert(K <= 6, "mailbox entry holds 6 doubles");
+    static_assert(K <= B200_BOX_DOUBLES, "mailbox entry too small");
     const int lane = threadIdx.x & 31;
     const unsigned long long seq = *((volatile unsigned long long*)pc.seq) + 1ull;
     const int par = (int)(seq & 1ull);
@@ -115,6 +116,36 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& pc, const double*
         for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(B200_FULL, got[j], r);
         result[j] = t;
     }
+    if (lane == 0) *((volatile unsigned long long*)pc.seq) = seq;
+}
+
+// The same for n <= B200_BOX_DOUBLES values held in memory (vals, result: local global / shared memory; may alias): the
+// whole first warp of ONE block calls it. Lane r < nranks stores the n values into rank r's mailbox and waits for rank r's
+// entry in its own; then lane j adds the j-th values of all entries in rank order.
+__device__ __forceinline__ void peer_allreduce_n(const PeerComm& pc, const double* vals, int n, double* result) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long seq = *((volatile unsigned long long*)pc.seq) + 1ull;
+    const int par = (int)(seq & 1ull);
+    if (lane < pc.nranks) {
+        volatile PeerBox* b = pc.boxes[lane] + par * B200_MAX_RANKS + pc.rank;
+        for (int j = 0; j < n; ++j) b->v[j] = vals[j];
+        __threadfence_system();
+        b->seq = seq;
+        volatile PeerBox* m = pc.boxes[pc.rank] + par * B200_MAX_RANKS + lane;
+        const long long t0 = clock64();
+        while (m->seq != seq) {
+            __nanosleep(32);
+            if (clock64() - t0 > 40000000000ll) { atomicExch(pc.error, 1u); break; }      // ~20 s: a peer is gone
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+        double t = 0.0;
+        for (int r = 0; r < pc.nranks; ++r) t += ((volatile PeerBox*)(pc.boxes[pc.rank] + par * B200_MAX_RANKS + r))->v[j];
+        result[j] = t;
+    }
+    __syncwarp();
     if (lane == 0) *((volatile unsigned long long*)pc.seq) = seq;
 }
 

@@ -22,6 +22,8 @@
 #include <cooperative_groups.h>
 
 #define LBFGS_MAXM 32
+#define LBFGS_GRAM_MAXM 8        // history sizes the one-reduction direction kernel serves (5 (M - 1) + 5 <= 40 dot products)
+#define LBFGS_GRAM_MAXK 40
 
 struct McsState {
     double dg, dgm, dginit, dgtest, dgx, dgxm, dgy, dgym, finit, fm, ftest1, fx, fxm, fy, fym;
@@ -39,6 +41,8 @@ struct LbfgsScalars {
     double rho[LBFGS_MAXM];
     McsState L;
     unsigned int red_counter;
+    // Gram matrices of the history, indexed by slot: SY[a][b] = s_a . y_b, YY[a][b] = y_a . y_b (lbfgs_direction_gram_kernel)
+    double SY[LBFGS_GRAM_MAXM][LBFGS_GRAM_MAXM], YY[LBFGS_GRAM_MAXM][LBFGS_GRAM_MAXM];
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sm) {
@@ -425,6 +429,156 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
         double t = a.wa[i];
         t += stp * a.q[i];
         a.x[i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same update with ONE reduction (history of at most LBFGS_GRAM_MAXM pairs). The two-loop recursion needs 2 (bound + 1)
+// dot products in sequence, each a grid barrier here and a round trip over NVLink on several GPUs (117 us per iteration on one
+// B200, 300 us on two). All of them are linear in quantities that are known up front: with q0 = -g and the Gram matrices
+// SY[a][b] = s_a.y_b, YY[a][b] = y_a.y_b of the stored pairs,
+//     alpha_i = rho_i (s_i.q0 - sum_{j > i} alpha_j SY[i][j])                                             (first loop, newest to oldest)
+//     beta_i  = rho_i (gamma (y_i.q0 - sum_j alpha_j YY[i][j]) + sum_{j < i} (alpha_j - beta_j) SY[j][i])  (second loop)
+//     d       = gamma q0 - sum_j gamma alpha_j y_j + sum_j (alpha_j - beta_j) s_j,   gamma = ys / yy of the newest pair
+//     g.d     = -(gamma |g|^2 - gamma sum_j alpha_j (y_j.q0) + sum_j (alpha_j - beta_j) (s_j.q0))
+// The Gram entries of old pairs never change; an iteration adds the row and column of the new pair. So: one pass computes the
+// 5 (bound) + 5 dot products that involve g or the new pair, one reduction (one exchange between GPUs), the scalars are
+// evaluated by every block, one pass writes d, the saves and the first trial point. Same mathematics as
+// HLBFGS_UPDATE_First_Step / Hessian / Second_Step (HLBFGS.cpp:90-196); the rounding differs from the level-by-level
+// evaluation the way a different summation order does.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LBFGS_DIR_THREADS)
+lbfgs_direction_gram_kernel(const __grid_constant__ LbfgsDirArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm_w[LBFGS_GRAM_MAXK][LBFGS_DIR_THREADS / 32];
+    __shared__ double sm_tot[LBFGS_GRAM_MAXK];
+    __shared__ double sm_ga[LBFGS_GRAM_MAXM], sm_c[LBFGS_GRAM_MAXM], sm_misc[2];
+    const u32 N = a.N;
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    LbfgsScalars* sc = a.sc;
+    const int bound = a.bound;                       // levels 0 .. bound, oldest to newest; level bound is the new pair
+    const int K = 5 + 5 * bound;
+    double* s_cur = a.s + (size_t)a.cur_pos * N;
+    double* y_cur = a.y + (size_t)a.cur_pos * N;
+    // pass A: the new pair and every dot product that involves it or g
+    double acc[LBFGS_GRAM_MAXK];
+#pragma unroll
+    for (int j = 0; j < LBFGS_GRAM_MAXK; ++j) acc[j] = 0.0;
+    for (u32 i = tid; i < N; i += nth) {
+        const double gi = a.g[i];
+        const double si = a.x[i] - a.px[i], yi = gi - a.pg[i];
+        s_cur[i] = si; y_cur[i] = yi;
+        const double q0 = -gi;
+        acc[0] += yi * si; acc[1] += yi * yi; acc[2] += gi * gi; acc[3] += si * q0; acc[4] += yi * q0;
+#pragma unroll
+        for (int j = 0; j < LBFGS_GRAM_MAXM - 1; ++j) {
+            if (j < bound) {
+                const double sj = a.s[(size_t)a.st1[j] * N + i], yj = a.y[(size_t)a.st1[j] * N + i];
+                acc[5 + 5 * j] += sj * q0; acc[6 + 5 * j] += yj * q0;
+                acc[7 + 5 * j] += si * yj; acc[8 + 5 * j] += sj * yi; acc[9 + 5 * j] += yi * yj;
+            }
+        }
+    }
+    // block sums (fixed tree), one partial per block and value
+#pragma unroll
+    for (int j = 0; j < LBFGS_GRAM_MAXK; ++j) {
+        if (j < K) {
+            const double r = warp_sum(acc[j]);
+            if (lane == 0) sm_w[j][w] = r;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        double r = 0.0;
+        for (int i = 0; i < LBFGS_DIR_THREADS / 32; ++i) r += sm_w[threadIdx.x][i];
+        a.partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = r;
+    }
+    __threadfence();
+    grid.sync();
+    // block j adds the partials of value j in a fixed order
+    double* totals = a.partials + (size_t)LBFGS_GRAM_MAXK * gridDim.x;
+    if ((int)blockIdx.x < K) {
+        double p = 0.0;
+        for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) p += __ldcg(a.partials + (size_t)blockIdx.x * gridDim.x + b);
+        const double r = block_sum(p, &sm_w[0][0]);
+        if (threadIdx.x == 0) { totals[blockIdx.x] = r; __threadfence(); }
+    }
+    grid.sync();
+    if (a.pc.nranks > 1) {
+        // the local totals become global ones: one exchange with the peers for all of them
+        if (blockIdx.x == 0 && w == 0) {
+            peer_allreduce_n(a.pc, totals, K, totals);
+            __threadfence();
+        }
+        grid.sync();
+    }
+    if ((int)threadIdx.x < K) sm_tot[threadIdx.x] = __ldcg(totals + threadIdx.x);
+    __syncthreads();
+    // scalars, by every block
+    if (threadIdx.x == 0) {
+        const double ys = sm_tot[0], yy = sm_tot[1], gg = sm_tot[2];
+        const int cur = a.cur_pos;
+        double SY[LBFGS_GRAM_MAXM][LBFGS_GRAM_MAXM], YY[LBFGS_GRAM_MAXM][LBFGS_GRAM_MAXM];   // by level
+        double u[LBFGS_GRAM_MAXM], wq[LBFGS_GRAM_MAXM], rho[LBFGS_GRAM_MAXM], alpha[LBFGS_GRAM_MAXM], beta[LBFGS_GRAM_MAXM];
+        for (int i = 0; i < bound; ++i) {
+            for (int j = 0; j < bound; ++j) { SY[i][j] = sc->SY[a.st1[i]][a.st1[j]]; YY[i][j] = sc->YY[a.st1[i]][a.st1[j]]; }
+            u[i] = sm_tot[5 + 5 * i]; wq[i] = sm_tot[6 + 5 * i];
+            SY[bound][i] = sm_tot[7 + 5 * i]; SY[i][bound] = sm_tot[8 + 5 * i];
+            YY[bound][i] = sm_tot[9 + 5 * i]; YY[i][bound] = sm_tot[9 + 5 * i];
+            rho[i] = sc->rho[a.st1[i]];
+        }
+        SY[bound][bound] = ys; YY[bound][bound] = yy; u[bound] = sm_tot[3]; wq[bound] = sm_tot[4]; rho[bound] = 1.0 / ys;
+        for (int i = bound; i >= 0; --i) {
+            double t = u[i];
+            for (int j = bound; j > i; --j) t -= alpha[j] * SY[i][j];
+            alpha[i] = rho[i] * t;
+        }
+        const double gamma = ys / yy;
+        double dotq = gamma * gg;                    // q0 . d, term by term
+        for (int i = 0; i <= bound; ++i) {
+            double t = wq[i];
+            for (int j = bound; j >= 0; --j) t -= alpha[j] * YY[i][j];
+            t *= gamma;
+            for (int j = 0; j < i; ++j) t += (alpha[j] - beta[j]) * SY[j][i];
+            beta[i] = rho[i] * t;
+        }
+        for (int i = 0; i <= bound; ++i) {
+            sm_ga[i] = gamma * alpha[i]; sm_c[i] = alpha[i] - beta[i];
+            dotq -= sm_ga[i] * wq[i]; dotq += sm_c[i] * u[i];
+        }
+        sm_misc[0] = gamma; sm_misc[1] = -dotq;      // g . d
+        if (blockIdx.x == 0) {
+            // the new pair's row and column stay for the next iterations; start of MCSRCH (LineSearch.cpp:60-100)
+            for (int i = 0; i < bound; ++i) {
+                sc->SY[cur][a.st1[i]] = SY[bound][i]; sc->SY[a.st1[i]][cur] = SY[i][bound];
+                sc->YY[cur][a.st1[i]] = YY[bound][i]; sc->YY[a.st1[i]][cur] = YY[i][bound];
+            }
+            sc->SY[cur][cur] = ys; sc->YY[cur][cur] = yy;
+            sc->rho[cur] = 1.0 / ys;
+            sc->stp = 1.0; sc->dot = -dotq;
+            sc->info = 0;
+            mcsrch_dev(sc, a.N_global);
+        }
+    }
+    __syncthreads();
+    // pass B: the direction, the saves (HLBFGS.cpp:502-503, LineSearch.cpp:84) and the first trial point x = wa + stp d.
+    // The search starts (info = -1, stp = 1) exactly when g.d < 0 (mcsrch_dev, start branch)
+    const double gamma = sm_misc[0];
+    const bool started = sm_misc[1] < 0.0 && a.N_global != 0;
+    for (u32 k = tid; k < N; k += nth) {
+        const double gk = a.g[k], xk = a.x[k];
+        double d = gamma * (-gk);
+#pragma unroll
+        for (int j = 0; j < LBFGS_GRAM_MAXM; ++j) {
+            if (j <= bound) {
+                d -= sm_ga[j] * a.y[(size_t)a.st1[j] * N + k];
+                d += sm_c[j] * a.s[(size_t)a.st1[j] * N + k];
+            }
+        }
+        a.q[k] = d; a.px[k] = xk; a.pg[k] = gk; a.wa[k] = xk;
+        if (started) { double t = xk; t += 1.0 * d; a.x[k] = t; }
     }
 }
 

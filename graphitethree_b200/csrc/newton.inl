@@ -163,10 +163,11 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (!coop) throw std::runtime_error("device does not support cooperative launches");
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_direction_kernel, LBFGS_DIR_THREADS, 0));
+        { int per_sm2 = 0; CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, lbfgs_direction_gram_kernel, LBFGS_DIR_THREADS, 0)); per_sm = std::min(per_sm, per_sm2); }
         if (per_sm < 1) throw std::runtime_error("lbfgs_direction_kernel does not fit on an SM");
         h->lb_dir_blocks = (u32)h->num_sms * (u32)std::min(per_sm, LBFGS_DIR_BLOCKS_PER_SM);
     }
-    h->lb_part.ensure(std::max<size_t>(6 * (size_t)h->lb_dir_blocks, 4 * (size_t)LBFGS_POST_BLOCKS)); h->lb_sc.ensure(1);
+    h->lb_part.ensure(std::max<size_t>((LBFGS_GRAM_MAXK + 1) * (size_t)h->lb_dir_blocks + LBFGS_GRAM_MAXK, 4 * (size_t)LBFGS_POST_BLOCKS)); h->lb_sc.ensure(1);
     CUDA_CHECK(cudaMemsetAsync(h->lb_sc.p, 0, sizeof(LbfgsScalars), h->stream));
     double* x = h->x.p + xoff; double* g = h->lb_g.p; double* q = h->lb_q.p;
     LbfgsScalars* sc = h->lb_sc.p;
@@ -200,13 +201,19 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         da.x = x; da.g = g; da.q = q; da.px = h->lb_px.p; da.pg = h->lb_pg.p; da.wa = h->lb_wa.p;
         da.s = h->lb_s.p; da.y = h->lb_y.p; da.sc = sc; da.partials = h->lb_part.p;
         da.pc = pc; da.N_global = N_global;
+        if (!h->evl[0]) for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&h->evl[i]));
+        CUDA_CHECK(cudaEventRecord(h->evl[0], h->stream));
         {
             void* kargs[] = {(void*)&da};
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lbfgs_direction_kernel, dim3(h->lb_dir_blocks), dim3(LBFGS_DIR_THREADS),
-                                                   kargs, 0, h->stream));
+            // with a history of at most LBFGS_GRAM_MAXM pairs: all dot products in one reduction (B200CVT_LBFGS_GRAM=0: level by level)
+            const bool gram = h->use_lbfgs_gram && da.bound >= 0 && M <= LBFGS_GRAM_MAXM && h->lb_dir_blocks >= (u32)LBFGS_GRAM_MAXK;
+            CUDA_CHECK(cudaLaunchCooperativeKernel(gram ? (const void*)lbfgs_direction_gram_kernel : (const void*)lbfgs_direction_kernel,
+                                                   dim3(h->lb_dir_blocks), dim3(LBFGS_DIR_THREADS), kargs, 0, h->stream));
             h->launches++;
         }
         if (sharded) newton_gather_seeds(h);          // the first trial point (written by the direction kernel)
+        CUDA_CHECK(cudaEventRecord(h->evl[1], h->stream));
+        h->evl_used = true;
         if (iter > 0 && M > 0) cur_pos = (cur_pos + 1) % M;
         // MCSRCH (LineSearch.cpp:100-230): the direction kernel has moved x to the first trial point, unless the search
         // could not start (info != -1; rare: the evaluation below is then wasted and not counted)

@@ -234,7 +234,8 @@ int b200cvt_get_timings(b200cvt_handle h, float* ms_out /* 6 entries */);
 int b200cvt_set_stream(b200cvt_handle h, void* stream);
 /* Cumulative device time per phase over all evaluations since the last reset, milliseconds (CUDA events on the
  * handle's stream): [0] sort+grid, [1] kNN + bisector table, [2] candidate pairs, [3] clip phase (compaction, class
- * sort, clip kernel, per-seed reduce, enlarged re-clips), [4] the clip kernel alone, [5] volumetric handles: the cell stage (vcell_kernel and its enlarged passes), included in [3]. */
+ * sort, clip kernel, per-seed reduce, enlarged re-clips), [4] the clip kernel alone, [5] volumetric handles: the cell stage (vcell_kernel and its enlarged passes), included in [3]; surface handles:
+ * the L-BFGS direction kernel and the push of the trial point to the peers (once per Newton iteration, outside the phases). */
 int b200cvt_get_cumulative(b200cvt_handle h, double* ms_out /* 6 */, uint64_t* evals_out, int reset);
 /* Roofline denominators measured on the device: non-tensor FP32 and FP64 FMA
  * throughput (TFLOP/s) and a STREAM-style copy (GB/s, read+write). Any pointer may be NULL. */

@@ -9,7 +9,7 @@ python - <<PY
 import json
 d = json.loads(open("gpurun_out/${TAG}_bench_n$N.json.log").read().strip().splitlines()[-1])
 print("N=$N value %.1f M  ms/step %.2f  e2e %.1f M  evals %s" % (d["value"]/1e6, d["ms_per_step"], d["e2e"]["value"]/1e6, d["run"]["evaluations_per_step"]))
-print("  phases", {k: round(v, 4) for k, v in d.get("phase_ms_per_evaluation", {}).items()}, " per-eval total %.3f" % (d["ms_per_step"]/d["run"]["evaluations_per_step"]))
+print("  phases", {k: round(v, 4) for k, v in d.get("phase_ms_per_evaluation", {}).items()}, " per-eval total %.3f" % (d["ms_per_step"]/d["run"]["evaluations_per_step"]), " lbfgs direction ms/iter", round(d.get("lbfgs_direction_ms_per_iteration", 0), 4))
 if d.get("c3"): print("  c3", {k: d["c3"].get(k) for k in ("ms_per_iteration", "lloyd_iterations_per_s", "seed_iterations_per_s", "error")})
 PY
 python - <<PY
