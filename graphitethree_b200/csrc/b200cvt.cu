@@ -731,8 +731,13 @@ static void launch_clip_tet(b200cvt_ctx* h, TetClipArgs& a) {
     if (a.nseeds == 0 && !a.nseeds_dev) return;
     size_t smem = (size_t)TETC_WARPS * a.kstride * 4 * sizeof(double);
     u32 blocks = a.nseeds_dev ? 148u * 4u : div_up(a.nseeds, TETC_WARPS);
-    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_tet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(h, clip_tet_kernel, blocks, TETC_WARPS * 32, smem, a);
+    if (a.mode == 3) {
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_tet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(h, clip_tet_kernel<true>, blocks, TETC_WARPS * 32, smem, a);
+    } else {
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(clip_tet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(h, clip_tet_kernel<false>, blocks, TETC_WARPS * 32, smem, a);
+    }
 }
 
 #ifndef COMPACT_BLOCKS_PER_SM

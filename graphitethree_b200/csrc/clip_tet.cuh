@@ -24,13 +24,14 @@
 #define TETC_MAXP 40      // planes (cell faces): 4 tet faces + cutting bisectors
 #define TETC_NONE 0xffu
 
-struct TetCell {
+template <bool EMIT>
+struct TetCellT {
     double p[TETC_MAXT][3];
     uint8_t v[TETC_MAXT][3];     // plane ids
     uint8_t t[TETC_MAXT][3];     // adjacent triangles
     uint8_t next[TETC_MAXT];
     uint8_t status[TETC_MAXT];   // 0 used, 1 conflict, 2 free
-    uint8_t pn[TETC_MAXP];       // plane -> position of the neighbour in the seed's list (planes 0..3: the tet's faces)
+    uint8_t pn[EMIT ? TETC_MAXP : 1];   // RDT emission only: plane -> position of the neighbour in the seed's list
     uint8_t nt;                  // slots in use (max_t)
     uint8_t np;                  // planes
     uint8_t first_free;
@@ -40,6 +41,7 @@ struct TetCell {
 __device__ __forceinline__ int tetc_plus1(int i) { return i == 2 ? 0 : i + 1; }
 __device__ __forceinline__ int tetc_minus1(int i) { return i == 0 ? 2 : i - 1; }
 
+template <class TetCell>
 __device__ __forceinline__ int tetc_create_triangle(TetCell& C) {
     if (C.first_free == TETC_NONE) {
         if (C.nt >= TETC_MAXT) { C.overflow = true; return 0; }
@@ -53,12 +55,14 @@ __device__ __forceinline__ int tetc_create_triangle(TetCell& C) {
     return r;
 }
 
+template <class TetCell>
 __device__ __forceinline__ int tetc_find_vertex(const TetCell& C, int t, int v) {
     return (int)((C.v[t][1] == v) | ((C.v[t][2] == v) * 2));
 }
 
 // ConvexCell::clip_by_plane<3>, fast predicates. Returns false if the bisector did not touch the cell.
-__device__ __noinline__ bool tetc_clip(TetCell& C, const double* pi, const double* pj, u32 jj, unsigned long long& st_pv) {
+template <bool EMIT>
+__device__ __noinline__ bool tetc_clip(TetCellT<EMIT>& C, const double* pi, const double* pj, u32 jj, unsigned long long& st_pv) {
     // Phase I: furthest point on pj's side, then flood fill of the conflict zone (side_fast)
     int furthest = -1;
     double fd = 0.0;
@@ -77,7 +81,7 @@ __device__ __noinline__ bool tetc_clip(TetCell& C, const double* pi, const doubl
     if (!(fd < 0.0)) return false;
     if (C.np >= TETC_MAXP) { C.overflow = true; return false; }
     const int new_v = C.np++;
-    C.pn[new_v] = (uint8_t)jj;
+    if (EMIT) C.pn[new_v] = (uint8_t)jj;
     int cbegin = TETC_NONE, cend = TETC_NONE;
     uint8_t stack[TETC_MAXT];
     int sn = 0;
@@ -195,6 +199,7 @@ struct TetClipArgs {
 #ifndef TETC_MINBLK
 #define TETC_MINBLK 1
 #endif
+template <bool EMIT>
 __global__ void __launch_bounds__(TETC_WARPS * 32, TETC_MINBLK)
 clip_tet_kernel(TetClipArgs a) {
     extern __shared__ double s_dyn[];
@@ -254,7 +259,7 @@ clip_tet_kernel(TetClipArgs a) {
             const u32 pidx = base + lane;
             if (pidx >= npairs) continue;
             const u32 f = row[pidx];
-            TetCell C;
+            TetCellT<EMIT> C;
             // ConvexCell::initialize_from_mesh_tetrahedron (generic_RVD_cell.cpp:208-252)
             {
                 const double* t = a.tet + (size_t)f * 12;
@@ -287,7 +292,7 @@ clip_tet_kernel(TetClipArgs a) {
             if (t0 < 0) continue;                       // empty cell
             if (!sr_ok && nn > 0) lexh = true;          // list used up before the radius test passed
             ++st_ne;
-            if (a.mode == 3) {
+            if (EMIT) {
                 // a vertex of the piece on three bisectors is a Voronoi vertex inside this tet: its Delaunay tet, once
                 // (a cell whose list was used up is run again with a longer one: its rows come from the final pass only)
                 if (sr_ok || nn == 0 || nn + 1 >= a.S || nn >= B200CVT_KMAX_DEV) {
