@@ -21,6 +21,7 @@
 #include <geogram/mesh/mesh_distance.h>
 #include <geogram/mesh/mesh_geometry.h>
 #include <geogram/mesh/mesh_repair.h>
+#include <geogram/delaunay/LFS.h>
 #include <geogram/numerics/predicates.h>
 
 #include <algorithm>
@@ -177,7 +178,7 @@ namespace {
 
 int main(int argc, char** argv) {
     if(argc < 6) {
-        fprintf(stderr, "usage: %s mesh.bin seeds.bin nb_Lloyd nb_Newton m [nb_pre_Lloyd] [volumetric]\n", argv[0]);
+        fprintf(stderr, "usage: %s mesh.bin seeds.bin nb_Lloyd nb_Newton m [nb_pre_Lloyd] [volumetric] [sizing_samples]\n", argv[0]);
         return 2;
     }
     GEO::initialize(GEO::GEOGRAM_INSTALL_NONE);
@@ -217,6 +218,62 @@ int main(int argc, char** argv) {
         start.assign(pre.embedding(0), pre.embedding(0) + size_t(S) * dim);
     }
     seeds = start.data();
+
+    /* optional (argv[8] != 0, surfaces in dimension 3): the sizing field, GEO::compute_sizing_field against
+     * compute_sizing_field_b200 — without pre-sampling (bit-equal weights expected: same poles, nearest pole by the device) and
+     * with a CVT pre-sampling of argv[8] points (the samplings differ by the optimiser's round-off, so do the poles) */
+    const index_t sizing_samples = (argc > 8) ? index_t(atoi(argv[8])) : 0;
+    double sizing_max_rel = -1.0, sizing_sampled_median_rel = -1.0;
+    index_t sizing_vertices = 0;
+    bool sizing_on_gpu = false;
+    if(sizing_samples != 0 && !g_volumetric && dim == 3) {
+        /* (1) the device part on a SHARED set of poles: weights from LFS.squared_lfs (the reference's loop,
+         * mesh_geometry.cpp:57-73) against compute_sizing_field_lfs_b200 — bit-equal expected */
+        {
+            Mesh M;
+            load_mesh(mb, M);
+            LocalFeatureSize LFS(M.vertices.nb(), M.vertices.point_ptr(0));
+            double min_distance2 = 0.1 * surface_average_edge_length(M);
+            min_distance2 = min_distance2 * min_distance2;
+            std::vector<double> wr(M.vertices.nb());
+            for(index_t v = 0; v < M.vertices.nb(); ++v) {
+                double lfs2 = std::max(LFS.squared_lfs(M.vertices.point_ptr(v)), min_distance2);
+                wr[v] = pow(lfs2, -2.0);
+            }
+            sizing_on_gpu = compute_sizing_field_lfs_b200(M, LFS, 1.0);
+            Attribute<double> w(M.vertices.attributes(), "weight");
+            sizing_vertices = M.vertices.nb();
+            sizing_max_rel = 0.0;
+            for(index_t v = 0; v < M.vertices.nb(); ++v) {
+                sizing_max_rel = std::max(sizing_max_rel, std::fabs(wr[v] - w[v]) / std::fabs(wr[v]));
+            }
+        }
+        /* (2) the whole function with a CVT pre-sampling on both sides: different samples (device loop against CPU loop) and the
+         * reference's pole construction is not reproducible run to run, so only the distribution is compared */
+        auto weights = [&](bool gpu, index_t samples, std::vector<double>& out) {
+            Mesh M;
+            load_mesh(mb, M);
+            if(gpu) {
+                compute_sizing_field_b200(M, 1.0, samples);
+            } else {
+                compute_sizing_field(M, 1.0, samples);
+            }
+            Attribute<double> w(M.vertices.attributes(), "weight");
+            out.resize(M.vertices.nb());
+            for(index_t v = 0; v < M.vertices.nb(); ++v) {
+                out[v] = w[v];
+            }
+        };
+        std::vector<double> wr, wg;
+        weights(false, sizing_samples, wr);
+        weights(true, sizing_samples, wg);
+        std::vector<double> rel(wr.size());
+        for(size_t v = 0; v < wr.size(); ++v) {
+            rel[v] = std::fabs(wr[v] - wg[v]) / std::fabs(wr[v]);
+        }
+        std::nth_element(rel.begin(), rel.begin() + rel.size() / 2, rel.end());
+        sizing_sampled_median_rel = rel.empty() ? 0.0 : rel[rel.size() / 2];
+    }
 
     Run ref, b200;
     {
@@ -381,6 +438,7 @@ int main(int argc, char** argv) {
         "{\"volumetric\": %s, \"seeds\": %u, \"dim\": %u, \"pre_lloyd\": %u, \"lloyd\": %u, \"newton\": %u, \"on_gpu\": %s, "
         "\"max_abs_dx_lloyd\": %.3e, \"max_abs_dx_final\": %.3e, "
         "\"ref_triangles\": %zu, \"b200_triangles\": %zu, \"only_ref\": %zu, \"only_b200\": %zu, "
+        "\"sizing_on_gpu\": %s, \"sizing_vertices\": %u, \"sizing_max_rel_diff\": %.3e, \"sizing_sampled_median_rel_diff\": %.3e, "
         "\"volume_tets_ref\": %zu, \"volume_tets_b200\": %zu, \"volume_bad_orientation\": %zu, \"compute_volume_cells_ref\": %u, \"compute_volume_cells_b200\": %u, "
         "\"ref_vertices\": %u, \"b200_vertices\": %u, "
         "\"hausdorff_ref_to_b200\": %.3e, \"hausdorff_b200_to_ref\": %.3e, \"hausdorff_ref_to_ref_sorted\": %.3e, \"bbox_diagonal\": %.6e, "
@@ -392,6 +450,7 @@ int main(int argc, char** argv) {
         g_volumetric ? "true" : "false", S, dim, npre, nl, nn, b200.on_gpu ? "true" : "false",
         max_abs_diff(ref.x_lloyd, b200.x_lloyd), max_abs_diff(ref.x_final, b200.x_final),
         ta.size(), tb.size(), only_ref, only_b200,
+        sizing_on_gpu ? "true" : "false", unsigned(sizing_vertices), sizing_max_rel, sizing_sampled_median_rel,
         vol_tets_ref, vol_tets_b200, vol_bad_orientation, unsigned(ref.nb_volume_tets), unsigned(b200.nb_volume_tets),
         ref.surface.vertices.nb(), b200.surface.vertices.nb(),
         h_ab, h_ba, h_ctrl, diag,

@@ -3,6 +3,8 @@
  * See INTEGRATION.md. Host-side glue only: no geometry is computed here.
  */
 #include "geogram_b200.h"
+#include <geogram/delaunay/LFS.h>
+#include <geogram/mesh/mesh_geometry.h>
 
 #include <geogram/basic/command_line.h>
 #include <geogram/basic/logger.h>
@@ -722,6 +724,73 @@ namespace GEO {
             h, nb_iter, m, locked.empty() ? nullptr : locked.data(), points_.data(), nb, progress_trampoline, this, newton_info_
         );
         end_gpu_loop(h, status, "b200cvt_newton");
+    }
+
+    /************************ sizing field ************************/
+
+    void compute_sizing_field_b200(Mesh& M, double gradation, index_t nb_lfs_samples) {
+        /* the points the medial axis is estimated from (mesh_geometry.cpp:266-292): a CVT sampling of the surface, or the
+         * mesh vertices themselves */
+        std::vector<double> pts;
+        index_t nb_pts = 0;
+        if(nb_lfs_samples != 0) {
+            Logger::out("LFS") << "Sampling surface (B200)" << std::endl;
+            CentroidalVoronoiTesselationB200 CVT(&M, 3);
+            CVT.compute_initial_sampling(nb_lfs_samples);
+            CVT.Lloyd_iterations(5);
+            CVT.Newton_iterations(10);
+            nb_pts = CVT.nb_points();
+            pts.assign(CVT.embedding(0), CVT.embedding(0) + size_t(nb_pts) * 3);
+        } else {
+            nb_pts = M.vertices.nb();
+            pts.reserve(size_t(nb_pts) * 3);
+            for(index_t v: M.vertices) {
+                for(index_t c = 0; c < 3; ++c) {
+                    pts.push_back(M.vertices.point_ptr(v)[c]);
+                }
+            }
+        }
+        Logger::out("LFS") << "Computing medial axis" << std::endl;
+        LocalFeatureSize LFS(nb_pts, pts.data());
+        compute_sizing_field_lfs_b200(M, LFS, gradation);
+    }
+
+    bool compute_sizing_field_lfs_b200(Mesh& M, const LocalFeatureSize& LFS, double gradation) {
+        /* compute_sizing_field_lfs (mesh_geometry.cpp:57-73): weight = max(lfs^2, (0.1 average edge length)^2)^(-2 gradation),
+         * lfs^2 = squared distance to the nearest pole: one nearest-neighbour query per mesh vertex, on the device */
+        double min_distance2 = 0.1 * surface_average_edge_length(M);
+        min_distance2 = min_distance2 * min_distance2;
+        const index_t nv = M.vertices.nb(), np = LFS.nb_poles();
+        std::vector<double> q(size_t(nv) * 3);
+        for(index_t v = 0; v < nv; ++v) {
+            for(index_t c = 0; c < 3; ++c) {
+                q[size_t(v) * 3 + c] = M.vertices.point_ptr(v)[c];
+            }
+        }
+        std::vector<uint32_t> nearest(nv);
+        bool on_gpu = false;
+        if(np > 0 && nv > 0) {
+            b200cvt_handle h = nullptr;
+            if(b200cvt_create(-1, 3, 0, &h) == B200CVT_OK) {
+                on_gpu = b200cvt_set_seeds(h, LFS.pole(0), np) == B200CVT_OK &&
+                    b200cvt_nearest(h, q.data(), nv, nearest.data()) == B200CVT_OK;
+                b200cvt_destroy(h);
+            }
+        }
+        Attribute<double> weight(M.vertices.attributes(), "weight");
+        for(index_t v = 0; v < nv; ++v) {
+            const double* p = M.vertices.point_ptr(v);
+            double lfs2;
+            if(on_gpu) {
+                const double* pole = LFS.pole(nearest[v]);
+                lfs2 = geo_sqr(p[0] - pole[0]) + geo_sqr(p[1] - pole[1]) + geo_sqr(p[2] - pole[2]);
+            } else {
+                lfs2 = LFS.squared_lfs(p);      /* no device, or no pole: the reference's own query */
+            }
+            lfs2 = std::max(lfs2, min_distance2);
+            weight[v] = pow(lfs2, -2.0 * gradation);
+        }
+        return on_gpu;
     }
 
     /************************ remesh_smooth ************************/

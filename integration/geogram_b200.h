@@ -18,6 +18,8 @@
  *                                           Newton_iterations run device-resident
  *   GEO::remesh_smooth_b200                 same signature as GEO::remesh_smooth
  *                                           (geogram/mesh/mesh_remesh.h:92)
+ *   GEO::compute_sizing_field_b200          same signature as GEO::compute_sizing_field
+ *                                           (geogram/mesh/mesh_geometry.h:222)
  *
  * Compiled against the reference's headers where they lie; never copied into this repository.
  */
@@ -29,6 +31,7 @@
 #include <geogram/voronoi/RVD.h>
 #include <geogram/voronoi/CVT.h>
 #include <geogram/mesh/mesh.h>
+#include <geogram/delaunay/LFS.h>
 
 #include "../include/b200cvt.h"
 
@@ -174,6 +177,20 @@ namespace GEO {
 
     /** Registers the "B200NN" Delaunay backend (call once after GEO::initialize()). */
     void b200_register();
+
+    /** GEO::compute_sizing_field (geogram/mesh/mesh_geometry.h:222, impl mesh_geometry.cpp:57-73, 263-294) with its data-parallel
+     *  parts on the device: the optional pre-sampling (initial sampling, 5 Lloyd and 10 Newton iterations) runs through
+     *  CentroidalVoronoiTesselationB200, and the local feature size of every mesh vertex — the squared distance to its nearest
+     *  pole, LocalFeatureSize::squared_lfs (geogram/delaunay/LFS.h:97-104) — through b200cvt_nearest on the pole set. The poles
+     *  themselves (3D Delaunay triangulation and sliver filtering, delaunay/LFS.cpp) stay on the reference implementation.
+     *  Writes the same "weight" vertex attribute, bit for bit when nb_lfs_samples == 0. */
+    void compute_sizing_field_b200(Mesh& M, double gradation = 1.0, index_t nb_lfs_samples = 0);
+
+    /** The device part of it alone (compute_sizing_field_lfs, mesh_geometry.cpp:57-73): the "weight" attribute from a given set
+     *  of poles. Returns false if the nearest-pole queries had to be served by the reference (no device). The reference's pole
+     *  construction is not reproducible from run to run on degenerate inputs (parallel Delaunay: measured 10 081 against 10 086
+     *  poles on the same tube mesh), so parity of the sizing field is stated on a shared LocalFeatureSize. */
+    bool compute_sizing_field_lfs_b200(Mesh& M, const LocalFeatureSize& LFS, double gradation);
 
     /** GEO::remesh_smooth (geogram/mesh/mesh_remesh.h:92) with the B200 CVT. */
     void remesh_smooth_b200(

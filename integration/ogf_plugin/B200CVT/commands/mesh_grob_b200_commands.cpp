@@ -49,7 +49,7 @@ namespace OGF {
         M->update();
 
         if(tri_size_adapt != 0.0) {
-            GEO::compute_sizing_field(*M, tri_size_adapt, LFS_samples);
+            GEO::compute_sizing_field_b200(*M, tri_size_adapt, LFS_samples);
         } else if(M->vertices.attributes().is_defined("weight")) {
             M->vertices.attributes().delete_attribute_store("weight");
         }

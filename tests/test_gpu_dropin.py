@@ -32,14 +32,14 @@ def write_inputs(tmp_path, V, F, X):
     return mp, sp
 
 
-def run_check(tmp_path, V, F, X, nl, nn, m=7, pre=1, volumetric=False):
+def run_check(tmp_path, V, F, X, nl, nn, m=7, pre=1, volumetric=False, sizing_samples=0):
     """pre = stock Lloyd iterations that make the common start: on a raw random sampling the reference's own first
     iteration depends on its thread count (cells that need more than 20 neighbours, check_SR = false; measured 7e-3
     between 1, 3 and 8 threads, 5e-15 afterwards) — the flagged configurations of the parity statement."""
     if not os.path.exists(EXE):
         pytest.fail("integration/_build/dropin_check is missing: run __graft_entry__.build() where /root/reference exists")
     mp, sp = write_inputs(tmp_path, V, F, X)
-    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m), str(pre), "1" if volumetric else "0"],
+    out = subprocess.run([EXE, mp, sp, str(nl), str(nn), str(m), str(pre), "1" if volumetric else "0", str(sizing_samples)],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
@@ -71,6 +71,23 @@ def test_dropin_lloyd_newton_trefoil(tmp_path):
     assert r["only_ref"] == 0 and r["only_b200"] == 0
     tol = 1e-6 * r["bbox_diagonal"]
     assert r["hausdorff_ref_to_b200"] <= tol and r["hausdorff_b200_to_ref"] <= tol
+
+
+def test_dropin_sizing_field(tmp_path):
+    """SURVEY.md §8 f4: GEO::compute_sizing_field against compute_sizing_field_b200. The device part — the local feature size of
+    every mesh vertex = squared distance to its nearest pole, LocalFeatureSize::squared_lfs — is compared on a SHARED set of poles:
+    the "weight" attribute is bit-equal. The pole construction itself (parallel 3D Delaunay, delaunay/LFS.cpp) stays on the reference
+    and is not reproducible from run to run on degenerate inputs, so the whole function (with a CVT pre-sampling on both sides) is
+    run and its deviation reported, not asserted."""
+    V, F = shapes.noise_sphere(40)
+    X = shapes.sample_surface(V, F, 500, 3)
+    r = run_check(tmp_path, V, F, X, 1, 0, sizing_samples=3000)
+    assert r["sizing_on_gpu"] and r["sizing_vertices"] == V.shape[0]
+    assert r["sizing_max_rel_diff"] == 0.0
+    # whole function, pre-sampled on both sides: reported only. weight = lfs^-4 of an unstable quantity (the medial axis of a
+    # noisy sphere) behind a pole construction that two runs of the reference itself do not reproduce (measured: 10 081 against
+    # 10 086 poles and weights apart by a factor 5 on the same tube mesh, /tmp check during development)
+    assert r["sizing_sampled_median_rel_diff"] >= 0.0
 
 
 def test_dropin_volumetric_lloyd_newton(tmp_path):
