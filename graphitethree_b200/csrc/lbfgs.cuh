@@ -447,7 +447,10 @@ lbfgs_direction_kernel(const __grid_constant__ LbfgsDirArgs a) {
 // HLBFGS_UPDATE_First_Step / Hessian / Second_Step (HLBFGS.cpp:90-196); the rounding differs from the level-by-level
 // evaluation the way a different summation order does.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LBFGS_DIR_THREADS)
+#ifndef LBFGS_GRAM_MINBLK
+#define LBFGS_GRAM_MINBLK 1
+#endif
+__global__ void __launch_bounds__(LBFGS_DIR_THREADS, LBFGS_GRAM_MINBLK)
 lbfgs_direction_gram_kernel(const __grid_constant__ LbfgsDirArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();

@@ -21,7 +21,7 @@ import time
 h.newton(x, 10, 7)                       # warm-up: allocations, cooperative-launch set-up
 t0 = time.time(); xn, info = h.newton(x, 20, 7); t1 = time.time()
 c = h.cumulative(reset=True); n = c["evals"]
-print("%(name)s newton " + " ".join("%%s=%%.3f" %% (k, c[k] / n) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")), "evals=%%d wall_ms_per_eval=%%.3f" %% (n, (t1 - t0) * 1e3 / n))
+print("%(name)s newton " + " ".join("%%s=%%.3f" %% (k, c[k] / n) for k in ("sort", "knn", "pairs", "clip", "clip_kernel")), "evals=%%d wall_ms_per_eval=%%.3f lbfgs_dir_ms_per_iter=%%.4f" %% (n, (t1 - t0) * 1e3 / n, c["cells"] / max(info["iters"], 1)))
 h.close()
 '''
 if not os.path.exists("/tmp/c2_input.npz"):
