@@ -315,6 +315,8 @@ struct b200cvt_ctx {
     DevBuf<u32> vgrid_cells, vgrid_need, facet_list2; DevBuf<uint2> tet_gbox; VGrid vg; bool vgrid_valid = false; u32 vgrid_R = 0;
     size_t vgrid_ncell = 0; bool vneed_active = false;   // the facet walk is restricted to the tets near the cells of the tet path
     DevBuf<u32> vc_bnd, vc_redo_a, vc_redo_b, vc_n;
+    DevBuf<u32> vt_ovf, vt_redo_a, vt_redo_b, vt_n;   // cell-by-tet kernel: cells it gives up on, cells whose list was used up
+    bool use_vcell_tet = false;                       // B200CVT_VCELL_TET=1: boundary cells through vcell_tet_kernel (measured slower in Lloyd mode)
     bool use_vcell = true;
     bool use_lbfgs_gram = true;                    // B200CVT_LBFGS_GRAM=0: the level-by-level direction kernel
     DevBuf<uint4> rdtv; DevBuf<unsigned long long> rdtv_n;   // volumetric RDT rows (mode 3)
@@ -812,6 +814,8 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
     CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
     const u32 kmax = std::min<u32>(B200CVT_KMAX, S > 0 ? S - 1 : 0);
     const bool vcell = h->use_vcell && nown > 0 && mode != 2;
+    VCellArgs v;
+    memset(&v, 0, sizeof(v));
     if (vcell) {
         // cell stage: every owned seed builds its Voronoi cell once; cells inside the domain are integrated on the spot
         NvtxRange r("b200cvt:cells");
@@ -821,8 +825,6 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
         CUDA_CHECK(cudaMemsetAsync(h->vc_n.p, 0, 4 * sizeof(u32), h->stream));
         CUDA_CHECK(cudaEventRecord(h->evc[0], h->stream));
         CUDA_CHECK(cudaMemsetAsync(h->vgrid_need.p, 0, sizeof(u32) * (h->vgrid_ncell / 32 + 2), h->stream));
-        VCellArgs v;
-        memset(&v, 0, sizeof(v));
         v.xs = h->xs.p; v.nbr = h->nbr.p; v.nbr_n = h->nbr_n.p; v.kstride = h->kstride; v.nbr_by_slot = 0;
         v.seed_list = nullptr; v.nseeds = nown; v.qbegin = h->qbegin();
         v.mode = mode; v.check_SR = check_SR; v.S = S;
@@ -903,6 +905,48 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
     c.stats = h->want_stats ? h->stats.p : nullptr;
     c.tets = h->rdtv.p; c.tet_n = h->rdtv_n.p; c.tet_cap = h->rdtv.cap;
     CUDA_CHECK(cudaEventRecord(h->evk[0], h->stream));
+    if (vcell && h->use_vcell_tet && mode != 3) {
+        // the cells of the tet path, cooperatively: the cell is built once and clipped by the four planes of every candidate tet
+        h->vt_ovf.ensure(S); h->vt_redo_a.ensure(S); h->vt_redo_b.ensure(S); h->vt_n.ensure(4);
+        CUDA_CHECK(cudaMemsetAsync(h->vt_n.p, 0, 4 * sizeof(u32), h->stream));
+        VCellTetArgs t;
+        memset(&t, 0, sizeof(t));
+        t.c = v;
+        t.c.nbr = h->nbr.p; t.c.nbr_n = h->nbr_n.p; t.c.kstride = h->kstride; t.c.nbr_by_slot = 0;
+        t.c.seed_list = h->vc_bnd.p; t.c.nseeds = 0; t.c.nseeds_dev = h->vc_n.p + 2;
+        t.c.redo_list = check_SR ? h->vt_redo_a.p : nullptr; t.c.redo_n = h->vt_n.p;
+        t.tet = h->tri.p; t.tet_inner = h->tet_inner.p;
+        t.pair_cnt = h->pair_cnt.p; t.pair_facet = h->pair_facet.p; t.cap = h->pair_cap;
+        t.ovf_list = h->vt_ovf.p; t.ovf_n = h->vt_n.p + 2;
+        LAUNCH(h, vcell_tet_kernel, (u32)h->num_sms * (u32)VCT_MINBLK, VC_WARPS * 32, 0, t);
+        if (check_SR) {
+            u32 kbig = 40;
+            u32* cur_list = h->vt_redo_a.p; u32* nxt_list = h->vt_redo_b.p;
+            int cur_slot = 0;
+            for (;;) {
+                u32 nredo = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&nredo, h->vt_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                if (nredo == 0) break;
+                h->host_stats[4] += nredo;
+                kbig = std::min<u32>(kbig, kmax);
+                knn_for_list(h, cur_list, nredo, kbig);
+                const int nslot = cur_slot ^ 1;
+                CUDA_CHECK(cudaMemsetAsync(h->vt_n.p + nslot, 0, sizeof(u32), h->stream));
+                VCellTetArgs r2 = t;
+                r2.c.nbr = h->nbr_big.p; r2.c.nbr_n = h->nbr_big_n.p; r2.c.kstride = kbig; r2.c.nbr_by_slot = 1;
+                r2.c.seed_list = cur_list; r2.c.nseeds = nredo; r2.c.nseeds_dev = nullptr;
+                r2.c.redo_list = kbig >= kmax ? nullptr : nxt_list; r2.c.redo_n = h->vt_n.p + nslot;
+                LAUNCH(h, vcell_tet_kernel, std::min<u32>(div_up(nredo, VC_WARPS), (u32)h->num_sms * 2u), VC_WARPS * 32, 0, r2);
+                std::swap(cur_list, nxt_list);
+                cur_slot = nslot;
+                if (kbig >= kmax) break;
+                kbig *= 2;
+            }
+        }
+        // what is left: cells with more vertices than slots
+        c.seed_list = h->vt_ovf.p; c.nseeds = 0; c.nseeds_dev = h->vt_n.p + 2;
+    }
     launch_clip_tet(h, c);
     CUDA_CHECK(cudaEventRecord(h->evk[1], h->stream));
     if (check_SR) {
@@ -1691,6 +1735,7 @@ int b200cvt_create(int device, int dim, int volumetric, b200cvt_handle* out) {
         h->device = device; h->dim = dim; h->volumetric = volumetric;
         { const char* e = getenv("B200CVT_VCELL"); h->use_vcell = !(e && atoi(e) == 0); }
         { const char* e = getenv("B200CVT_LBFGS_GRAM"); h->use_lbfgs_gram = !(e && atoi(e) == 0); }
+        { const char* e = getenv("B200CVT_VCELL_TET"); h->use_vcell_tet = (e && atoi(e) != 0); }
         CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;

@@ -287,6 +287,15 @@ clip_tet_kernel(TetClipArgs a) {
                 if (C.overflow) break;
             }
             if (C.overflow) { lflags |= 4; continue; }
+            if (!sr_ok && nn > 0) {
+                // the list is used up: one more radius test on the FINAL piece. Every seed outside the list is at least as far as
+                // its last entry, so a piece that passes is exact although the loop never saw a farther neighbour (the reference
+                // would enlarge the list by one and stop at once, generic_RVD.h:2330-2346)
+                double R2 = 0.0;
+                for (int k = 0; k < C.nt; ++k)
+                    if (C.status[k] == 0) R2 = fmax(R2, dist2<3>(pi, C.p[k]));
+                if (nb_d[nn - 1] > 4.1 * R2) sr_ok = true;
+            }
             int t0 = -1;
             for (int k = 0; k < C.nt; ++k) if (C.status[k] == 0) { t0 = k; break; }
             if (t0 < 0) continue;                       // empty cell

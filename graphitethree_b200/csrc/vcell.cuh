@@ -202,28 +202,38 @@ __device__ __forceinline__ double vc_radius2(const double (*P)[VC_SLOTS], const 
     return vc_warp_max_nonneg(r);
 }
 
-// ConvexCell::clip_by_plane with the bisector of (pi, pj), the whole warp on one cell. Returns true if the plane cut.
+// ConvexCell::clip_by_plane, the whole warp on one cell. Returns true if the plane cut.
+// PLANE = false: the bisector of (pi, pj = (ex, ey, ez)); id = position of pj in the seed's neighbour list; the plane gets the next id.
+// PLANE = true : the half-space ex x + ey y + ez z + ew >= 0 (a face of a tetrahedron); id = the plane id it gets.
+template <bool PLANE>
 __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4* T, u32* B, unsigned short* IT, unsigned char* FS, unsigned char* PLN, VcState& st,
-                                        double pix, double piy, double piz, double pjx, double pjy, double pjz, u32 jj, int lane) {
+                                        double pix, double piy, double piz, double ex, double ey, double ez, double ew, u32 id, int lane) {
+    const double pjx = ex, pjy = ey, pjz = ez;
     const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
     double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0, rA = 0.0, rB = 0.0;
     if (uA) {
         ax = P[0][lane]; ay = P[1][lane]; az = P[2][lane];
-        rA += (pjx - ax) * (pjx - ax); rA -= (pix - ax) * (pix - ax);
-        rA += (pjy - ay) * (pjy - ay); rA -= (piy - ay) * (piy - ay);
-        rA += (pjz - az) * (pjz - az); rA -= (piz - az) * (piz - az);
+        if (PLANE) { rA += ax * ex; rA += ay * ey; rA += az * ez; rA += ew; }
+        else {
+            rA += (pjx - ax) * (pjx - ax); rA -= (pix - ax) * (pix - ax);
+            rA += (pjy - ay) * (pjy - ay); rA -= (piy - ay) * (piy - ay);
+            rA += (pjz - az) * (pjz - az); rA -= (piz - az) * (piz - az);
+        }
     }
     if (uB) {
         bx = P[0][lane + 32]; by = P[1][lane + 32]; bz = P[2][lane + 32];
-        rB += (pjx - bx) * (pjx - bx); rB -= (pix - bx) * (pix - bx);
-        rB += (pjy - by) * (pjy - by); rB -= (piy - by) * (piy - by);
-        rB += (pjz - bz) * (pjz - bz); rB -= (piz - bz) * (piz - bz);
+        if (PLANE) { rB += bx * ex; rB += by * ey; rB += bz * ez; rB += ew; }
+        else {
+            rB += (pjx - bx) * (pjx - bx); rB -= (pix - bx) * (pix - bx);
+            rB += (pjy - by) * (pjy - by); rB -= (piy - by) * (piy - by);
+            rB += (pjz - bz) * (pjz - bz); rB -= (piz - bz) * (piz - bz);
+        }
     }
     const bool cA = uA && rA < 0.0, cB = uB && rB < 0.0;
     const u32 c0lo = __ballot_sync(B200_FULL, cA);
     const u32 c0hi = st.used_hi ? __ballot_sync(B200_FULL, cB) : 0u;
     if ((c0lo | c0hi) == 0u) return false;
-    if (st.np >= 255u) { st.overflow = true; return false; }
+    if (!PLANE && st.np >= 250u) { st.overflow = true; return false; }     // ids 250 .. 253 are the faces of a tetrahedron
     const uchar4 tA = uA ? T[lane] : make_uchar4(0, 0, 0, 0);
     const uchar4 tB = uB ? T[lane + 32] : make_uchar4(0, 0, 0, 0);
     // conflict zone = the connected part of the negative vertices that holds the furthest one (flood fill)
@@ -253,8 +263,8 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
             khi = bslot < 32u ? 0u : (1u << (bslot - 32u));
         }
     }
-    const u32 new_v = st.np++;
-    if (lane == 0) PLN[new_v] = (unsigned char)jj;      // which neighbour of the list the plane is the bisector of
+    const u32 new_v = PLANE ? id : st.np++;
+    if (!PLANE && lane == 0) PLN[new_v] = (unsigned char)id;      // which neighbour of the list the plane is the bisector of
     const bool zA = (klo >> lane) & 1u, zB = (khi >> lane) & 1u;
     u32 eA = 0u, eB = 0u;       // bit e: edge e of the zone vertex leads to a kept vertex
     if (zA) eA = (vc_in(klo, khi, tA.x) ? 0u : 1u) | (vc_in(klo, khi, tA.y) ? 0u : 2u) | (vc_in(klo, khi, tA.z) ? 0u : 4u);
@@ -294,10 +304,13 @@ __device__ __forceinline__ bool vc_clip(double (*P)[VC_SLOTS], uchar4* V, uchar4
     const bool mine = (u32)lane < total;
     if (mine) {
         // bisector (ConvexCell::clip_by_plane / intersect_geom): n = pi - pj, d = -(n . (pi + pj)) / 2
-        const double nx = pix - pjx, ny = piy - pjy, nz = piz - pjz;
-        double dd = 0.0;
-        dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
-        dd = 0.5 * dd;
+        double nx = ex, ny = ey, nz = ez, dd = ew;
+        if (!PLANE) {
+            nx = pix - pjx; ny = piy - pjy; nz = piz - pjz;
+            dd = 0.0;
+            dd -= nx * (pjx + pix); dd -= ny * (pjy + piy); dd -= nz * (pjz + piz);
+            dd = 0.5 * dd;
+        }
         const u32 it = IT[lane];
         const u32 t = it & 0xffu, e = it >> 8;
         N = FS[lane];
@@ -352,6 +365,73 @@ __device__ __forceinline__ double vc_tet_volume(double ax, double ay, double az,
     const double y = V2 * W0 - V0 * W2;
     const double z = V0 * W1 - V1 * W0;
     return fabs((U0 * x + U1 * y + U2 * z) / 6.0);
+}
+
+// Integration of one cell (per-lane partial sums are ADDED to acc_*; the caller reduces over the warp). Every face (plane id) is
+// fanned from its lowest-numbered vertex; one fan triangle per (vertex, face) corner, all corners in parallel.
+// inner: bit lf set = plane 250 + lf is a face shared with another tetrahedron (skipped by the func/grad action, visit_inner_tets = false).
+__device__ __forceinline__ void vc_integrate(double (*P)[VC_SLOTS], const uchar4* V, const uchar4* T, u32* B, const VcState& st,
+                                             double pix, double piy, double piz, int mode, u32 inner, int lane,
+                                             double& acc_s, double& acc_x, double& acc_y, double& acc_z) {
+    const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
+    double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+    uchar4 vA = make_uchar4(0, 0, 0, 0), vB = vA, tA = vA, tB = vA;
+    if (uA) { ax = P[0][lane]; ay = P[1][lane]; az = P[2][lane]; vA = V[lane]; tA = T[lane]; }
+    if (uB) { bx = P[0][lane + 32]; by = P[1][lane + 32]; bz = P[2][lane + 32]; vB = V[lane + 32]; tB = T[lane + 32]; }
+    for (u32 i = lane; i < 256u; i += 32) B[i] = 0xffffffffu;
+    __syncwarp();
+    if (uA) { atomicMin(&B[vA.x], (u32)lane); atomicMin(&B[vA.y], (u32)lane); atomicMin(&B[vA.z], (u32)lane); }
+    if (uB) { atomicMin(&B[vB.x], (u32)lane + 32u); atomicMin(&B[vB.y], (u32)lane + 32u); atomicMin(&B[vB.z], (u32)lane + 32u); }
+    __syncwarp();
+    const u32 t0 = st.used_lo ? (u32)__ffs((int)st.used_lo) - 1u : 32u + (u32)__ffs((int)st.used_hi) - 1u;
+    const double q0x = P[0][t0], q0y = P[1][t0], q0z = P[2][t0];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (!(half ? uB : uA)) continue;
+        const u32 t = half ? (u32)lane + 32u : (u32)lane;
+        const uchar4 vt = half ? vB : vA, tt = half ? tB : tA;
+        const double px = half ? bx : ax, py = half ? by : ay, pz = half ? bz : az;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const u32 cv = i == 0 ? vt.x : (i == 1 ? vt.y : vt.z);
+            const u32 nx = i == 0 ? tt.y : (i == 1 ? tt.z : tt.x);       // next vertex around the face (move_to_next_around_vertex)
+            const u32 A = B[cv];
+            if (t == A || nx == A) continue;
+            const double Ax = P[0][A], Ay = P[1][A], Az = P[2][A];
+            const double Nx = P[0][nx], Ny = P[1][nx], Nz = P[2][nx];
+            if (mode == 0) {
+                // ComputeCentroidsVolumetric over TetrahedronAction (generic_RVD.h:901-978, RVD.cpp:428-497): tets from the cell's first vertex
+                if (A == t0) continue;
+                const double m = vc_tet_volume(q0x, q0y, q0z, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
+                const double sc = m / 4.0;
+                acc_s += m;
+                acc_x += sc * (q0x + Ax + px + Nx); acc_y += sc * (q0y + Ay + py + Ny); acc_z += sc * (q0z + Az + pz + Nz);
+            } else {
+                // ComputeCVTFuncGradVolumetric (RVD.cpp:791-876): pyramid of the face triangle with apex p_i
+                if (cv >= 250u && ((inner >> (cv - 250u)) & 1u)) continue;
+                const double mi = vc_tet_volume(pix, piy, piz, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
+                double fi = 0.0;
+                {
+                    const double Uc = Ax - pix, Vc = px - pix, Wc = Nx - pix;
+                    fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                }
+                {
+                    const double Uc = Ay - piy, Vc = py - piy, Wc = Ny - piy;
+                    fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                }
+                {
+                    const double Uc = Az - piz, Vc = pz - piz, Wc = Nz - piz;
+                    fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
+                }
+                fi *= (mi / 10.0);
+                acc_s += fi;
+                acc_x += 2.0 * mi * (0.75 * pix - 0.25 * Ax - 0.25 * px - 0.25 * Nx);
+                acc_y += 2.0 * mi * (0.75 * piy - 0.25 * Ay - 0.25 * py - 0.25 * Ny);
+                acc_z += 2.0 * mi * (0.75 * piz - 0.25 * Az - 0.25 * pz - 0.25 * Nz);
+            }
+        }
+    }
+    __syncwarp();
 }
 
 #ifndef VC_MINBLK
@@ -414,7 +494,7 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
                 const double dj = shfl_d(qd, (int)l);
                 if (dj > 4.1 * R2) { sr_ok = true; done = true; break; }
                 ++st_clips;
-                const bool cut = vc_clip(P, V, T, B, IT, FS, PLN, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), base + l, lane);
+                const bool cut = vc_clip<false>(P, V, T, B, IT, FS, PLN, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), 0.0, base + l, lane);
                 if (st.overflow || (st.used_lo | st.used_hi) == 0u) { done = true; break; }
                 if (cut) R2 = vc_radius2(P, st, pix, piy, piz, lane);
             }
@@ -520,63 +600,8 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
             if (eB) { const unsigned long long r = base_row + __popc(mA) + __popc(mB & ltm); if (r < a.tet_cap) a.tets[r] = rowB; }
             continue;
         }
-        // integrate. Every face (plane id) is fanned from its lowest-numbered vertex; one fan triangle per (vertex, face) corner.
-        uchar4 vA = make_uchar4(0, 0, 0, 0), vB = vA, tA = vA, tB = vA;
-        if (uA) { vA = V[lane]; tA = T[lane]; }
-        if (uB) { vB = V[lane + 32]; tB = T[lane + 32]; }
-        for (u32 i = lane; i < st.np; i += 32) B[i] = 0xffffffffu;
-        __syncwarp();
-        if (uA) { atomicMin(&B[vA.x], (u32)lane); atomicMin(&B[vA.y], (u32)lane); atomicMin(&B[vA.z], (u32)lane); }
-        if (uB) { atomicMin(&B[vB.x], (u32)lane + 32u); atomicMin(&B[vB.y], (u32)lane + 32u); atomicMin(&B[vB.z], (u32)lane + 32u); }
-        __syncwarp();
-        const u32 t0 = st.used_lo ? (u32)__ffs((int)st.used_lo) - 1u : 32u + (u32)__ffs((int)st.used_hi) - 1u;
-        const double q0x = P[0][t0], q0y = P[1][t0], q0z = P[2][t0];
         double acc_s = 0.0, acc_x = 0.0, acc_y = 0.0, acc_z = 0.0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (!(half ? uB : uA)) continue;
-            const u32 t = half ? (u32)lane + 32u : (u32)lane;
-            const uchar4 vt = half ? vB : vA, tt = half ? tB : tA;
-            const double px = half ? bx : ax, py = half ? by : ay, pz = half ? bz : az;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const u32 cv = i == 0 ? vt.x : (i == 1 ? vt.y : vt.z);
-                const u32 nx = i == 0 ? tt.y : (i == 1 ? tt.z : tt.x);       // next vertex around the face (move_to_next_around_vertex)
-                const u32 A = B[cv];
-                if (t == A || nx == A) continue;
-                const double Ax = P[0][A], Ay = P[1][A], Az = P[2][A];
-                const double Nx = P[0][nx], Ny = P[1][nx], Nz = P[2][nx];
-                if (a.mode == 0) {
-                    // ComputeCentroidsVolumetric over TetrahedronAction (generic_RVD.h:901-978, RVD.cpp:428-497): tets from the cell's first vertex
-                    if (A == t0) continue;
-                    const double m = vc_tet_volume(q0x, q0y, q0z, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
-                    const double sc = m / 4.0;
-                    acc_s += m;
-                    acc_x += sc * (q0x + Ax + px + Nx); acc_y += sc * (q0y + Ay + py + Ny); acc_z += sc * (q0z + Az + pz + Nz);
-                } else {
-                    // ComputeCVTFuncGradVolumetric (RVD.cpp:791-876): pyramid of the face triangle with apex p_i
-                    const double mi = vc_tet_volume(pix, piy, piz, Ax, Ay, Az, px, py, pz, Nx, Ny, Nz);
-                    double fi = 0.0;
-                    {
-                        const double Uc = Ax - pix, Vc = px - pix, Wc = Nx - pix;
-                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
-                    }
-                    {
-                        const double Uc = Ay - piy, Vc = py - piy, Wc = Ny - piy;
-                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
-                    }
-                    {
-                        const double Uc = Az - piz, Vc = pz - piz, Wc = Nz - piz;
-                        fi += Uc * Uc + Vc * Vc + Wc * Wc; fi += (Uc * Vc + Vc * Wc + Wc * Uc);
-                    }
-                    fi *= (mi / 10.0);
-                    acc_s += fi;
-                    acc_x += 2.0 * mi * (0.75 * pix - 0.25 * Ax - 0.25 * px - 0.25 * Nx);
-                    acc_y += 2.0 * mi * (0.75 * piy - 0.25 * Ay - 0.25 * py - 0.25 * Ny);
-                    acc_z += 2.0 * mi * (0.75 * piz - 0.25 * Az - 0.25 * pz - 0.25 * Nz);
-                }
-            }
-        }
+        vc_integrate(P, V, T, B, st, pix, piy, piz, a.mode, 0u, lane, acc_s, acc_x, acc_y, acc_z);
         acc_s = warp_sum(acc_s); acc_x = warp_sum(acc_x); acc_y = warp_sum(acc_y); acc_z = warp_sum(acc_z);
         if (lane == 0) {
             a.out_s[s] = acc_s;
@@ -594,5 +619,223 @@ __global__ void __launch_bounds__(VC_WARPS * 32, VC_MINBLK) vcell_kernel(VCellAr
         if (st_cells) atomicAdd(&a.stats[9], st_cells);
         if (st_bnd) atomicAdd(&a.stats[10], st_bnd);
         if (st_clips) atomicAdd(&a.stats[12], st_clips);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The cells that may reach the domain boundary: cell ∩ tet for every candidate tet, cooperatively.
+// The (tet, seed) kernel of clip_tet.cuh starts from the tet and applies up to 20 bisectors to a 4..10-vertex piece, one piece
+// per lane (7.9 of 32 lanes). Here the warp builds the seed's cell once (as vcell_kernel), then, tet by tet, clips a COPY of
+// the cell by the four face planes of the tet (vc_clip<true>) and integrates the piece — the same set tet ∩ cell(i), summed over
+// the candidate tets in ascending id. A piece is exact when the last neighbour of the list is farther than 2.02 R_piece (then
+// no seed outside the list can cut it): otherwise the cell is flagged (Lloyd mode) or run again with a longer list (check_SR),
+// exactly the two outcomes of clip_by_cell_SR (generic_RVD.h:2295-2346). Cells that overflow the slots go to clip_tet_kernel.
+// ---------------------------------------------------------------------------------------
+struct VCellTetArgs {
+    VCellArgs c;                       // seed_list = the cells of the tet path; redo_list: list used up (check_SR); bnd_list unused
+    const double* tet; const uint8_t* tet_inner;
+    const u32* pair_cnt; u32* pair_facet; u32 cap;
+    u32* ovf_list; u32* ovf_n;         // cells this kernel gives up on
+};
+
+__device__ __forceinline__ double vc_warp_min_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(B200_FULL, v, m));
+    return v;
+}
+__device__ __forceinline__ double vc_warp_max_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(B200_FULL, v, m));
+    return v;
+}
+
+#ifndef VCT_MINBLK
+#define VCT_MINBLK 2
+#endif
+__global__ void __launch_bounds__(VC_WARPS * 32, VCT_MINBLK) vcell_tet_kernel(VCellTetArgs ta) {
+    const VCellArgs& a = ta.c;
+    __shared__ double sP[VC_WARPS][3][VC_SLOTS];
+    __shared__ uchar4 sV[VC_WARPS][VC_SLOTS];
+    __shared__ uchar4 sT[VC_WARPS][VC_SLOTS];
+    __shared__ double sP2[VC_WARPS][3][VC_SLOTS];
+    __shared__ uchar4 sV2[VC_WARPS][VC_SLOTS];
+    __shared__ uchar4 sT2[VC_WARPS][VC_SLOTS];
+    __shared__ u32 sB[VC_WARPS][256];
+    __shared__ unsigned short sIT[VC_WARPS][32];
+    __shared__ unsigned char sFS[VC_WARPS][VC_SLOTS];
+    __shared__ unsigned char sPLN[VC_WARPS][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double (*P)[VC_SLOTS] = sP[w];
+    uchar4* V = sV[w];
+    uchar4* T = sT[w];
+    double (*P2)[VC_SLOTS] = sP2[w];
+    uchar4* V2 = sV2[w];
+    uchar4* T2 = sT2[w];
+    u32* B = sB[w];
+    unsigned short* IT = sIT[w];
+    unsigned char* FS = sFS[w];
+    unsigned char* PLN = sPLN[w];
+    const SeedRec<3>* xs = (const SeedRec<3>*)a.xs;
+    const u32 nseeds = a.nseeds_dev ? *a.nseeds_dev : a.nseeds;
+    for (u32 si = blockIdx.x * VC_WARPS + w; si < nseeds; si += gridDim.x * VC_WARPS) {
+        const u32 s = a.seed_list ? a.seed_list[si] : a.qbegin + si;
+        const double pix = xs[s].p[0], piy = xs[s].p[1], piz = xs[s].p[2];
+        const size_t nrow = a.nbr_by_slot ? (size_t)si : (size_t)s;
+        const u32 nn = min(a.nbr_n[nrow], a.kstride);
+        const u32* nrowp = a.nbr + nrow * a.kstride;
+        __syncwarp();
+        if (lane < 8) {
+            const int b0 = lane & 1, b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1;
+            P[0][lane] = b0 ? a.box_hi[0] : a.box_lo[0];
+            P[1][lane] = b1 ? a.box_hi[1] : a.box_lo[1];
+            P[2][lane] = b2 ? a.box_hi[2] : a.box_lo[2];
+            uchar4 v = make_uchar4((unsigned char)b0, (unsigned char)(2 + b1), (unsigned char)(4 + b2), 0);
+            uchar4 t = make_uchar4((unsigned char)(lane ^ 1), (unsigned char)(lane ^ 2), (unsigned char)(lane ^ 4), 0);
+            if ((b0 + b1 + b2) & 1) {
+                unsigned char x = v.y; v.y = v.z; v.z = x;
+                x = t.y; t.y = t.z; t.z = x;
+            }
+            V[lane] = v; T[lane] = t;
+        }
+        __syncwarp();
+        VcState st;
+        st.used_lo = 0xffu; st.used_hi = 0u; st.np = 6u; st.overflow = false;
+        double R2 = vc_radius2(P, st, pix, piy, piz, lane);
+        double last_d = 0.0;
+        bool done = false;
+        for (u32 base = 0; base < nn && !done; base += 32) {
+            double qx = 0.0, qy = 0.0, qz = 0.0, qd = 0.0;
+            if (base + lane < nn) {
+                const SeedRec<3>* r = xs + nrowp[base + lane];
+                qx = r->p[0]; qy = r->p[1]; qz = r->p[2];
+                const double dx = qx - pix, dy = qy - piy, dz = qz - piz;
+                qd = dx * dx; qd += dy * dy; qd += dz * dz;
+            }
+            const u32 cnt = min(32u, nn - base);
+            if (base + cnt == nn) last_d = shfl_d(qd, (int)cnt - 1);
+            for (u32 l = 0; l < cnt; ++l) {
+                const double dj = shfl_d(qd, (int)l);
+                if (dj > 4.1 * R2) { done = true; break; }
+                const bool cut = vc_clip<false>(P, V, T, B, IT, FS, PLN, st, pix, piy, piz, shfl_d(qx, (int)l), shfl_d(qy, (int)l), shfl_d(qz, (int)l), 0.0, base + l, lane);
+                if (st.overflow || (st.used_lo | st.used_hi) == 0u) { done = true; break; }
+                if (cut) R2 = vc_radius2(P, st, pix, piy, piz, lane);
+            }
+        }
+        if (nn > 0 && last_d == 0.0) {
+            // the loop left before the last chunk was loaded: the distance of the last neighbour of the list
+            const SeedRec<3>* r = xs + nrowp[nn - 1];
+            const double dx = r->p[0] - pix, dy = r->p[1] - piy, dz = r->p[2] - piz;
+            last_d = dx * dx; last_d += dy * dy; last_d += dz * dz;
+        }
+        if (st.overflow) {
+            if (lane == 0) { const u32 pos = atomicAdd(ta.ovf_n, 1u); ta.ovf_list[pos] = s; }
+            continue;
+        }
+        double acc_s = 0.0, acc_x = 0.0, acc_y = 0.0, acc_z = 0.0;
+        bool any_exh = false, gave_up = false;
+        if ((st.used_lo | st.used_hi) != 0u) {
+            // bounding box of the cell: tets outside of it are skipped without a clip
+            const bool uA = (st.used_lo >> lane) & 1u, uB = (st.used_hi >> lane) & 1u;
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (uA) { lo[c] = P[c][lane]; hi[c] = P[c][lane]; }
+                if (uB) { lo[c] = fmin(lo[c], P[c][lane + 32]); hi[c] = fmax(hi[c], P[c][lane + 32]); }
+                lo[c] = vc_warp_min_d(lo[c]); hi[c] = vc_warp_max_d(hi[c]);
+            }
+            // candidate tets in ascending id (rows are filled through atomics)
+            const u32 npairs = min(ta.pair_cnt[s], ta.cap);
+            u32* row = ta.pair_facet + (size_t)s * ta.cap;
+            if (npairs > 1) {
+                u32 n2 = 32; while (n2 < npairs) n2 <<= 1;
+                n2 = min(n2, ta.cap);
+                for (u32 t = npairs + lane; t < n2; t += 32) row[t] = B200_NONE;
+                __syncwarp();
+                for (u32 k = 2; k <= n2; k <<= 1)
+                    for (u32 j = k >> 1; j > 0; j >>= 1) {
+                        for (u32 t = lane; t < n2; t += 32) {
+                            const u32 p = t ^ j;
+                            if (p > t) {
+                                const u32 vt = row[t], vp = row[p];
+                                const bool up = ((t & k) == 0);
+                                if ((vt > vp) == up) { row[t] = vp; row[p] = vt; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+            }
+            for (u32 pidx = 0; pidx < npairs && !gave_up; ++pidx) {
+                const u32 f = row[pidx];
+                const double* tp = ta.tet + (size_t)f * 12;
+                double c[4][3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) c[k][q] = __ldg(tp + k * 3 + q);
+                bool apart = false;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double tmin = fmin(fmin(c[0][q], c[1][q]), fmin(c[2][q], c[3][q]));
+                    const double tmax = fmax(fmax(c[0][q], c[1][q]), fmax(c[2][q], c[3][q]));
+                    apart = apart || tmin > hi[q] || tmax < lo[q];
+                }
+                if (apart) continue;
+                // work copy of the cell
+                __syncwarp();
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int sl = lane + 32 * h2;
+                    if (((h2 ? st.used_hi : st.used_lo) >> lane) & 1u) {
+                        P2[0][sl] = P[0][sl]; P2[1][sl] = P[1][sl]; P2[2][sl] = P[2][sl];
+                        V2[sl] = V[sl]; T2[sl] = T[sl];
+                    }
+                }
+                __syncwarp();
+                VcState s2 = st;
+                bool empty = false;
+#pragma unroll 1
+                for (int lf = 0; lf < 4 && !empty; ++lf) {
+                    const int i0 = (lf + 1) & 3, i1 = (lf + 2) & 3, i2 = (lf + 3) & 3;
+                    const double ux = c[i1][0] - c[i0][0], uy = c[i1][1] - c[i0][1], uz = c[i1][2] - c[i0][2];
+                    const double vx = c[i2][0] - c[i0][0], vy = c[i2][1] - c[i0][1], vz = c[i2][2] - c[i0][2];
+                    double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+                    double sg = 0.0;
+                    sg += nx * (c[lf][0] - c[i0][0]); sg += ny * (c[lf][1] - c[i0][1]); sg += nz * (c[lf][2] - c[i0][2]);
+                    if (sg == 0.0) { empty = true; break; }               // flat tet: no volume
+                    if (sg < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+                    double dd = 0.0;
+                    dd -= nx * c[i0][0]; dd -= ny * c[i0][1]; dd -= nz * c[i0][2];
+                    vc_clip<true>(P2, V2, T2, B, IT, FS, PLN, s2, pix, piy, piz, nx, ny, nz, dd, 250u + (u32)lf, lane);
+                    if (s2.overflow) { gave_up = true; break; }
+                    if ((s2.used_lo | s2.used_hi) == 0u) empty = true;
+                }
+                if (gave_up || empty) continue;
+                if (nn > 0) {
+                    const double R2p = vc_radius2(P2, s2, pix, piy, piz, lane);
+                    if (!(last_d > 4.1 * R2p)) any_exh = true;
+                }
+                vc_integrate(P2, V2, T2, B, s2, pix, piy, piz, a.mode, (u32)ta.tet_inner[f], lane, acc_s, acc_x, acc_y, acc_z);
+            }
+        }
+        if (gave_up) {
+            if (lane == 0) { const u32 pos = atomicAdd(ta.ovf_n, 1u); ta.ovf_list[pos] = s; }
+            continue;
+        }
+        if (any_exh && a.check_SR && nn + 1 < a.S && nn < B200CVT_KMAX_DEV && a.redo_list) {
+            if (lane == 0) { const u32 pos = atomicAdd(a.redo_n, 1u); a.redo_list[pos] = s; }
+            continue;
+        }
+        acc_s = warp_sum(acc_s); acc_x = warp_sum(acc_x); acc_y = warp_sum(acc_y); acc_z = warp_sum(acc_z);
+        if (lane == 0) {
+            a.out_s[s] = acc_s;
+            a.out_v[(size_t)s * 3 + 0] = acc_x; a.out_v[(size_t)s * 3 + 1] = acc_y; a.out_v[(size_t)s * 3 + 2] = acc_z;
+            uint8_t f8 = (uint8_t)(a.flags[s] & ~(uint8_t)(1 | 4 | 8));
+            if (any_exh) {
+                if (!a.check_SR) f8 |= 1;
+                else if (nn + 1 >= a.S) { }
+                else if (nn >= B200CVT_KMAX_DEV) f8 |= 8;
+            }
+            a.flags[s] = f8;
+        }
     }
 }

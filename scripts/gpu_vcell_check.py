@@ -8,6 +8,7 @@ from graphitethree_b200 import capi, shapes
 
 def handle(vcell, V, T):
     os.environ["B200CVT_VCELL"] = "1" if vcell else "0"
+    os.environ["B200CVT_VCELL_TET"] = os.environ.get("VCELL_TET", "1")
     h = capi.Handle(3, volumetric=True)
     h.set_mesh(V, T)
     return h
