@@ -318,6 +318,8 @@ struct b200cvt_ctx {
     DevBuf<u32> vt_ovf, vt_redo_a, vt_redo_b, vt_n;   // cell-by-tet kernel: cells it gives up on, cells whose list was used up
     bool use_vcell_tet = false;                       // B200CVT_VCELL_TET=1: boundary cells through vcell_tet_kernel (measured slower in Lloyd mode)
     bool use_vcell = true;
+    // Newton loop on one GPU: the enlargement check of an evaluation is read with the line-search record
+    bool defer_redo = false, redo_deferred = false; ClipArgs pending_clip;
     bool use_lbfgs_gram = true;                    // B200CVT_LBFGS_GRAM=0: the level-by-level direction kernel
     DevBuf<uint4> rdtv; DevBuf<unsigned long long> rdtv_n;   // volumetric RDT rows (mode 3)
     cudaEvent_t evc[2] = {nullptr, nullptr};   // around the cell stage
@@ -982,6 +984,47 @@ static void evaluate_volume(b200cvt_ctx* h, int mode, int check_SR) {
     h->ev_pending = true;
 }
 
+// enlarge_neighborhood loop (generic_RVD.h:2179-2197), batched over the seeds that need it
+template <int D>
+static void surface_redo_loop(b200cvt_ctx* h, const ClipArgs& c) {
+    const u32 S = h->S;
+    u32 kbig = 40;
+    u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
+    int cur_slot = 0;
+    for (;;) {
+        u32 nredo = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (nredo == 0) break;
+        h->host_stats[4] += nredo;
+        kbig = std::min<u32>(kbig, B200CVT_KMAX);
+        kbig = std::min<u32>(kbig, S - 1);
+        h->nbr_big.ensure((size_t)nredo * kbig);
+        h->nbr_big_n.ensure(nredo);
+        KnnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
+        a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
+        a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
+        a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
+        launch_knn<D>(h, a, nredo);
+        int nslot = cur_slot ^ 1;
+        CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
+        ClipArgs r = c;
+        r.nbr = h->nbr_big.p; r.nbr_n = h->nbr_big_n.p; r.kstride = kbig; r.nbr_by_slot = 1;
+        r.seed_list = cur_list; r.nseeds = nredo;
+        r.redo_list = nxt_list; r.redo_n = h->redo_n.p + nslot;
+        launch_clip<D>(h, r);
+        std::swap(cur_list, nxt_list);
+        cur_slot = nslot;
+        if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) {
+            // the kernel flags KMAX itself when the list cannot grow any more
+            break;
+        }
+        kbig *= 2;
+    }
+}
+
 template <int D>
 static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     if (!h->has_mesh) throw StateError("no mesh: call b200cvt_set_mesh first");
@@ -1126,42 +1169,11 @@ static void evaluate_t(b200cvt_ctx* h, int mode, int check_SR) {
     }
 
     if (check_SR) {
-        // enlarge_neighborhood loop (generic_RVD.h:2179-2197), batched over the seeds that need it
-        u32 kbig = 40;
-        u32* cur_list = h->redo_a.p; u32* nxt_list = h->redo_b.p;
-        int cur_slot = 0;
-        for (;;) {
-            u32 nredo = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&nredo, h->redo_n.p + cur_slot, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
-            CUDA_CHECK(cudaStreamSynchronize(h->stream));
-            if (nredo == 0) break;
-            h->host_stats[4] += nredo;
-            kbig = std::min<u32>(kbig, B200CVT_KMAX);
-            kbig = std::min<u32>(kbig, S - 1);
-            h->nbr_big.ensure((size_t)nredo * kbig);
-            h->nbr_big_n.ensure(nredo);
-            KnnArgs a;
-            memset(&a, 0, sizeof(a));
-            a.xs = h->xs.p; a.cell_range = h->cell_range.p; a.rank_of = h->rank_of.p;
-            a.query_list = cur_list; a.ksize = nullptr; a.out_by_slot = 1;
-            a.k = kbig; a.kstride = kbig; a.S = S; a.qbegin = 0; a.qend = nredo;
-            a.nbr = h->nbr_big.p; a.nbr_n = h->nbr_big_n.p; a.sqd = nullptr; a.flags = h->flags.p; a.g = h->g;
-            launch_knn<D>(h, a, nredo);
-            int nslot = cur_slot ^ 1;
-            CUDA_CHECK(cudaMemsetAsync(h->redo_n.p + nslot, 0, sizeof(u32), h->stream));
-            ClipArgs r = c;
-            r.nbr = h->nbr_big.p; r.nbr_n = h->nbr_big_n.p; r.kstride = kbig; r.nbr_by_slot = 1;
-            r.seed_list = cur_list; r.nseeds = nredo;
-            r.redo_list = nxt_list; r.redo_n = h->redo_n.p + nslot;
-            launch_clip<D>(h, r);
-            std::swap(cur_list, nxt_list);
-            cur_slot = nslot;
-            if (kbig >= std::min<u32>(B200CVT_KMAX, S - 1)) {
-                // the kernel flags KMAX itself when the list cannot grow any more
-                break;
-            }
-            kbig *= 2;
-        }
+        if (h->defer_redo) {
+            // Newton loop on one GPU: the count of seeds that need longer lists is read together with the line-search record
+            // (lbfgs_post_eval_kernel leaves the search untouched while it is non-zero), one host round trip less per evaluation
+            h->pending_clip = c; h->redo_deferred = true;
+        } else surface_redo_loop<D>(h, c);
     }
     CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
     h->has_results = true;

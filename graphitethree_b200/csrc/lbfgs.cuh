@@ -595,7 +595,7 @@ lbfgs_direction_gram_kernel(const __grid_constant__ LbfgsDirArgs a) {
 // Deterministic: fixed partition, per-block partials added in order by the last block.
 __global__ void __launch_bounds__(LBFGS_POST_THREADS)
 lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const double* q, const double* x,
-                       double* partials, LbfgsScalars* sc, int resume, PeerComm pc, u32 n_global) {
+                       double* partials, LbfgsScalars* sc, int resume, PeerComm pc, u32 n_global, const u32* pending) {
     __shared__ double sm[32];
     __shared__ bool last;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -642,7 +642,15 @@ lbfgs_post_eval_kernel(u32 ns, const double* fs, u32 n, const double* g, const d
         sc->dot = tot[1];
         sc->gnorm = sqrt(tot[2]);
         sc->xnorm = sqrt(tot[3]);
-        // a line search that could not start (info != -1 after the direction kernel) stays as it is
-        if (resume && sc->info == -1) mcsrch_dev(sc, n_global);
+        // *pending != 0: some seeds of this evaluation still wait for longer neighbour lists (the host reads that count with this
+        // record): the evaluation is not complete, the search is left untouched and marked (info = -2); the kernel runs again
+        // when the lists have been enlarged
+        const bool incomplete = pending && *pending != 0u;
+        if (incomplete) { if (sc->info == -1) sc->info = -2; }
+        else {
+            if (sc->info == -2) sc->info = -1;
+            // a line search that could not start (info != -1 after the direction kernel) stays as it is
+            if (resume && sc->info == -1) mcsrch_dev(sc, n_global);
+        }
     }
 }

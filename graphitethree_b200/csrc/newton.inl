@@ -20,9 +20,26 @@ static u32 lb_local_seeds(b200cvt_ctx* h) {
 }
 
 template <int D>
-static void newton_eval_t(b200cvt_ctx* h) {
+static void newton_scatter_one_gpu(b200cvt_ctx* h) {
+    LAUNCH(h, scatter_results_kernel<D>, div_up(h->S, 256), 256, 0, (const SeedRec<D>*)h->xs.p, 0u, h->S, h->out_s.p, h->out_v.p,
+           h->flags.p, h->pair_cnt.p, h->locked.p, 1, (double*)nullptr, h->lb_g.p, h->flags_orig.p, h->cnt_orig.p);
+}
+
+// the enlargement loop an evaluation left for later (evaluate_t, defer_redo), then the gradient again
+static void newton_finish_deferred(b200cvt_ctx* h) {
+    if (h->dim == 3) { surface_redo_loop<3>(h, h->pending_clip); newton_scatter_one_gpu<3>(h); }
+    else { surface_redo_loop<6>(h, h->pending_clip); newton_scatter_one_gpu<6>(h); }
+    CUDA_CHECK(cudaMemsetAsync(h->redo_n.p, 0, 4 * sizeof(u32), h->stream));
+    h->redo_deferred = false;
+}
+
+template <int D>
+static void newton_eval_t(b200cvt_ctx* h, bool defer) {
     h->grid_valid = false; h->knn_valid = false;
+    h->redo_deferred = false;
+    h->defer_redo = defer && h->nranks == 1 && !h->volumetric;
     evaluate(h, 1, 1);
+    h->defer_redo = false;
     const u32 S = h->S;
     if (h->has_comm && h->nranks > 1 && h->pb_valid) {
         // peer-memory path: every gradient row is stored into its owner's slice, then a barrier
@@ -48,8 +65,7 @@ static void newton_eval_t(b200cvt_ctx* h) {
         return;
     }
     if (h->nranks == 1) {
-        LAUNCH(h, scatter_results_kernel<D>, div_up(S, 256), 256, 0, (const SeedRec<D>*)h->xs.p, 0u, S, h->out_s.p, h->out_v.p,
-               h->flags.p, h->pair_cnt.p, h->locked.p, 1, (double*)nullptr, h->lb_g.p, h->flags_orig.p, h->cnt_orig.p);
+        newton_scatter_one_gpu<D>(h);
     } else {
         if (!h->x_slice) throw StateError("seeds are partitioned but no exchange was set (b200cvt_set_exchange)");
         pack_slice<D>(h, h->out_s.p, h->out_v.p);
@@ -59,8 +75,8 @@ static void newton_eval_t(b200cvt_ctx* h) {
                h->locked.p, 1, h->lb_g.p, h->s_orig.p);
     }
 }
-static void newton_eval(b200cvt_ctx* h) {
-    if (h->dim == 3) newton_eval_t<3>(h); else newton_eval_t<6>(h);
+static void newton_eval(b200cvt_ctx* h, bool defer = false) {
+    if (h->dim == 3) newton_eval_t<3>(h, defer); else newton_eval_t<6>(h, defer);
 }
 
 static const double* newton_fs(b200cvt_ctx* h) {
@@ -181,7 +197,7 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
     auto post_eval = [&](int resume) {
         const u32 nfs = sharded ? h->qend() - h->qbegin() : S;
         LAUNCH(h, lbfgs_post_eval_kernel, LBFGS_POST_BLOCKS, LBFGS_POST_THREADS, 0, nfs, newton_fs(h), N, g, q, x, h->lb_part.p, sc, resume,
-               pc, N_global);
+               pc, N_global, h->redo_deferred ? (const u32*)h->redo_n.p : (const u32*)nullptr);
     };
     newton_eval(h); nfev_total++;
     post_eval(0);
@@ -219,11 +235,19 @@ static void newton_loop(b200cvt_ctx* h, u32 nb_iter, u32 m, b200cvt_progress_cb 
         // could not start (info != -1; rare: the evaluation below is then wasted and not counted)
         u32 nfev_ls = 0;
         for (;;) {
-            newton_eval(h);
+            newton_eval(h, true);
             nfev_ls++;
             post_eval(1);
             CUDA_CHECK(cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
             sync_stream(h);
+            if (hs.info == -2) {
+                // some seeds needed longer neighbour lists: finish the evaluation, then the line-search decision
+                newton_finish_deferred(h);
+                post_eval(1);
+                CUDA_CHECK(cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+                sync_stream(h);
+            }
+            h->redo_deferred = false;
             ls_info = hs.info;
             if (ls_info != -1) break;
             LAUNCH(h, step_kernel, nb, 256, 0, N, sc, h->lb_wa.p, q, x);
